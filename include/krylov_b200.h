@@ -1,0 +1,201 @@
+/*
+ * krylov_b200.h -- C ABI of libkrylov_b200.so (sm_100a).
+ *
+ * The reference (ju-liu/krylov, pure Python) has no FFI; its "kernels" are the
+ * NumPy/SciPy/LAPACK call sites listed in SURVEY.md section 2.1.  Each entry
+ * point below names the reference call site(s) it replaces
+ * (paths relative to /root/reference/src/krylov/).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative KB_E* code otherwise;
+ *    kb_last_error() returns the thread-local message of the last failure.
+ *  - vectors are fp64 device pointers of logical shape (n, k), row-major,
+ *    contiguous (k right-hand sides advance in lock-step);
+ *    "slot" arguments are device arrays of k doubles (one scalar per column).
+ *  - the caller owns every vector/matrix buffer; the library owns only the
+ *    opaque handles and the reduction workspace inside kb_ws.
+ *  - every launch goes to `stream` (a cudaStream_t cast to void*), is
+ *    asynchronous and never synchronises the device.
+ *  - reductions are deterministic: block partials in a fixed order, finished
+ *    by the last-arriving block in a fixed-shape pass.
+ *  - gating: kb_ws_set_gate(ws, stop_at, tag) makes every later launch through
+ *    that workspace a no-op when *stop_at <= tag at kernel start (device-side
+ *    convergence control without a host round-trip per iteration).
+ */
+#ifndef KRYLOV_B200_H
+#define KRYLOV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_OK 0
+#define KB_EINVAL -1
+#define KB_ECUDA -2
+#define KB_ENOMEM -3
+#define KB_EUNSUPPORTED -4
+
+typedef struct kb_csr_s* kb_csr_t; /* CSR matrix view + schedule */
+typedef struct kb_ws_s* kb_ws_t;   /* reduction workspace + gate  */
+
+/* --- library ---------------------------------------------------------- */
+int kb_version(void);
+int kb_last_error(char* buf, size_t len);
+int kb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* --- workspace -------------------------------------------------------- */
+int kb_ws_create(kb_ws_t* ws, int max_k);
+int kb_ws_destroy(kb_ws_t ws);
+/* stop_at: device int (or NULL to disable); launches are skipped when *stop_at <= tag */
+int kb_ws_set_gate(kb_ws_t ws, const int* stop_at, int tag);
+
+/* --- CSR handle ------------------------------------------------------- */
+/* rowptr (n_rows+1, int32), colidx/vals (nnz) are device arrays owned by the
+ * caller.  padded != 0 promises 16-byte aligned colidx/vals with >= 4 readable
+ * elements past nnz (enables the TMA-staged kernel).  Replaces the scipy CSR
+ * object the reference multiplies with at _helpers.py:47,61. */
+int kb_csr_create(kb_csr_t* h, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                  const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                  int padded, void* stream);
+int kb_csr_destroy(kb_csr_t h);
+/* schedule: 0 = auto, 1 = row-wise generic kernel, 2 = TMA-staged stream kernel (k == 1) */
+int kb_csr_set_schedule(kb_csr_t h, int schedule);
+int kb_csr_get_info(kb_csr_t h, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
+                    int* max_row_len, int* schedule);
+
+/* --- sparse products: `A @ x` (cg.py:86,180; arnoldi.py:73,176,244;
+ *     minres.py:111,121; gmres.py:106) fused with what follows it ---------
+ * t = A x, then
+ *   mode 0: y = t
+ *   mode 1: y = t - coef[c] * z          (Lanczos: arnoldi.py:244-249)
+ *   mode 2: y = z - t                    (residual b - A x: cg.py:86)
+ * and, in the same pass,
+ *   dot 0: nothing     dot 1: out[c] = sum_i w[i,c] * y[i,c]   (cg.py:183, arnoldi.py:160,252)
+ *   dot 2: out[c] = sum_i y[i,c]^2                               (cg.py:89, gmres.py:108)
+ * x has n_cols rows; y, z, w have n_rows rows. */
+int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y,
+            int mode, const double* z, const double* coef,
+            int dot, const double* w, double* out, void* stream);
+
+/* boundary rows of a row-partitioned matrix: for i in rows[]:
+ *   y[i] += sum_j hv[j] * xh[hc[j]];  out[c] = sum_i w[i,c] * (added part)  (dot 1)
+ *   or, dot 2, out[c] = sum_i (2*y_old*h + h*h) correction is NOT used: dot 2 is unsupported here. */
+int kb_spmv_halo_add(kb_ws_t ws, int k, int64_t n_brows, const int32_t* rows,
+                     const int32_t* hrowptr, const int32_t* hcol, const double* hval,
+                     const double* xh, double* y, int dot, const double* w, double* out,
+                     void* stream);
+/* gather x[idx[i], :] -> buf[i, :] (halo send buffer) */
+int kb_pack_rows(kb_ws_t ws, int k, int64_t n_idx, const int32_t* idx, const double* x,
+                 double* buf, void* stream);
+
+/* --- reductions: inner(x, y) / norms (_helpers.py:101-110) ------------- */
+int kb_dot(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, double* out,
+           void* stream);
+
+/* --- CG (cg.py:155-234) ------------------------------------------------ */
+/* alpha = rho / nz(pAp [+ pAp2]);  x += alpha p;  r -= alpha Ap;  rr = <r, r>
+ * (cg.py:185,196,200,209).  pAp2 may be NULL (halo dot correction otherwise). */
+int kb_cg_update_xr(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
+                    const double* pAp2, const double* p, const double* Ap, double* x,
+                    double* r, double* rr_out, void* stream);
+/* what & 2: record resnorm[step] = sqrt(rho_new) into hist[step*k + c]; if all
+ *           columns satisfy resnorm <= crit[c] set *stop_at = step (cg.py:156,214-217)
+ * what & 1: omega = rho_new / nz(rho_old);  p = r + omega p  (cg.py:175-178) */
+int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new,
+                   const double* rho_old, const double* crit, double* hist, int* stop_at,
+                   const double* r, double* p, int what, void* stream);
+
+/* --- generic vector kernels (fallback path for M/Ml/Mr/custom inner) ---- */
+/* y += sign * coef[c] * x   (product rounded, then sum: NumPy temporaries) */
+int kb_axpy(kb_ws_t ws, int64_t n, int k, double sign, const double* coef, const double* x,
+            double* y, void* stream);
+/* y = x + coef[c] * y */
+int kb_xpby(kb_ws_t ws, int64_t n, int k, const double* x, const double* coef, double* y,
+            void* stream);
+/* out = x / nz(coef[c])   (arnoldi.py:147-150,191-193,274-277) */
+int kb_div_scale(kb_ws_t ws, int64_t n, int k, const double* x, const double* coef,
+                 double* out, void* stream);
+/* out = x + y */
+int kb_add(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, double* out,
+           void* stream);
+
+/* --- Lanczos / MINRES (arnoldi.py:237-281, minres.py:168-236) ---------- */
+/* w -= sign*coef[c] * u, then out[c] = <z, w> (dot 1) or <w, w> (dot 2) or nothing.
+ * MGS step (arnoldi.py:157-162) and Lanczos alpha-step (arnoldi.py:264-267). */
+int kb_axpy_dot(kb_ws_t ws, int64_t n, int k, const double* coef, const double* u, double* w,
+                int dot, const double* z, double* out, void* stream);
+/* per-column state of the MINRES recurrences; all device arrays of k doubles
+ * unless noted.  One launch of one block. (minres.py:190-228, givens.py:35-45) */
+typedef struct {
+  const double* alpha; /* <v, Av>                 (dot slot) */
+  const double* ww;    /* <Av, M Av>              (dot slot) */
+  double* h2prev;      /* beta_{k-1}; updated to beta_k */
+  double* g0;          /* (2k) current rotation  (c, s) */
+  double* g1;          /* (2k) previous rotation (c, s) */
+  double* y0;          /* running rhs entry */
+  double* coefs;       /* (5k) out: R0, R1, R2, y0*, h2 for kb_minres_update */
+  const double* crit;
+  double* hist;        /* ((maxiter+1) k) */
+  int* stop_at;
+  int* flags;          /* bit0: invariant subspace */
+} kb_minres_state;
+int kb_minres_scalar(kb_ws_t ws, int k, int iter, const kb_minres_state* st, void* stream);
+/* z = (v - R0 W0 - R1 W1)/nz(R2); W0 <- z (becomes W1 by buffer rotation);
+ * yk += y0 z; vnext = Av / nz(h2)   (minres.py:219-221, arnoldi.py:274-277) */
+int kb_minres_update(kb_ws_t ws, int64_t n, int k, const double* coefs, const double* v,
+                     double* W0, const double* W1, const double* Av, double* yk,
+                     double* vnext, void* stream);
+
+/* --- Arnoldi-MGS / GMRES (arnoldi.py:167-200, gmres.py:179-234) -------- */
+typedef struct {
+  const double* dots;  /* (num_reorthos*(j+1)*k) MGS coefficients of this step */
+  const double* ww;    /* <w, M w> */
+  int num_reorthos;
+  int maxiter;
+  double* R;           /* ((maxiter+1) * maxiter * k) Hessenberg -> R of its QR */
+  double* Gc;          /* (maxiter * k) rotation cosines */
+  double* Gs;          /* (maxiter * k) rotation sines */
+  double* y;           /* ((maxiter+1) * k) rhs of the projected system */
+  double* hlast;       /* (k) out: h[j+1] for the normalisation */
+  const double* crit;
+  double* hist;
+  int* stop_at;
+  int* flags;
+  int have_h;          /* 1: Householder path -- `dots` already holds h[0..j+1] */
+} kb_gmres_state;
+int kb_gmres_scalar(kb_ws_t ws, int k, int iter, const kb_gmres_state* st, void* stream);
+/* yy = R[:m,:m]^-1 y[:m] per column (all-zero column -> zeros) (gmres.py:24-38) */
+int kb_gmres_solve_y(kb_ws_t ws, int k, int m, int maxiter, const double* R, const double* y,
+                     double* yy, void* stream);
+/* out = x0 + sum_{j<m} yy[j,c] * V[j]  with V[j] = Vbuf + j*vstride  (gmres.py:96-98) */
+int kb_basis_combine(kb_ws_t ws, int64_t n, int k, int m, const double* yy, const double* Vbuf,
+                     int64_t vstride, const double* x0, double* out, void* stream);
+
+/* --- Householder (householder.py:26-62, arnoldi.py:65-104), k == 1 ------ */
+/* Builds the reflector for the tail x[off:]: v (length n, zeros before off),
+ * params[0..3] = alpha, beta, xnorm, sigma2-taken-from-slot.  Two launches. */
+int kb_house_make(kb_ws_t ws, int64_t n, int64_t off, const double* x, double* v,
+                  double* params, double* scratch, void* stream);
+/* single-element edits used by the Householder Arnoldi step:
+ *  op 0: x[idx] *= s[0];  op 1: x[idx] = val;  op 2: dst[0] = x[idx] */
+int kb_poke(kb_ws_t ws, int op, double* x, int64_t idx, const double* s, double val,
+            double* dst, void* stream);
+
+/* test hook: out[3i..3i+2] = (c, s, r) of LAPACK dlartg(f[i], g[i])  (givens.py:35-38) */
+int kb_lartg(int n, const double* f, const double* g, double* out, void* stream);
+
+/* --- synthetic inputs, built in HBM ---------------------- */
+/* rows of the 7-point stencil for planes z_lo <= z < z_hi, global columns.
+ * coeffs = {diag, lx, ly, lz, ux, uy, uz}.  Pass 1 (vals == NULL) writes
+ * per-row counts into rowptr[1..]; after an inclusive scan by the caller,
+ * pass 2 fills colidx/vals. */
+int kb_stencil7(int nx, int ny, int nz, int z_lo, int z_hi, const double* coeffs_host,
+                int32_t* rowptr, int32_t* colidx, double* vals, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRYLOV_B200_H */

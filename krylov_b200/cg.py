@@ -1,0 +1,238 @@
+"""Preconditioned CG on the device -- drop-in for ``krylov.cg`` (cg.py:16-259).
+
+Same signature, same return value ``(xk if success else None, Info)``, same
+stopping rule (updated residual below ``max(tol*||r0||, atol)`` is confirmed
+with an explicit residual that overwrites ``resnorms[-1]``, cg.py:156-164),
+same zero-division guards, same ``callback(xk, Ml_rk)``.
+
+Two paths:
+  * fused (M = Ml = None, default inner product, A a matrix): three kernels per
+    iteration -- ``p`` update, SpMV fused with ``<p, Ap>``, x/r update fused with
+    ``<r, r>`` -- plus a one-block record/convergence kernel; all scalars stay in
+    HBM, iterations are enqueued in batches and gated on a device flag, so the
+    host reads back once per batch, not per iteration.
+  * general (preconditioners, custom ``inner``, duck-typed operators): the
+    reference loop statement by statement, every vector statement one kernel,
+    scalars on the host.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._alg import Alg, nz
+from .device import Ops
+from .operators import Info, Problem
+
+INT_MAX = 2**31 - 1
+_BATCH_MIN, _BATCH_MAX = 8, 256
+
+
+def cg(A, b, M=None, Ml=None, inner=None, x0=None, tol=1e-5, atol=1.0e-15, maxiter=None,
+       return_arnoldi=False, callback=None, inner_product=None):
+    if inner is None and inner_product is not None:  # alias used by BASELINE.json's wording
+        inner = inner_product
+    prob = Problem(A, b, x0)
+    maxiter = prob.n if maxiter is None else int(maxiter)
+    with torch.cuda.device(prob.device):
+        if M is None and Ml is None and inner is None and prob.A_csr is not None:
+            return _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback)
+        return _cg_general(prob, M, Ml, inner, tol, atol, maxiter, return_arnoldi, callback)
+
+
+def _num_operations(k):
+    # cg.py:243-250
+    return {"A": 1 + k, "M": 2 + k, "Ml": 2 + k, "Mr": 1 + k, "inner": 2 + 2 * k,
+            "axpy": 2 + 2 * k}
+
+
+def _finish(prob, success, xk, k, resn, arnoldi):
+    xk_user = prob.to_user(xk)
+    resnorms = [prob.scalars_to_user(r) for r in resn]
+    return (xk_user if success else None), Info(
+        success, xk_user, k, resnorms, num_operations=_num_operations(k), arnoldi=arnoldi)
+
+
+class _LanczosLog:
+    """cg.py:141-149, 220-232: Lanczos basis and tridiagonal from CG scalars."""
+
+    def __init__(self, prob, ops, maxiter, z0, r0, nrm0):
+        self.prob, self.ops = prob, ops
+        self.V, self.P = [], []
+        self.H = np.zeros([maxiter + 1, maxiter] + list(prob.user_shape[1:]), dtype=float)
+        self.alpha_old = 0
+        self._push(z0, r0, np.where(nrm0 > 0.0, nrm0, 1.0))
+
+    def _push(self, z, r, d):
+        cd = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(d, (self.prob.k,)),
+                                                   dtype=np.float64)).to(self.prob.device)
+        for lst, vec in ((self.V, z), (self.P, r)):
+            out = torch.empty_like(vec)
+            self.ops.div_scale(out, vec, cd)
+            lst.append(self.prob.to_user(out))
+
+    def step(self, k, z, r, alpha, omega, rho_new, rho_old):
+        shp = self.prob.user_shape[1:]
+        nrm = np.sqrt(rho_new)
+        sgn = (-1.0) ** (k + 1)
+        self._push(z, r, sgn * nrm)  # (-1)^(k+1) * v / nrm  ==  v / ((-1)^(k+1) nrm)
+        a = np.reshape(alpha, shp) if shp else alpha[0]
+        self.H[k, k] = 1.0 / a
+        if k > 0:
+            self.H[k - 1, k] = self.H[k, k - 1]
+            self.H[k, k] += (np.reshape(omega, shp) if shp else omega[0]) / self.alpha_old
+        q = np.sqrt(rho_new / rho_old) / alpha
+        self.H[k + 1, k] = np.reshape(q, shp) if shp else q[0]
+        self.alpha_old = a
+
+    def result(self, k):
+        return [self.V, self.H[: k + 1, :k], self.P]
+
+
+# ---------------------------------------------------------------------------
+def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback):
+    A, b, x0 = prob.A_csr, prob.b, prob.x0
+    n, k, dev = prob.n, prob.k, prob.device
+    ops = Ops(n, k, dev)
+    r = ops.vec(zero=False)
+    Ap = ops.vec(zero=False)
+    yk = ops.vec(zero=True)
+    sl = ops.slots(4)  # rho (ping-pong: rho_i lives in sl[i % 2]), <p,Ap>, scratch
+    stop_at = torch.full((1,), INT_MAX, dtype=torch.int32, device=dev)
+    hist = torch.zeros((_BATCH_MAX, k), dtype=torch.float64, device=dev)
+
+    # initial residual r0 = b - A x0 fused with <r0, r0>  (cg.py:116)
+    ops.gate(None, 0)
+    ops.spmv(A, x0, r, mode=2, z=b, dot=2, out=sl[0])
+    rho0 = sl[0].cpu().numpy().copy()
+    nrm0 = np.sqrt(rho0)
+    if callback is not None:
+        callback(prob.to_user(x0), prob.to_user(r))
+    resn = [nrm0]
+    crit = np.maximum(tol * nrm0, atol)  # cg.py:154
+    crit_d = torch.from_numpy(crit).to(dev)
+    p = r.clone()
+    log = _LanczosLog(prob, ops, maxiter, r, r, nrm0) if return_arnoldi else None
+
+    step_by_step = callback is not None or return_arnoldi
+    batch = 1 if step_by_step else _BATCH_MIN
+    kk = 0
+    success = False
+    xk = None
+    while True:
+        if np.all(resn[-1] <= crit):
+            # "oh really?" -- explicit residual of xk = x0 + yk  (cg.py:156-164)
+            if xk is None:
+                xk = torch.empty_like(yk)
+                ops.add(xk, x0, yk)
+            ops.spmv(A, xk, Ap, mode=2, z=b, dot=2, out=sl[3])
+            resn[-1] = np.sqrt(sl[3].cpu().numpy().copy())
+            if np.all(resn[-1] <= crit):
+                success = True
+                break
+        if kk == maxiter:
+            break
+        nb = min(batch, maxiter - kk)
+        stop_at.fill_(INT_MAX)
+        hist_ptr = hist.data_ptr() - (kk + 1) * k * 8  # row (kk+1) of the history == hist[0]
+        for i in range(kk, kk + nb):
+            cur, nxt = sl[i % 2], sl[(i + 1) % 2]
+            ops.gate(stop_at, i)  # iteration i is a no-op once a step <= i converged
+            if i > 0:
+                ops.cg_update_p(cur, nxt, r, p)  # omega = rho_i / rho_{i-1}; p = r + omega p
+            ops.spmv(A, p, Ap, dot=1, w=p, out=sl[2])  # Ap = A p, <p, Ap>
+            ops.cg_update_xr(cur, sl[2], None, p, Ap, yk, r, nxt)  # rho_{i+1} -> nxt
+            ops.cg_record(i + 1, nxt, crit_d, hist_ptr, stop_at)
+        ops.gate(None, 0)
+        s = int(stop_at.item())  # one host read per batch
+        done = min(s, kk + nb) - kk
+        rows = hist[:done].cpu().numpy()
+        if log is not None:  # batch == 1 here
+            sv = sl.cpu().numpy()
+            rho_i, rho_n, pAp = sv[kk % 2], sv[(kk + 1) % 2], sv[2]
+            alpha = rho_i / nz(pAp)
+            omega = rho_i / nz(log.rho_prev) if kk > 0 else None
+            log.step(kk, r, r, alpha, omega, rho_n, rho_i)
+            log.rho_prev = rho_i
+        for j in range(done):
+            resn.append(rows[j].copy())
+        kk += done
+        xk = None
+        if callback is not None:
+            xk = torch.empty_like(yk)
+            ops.add(xk, x0, yk)
+            callback(prob.to_user(xk), prob.to_user(r))
+        if not step_by_step:
+            batch = min(2 * batch, _BATCH_MAX)
+
+    if xk is None:
+        xk = torch.empty_like(yk)
+        ops.add(xk, x0, yk)
+    prob.launches = ops.launches
+    return _finish(prob, success, xk, kk, resn, log.result(kk) if log is not None else None)
+
+
+# ---------------------------------------------------------------------------
+def _cg_general(prob, M, Ml, inner, tol, atol, maxiter, return_arnoldi, callback):
+    alg = Alg(prob, inner)
+    ops = alg.ops
+    A, b, x0 = prob.A, prob.b, prob.x0
+    M = prob.operator(M)
+    Ml = prob.operator(Ml)
+
+    def residual_triple(z):  # cg.py:72-95
+        r_ = alg.apply(Ml, alg.residual(A, b, z))
+        z_ = alg.apply(M, r_)
+        return z_, r_, alg.inner(r_, z_)
+
+    z0, r0, rho = residual_triple(x0)
+    nrm0 = np.sqrt(rho)
+    if callback is not None:
+        callback(prob.to_user(x0), prob.to_user(r0))
+    resn = [nrm0]
+    yk = ops.vec(zero=True)
+    xk = None
+    rho_prev = None
+    r = r0.clone()
+    z = z0.clone() if z0 is not r0 else r
+    p = z.clone()
+    log = _LanczosLog(prob, ops, maxiter, z0, r0, nrm0) if return_arnoldi else None
+
+    kk = 0
+    success = False
+    crit = np.maximum(tol * nrm0, atol)
+    omega = None
+    while True:
+        if np.all(resn[-1] <= crit):
+            xk = alg.add(x0, yk) if xk is None else xk
+            _, _, n2 = residual_triple(xk)
+            resn[-1] = np.sqrt(n2)
+            if np.all(resn[-1] <= crit):
+                success = True
+                break
+        if kk == maxiter:
+            break
+        if kk > 0:
+            omega = rho / nz(rho_prev)
+            alg.xpby(p, z, omega)  # p = z + omega p   (cg.py:178)
+        Ap = alg.apply_chain([A, Ml], p)  # Product(Ml, A) @ p  (cg.py:109,180)
+        pAp = alg.inner(p, Ap)
+        alpha = rho / nz(pAp)
+        alg.axpy(yk, alpha, p)  # cg.py:196
+        xk = None
+        alg.axpy(r, alpha, Ap, sign=-1.0)  # cg.py:200
+        if callback is not None:
+            xk = alg.add(x0, yk)
+            callback(prob.to_user(xk), prob.to_user(r))
+        z = alg.apply(M, r)  # cg.py:207
+        rho_new = alg.inner(r, z)
+        rho_prev, rho = rho, rho_new
+        resn.append(np.sqrt(rho_new))
+        if log is not None:
+            log.step(kk, z, r, alpha, omega, rho, rho_prev)
+        kk += 1
+
+    if xk is None:
+        xk = alg.add(x0, yk)
+    prob.launches = ops.launches
+    return _finish(prob, success, xk, kk, resn, log.result(kk) if log is not None else None)

@@ -1,0 +1,164 @@
+"""Device-resident CSR matrix: the object behind ``A @ x`` on the hot path.
+
+Replaces the SciPy CSR matrix (sparsetools ``csr_matvec`` / ``csr_matvecs``)
+the reference multiplies with at ``_helpers.py:47,61``.  fp64 values, int32
+indices (index traffic is a third of the matrix bytes).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .device import Ops, as_device_matrix, cur_stream, ptr, require_cuda
+
+_SCHEDULES = {"auto": 0, "rowwise": 1, "stream": 2}
+_PAD = 4  # elements readable past nnz (TMA tiles are 4-aligned windows)
+
+
+def _padded(t: torch.Tensor) -> torch.Tensor:
+    n = t.numel()
+    out = torch.zeros(((n + 3) // 4) * 4 + _PAD, dtype=t.dtype, device=t.device)
+    out[:n] = t
+    return out
+
+
+class CsrMatrix:
+    """CSR matrix in HBM.  ``shape``/``dtype``/``__matmul__`` make it a valid
+    operator for the solvers (reference protocol: ``_helpers.py:14-17``)."""
+
+    dtype = np.dtype(np.float64)
+
+    def __init__(self, rowptr, colidx, vals, shape, device=None):
+        require_cuda()
+        dev = torch.device(device) if device is not None else torch.device(
+            "cuda", torch.cuda.current_device())
+        self.device = dev
+        self.shape = (int(shape[0]), int(shape[1]))
+        rowptr = torch.as_tensor(rowptr).to(device=dev, dtype=torch.int32).contiguous()
+        colidx = torch.as_tensor(colidx).to(device=dev, dtype=torch.int32).contiguous()
+        vals = torch.as_tensor(vals).to(device=dev, dtype=torch.float64).contiguous()
+        if rowptr.numel() != self.shape[0] + 1:
+            raise ValueError("rowptr must have n_rows + 1 entries")
+        self.nnz = int(vals.numel())
+        if colidx.numel() != self.nnz:
+            raise ValueError("colidx and vals differ in length")
+        self.rowptr = rowptr
+        self.colidx = _padded(colidx)
+        self.vals = _padded(vals)
+        self._finish()
+
+    @classmethod
+    def _from_device_arrays(cls, rowptr, colidx_padded, vals_padded, nnz, shape):
+        """Adopt already padded device arrays without a copy (stencil generator)."""
+        self = cls.__new__(cls)
+        self.device = vals_padded.device
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.nnz = int(nnz)
+        self.rowptr, self.colidx, self.vals = rowptr, colidx_padded, vals_padded
+        self._finish()
+        return self
+
+    def _finish(self):
+        self._ops = {}
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.kb_csr_create(C.byref(h), self.shape[0], self.shape[1], self.nnz,
+                                    ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), 1,
+                                    cur_stream()))
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib.kb_csr_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------ builders --
+    @classmethod
+    def from_scipy(cls, A, device=None):
+        A = A.tocsr()
+        if np.iscomplexobj(A.data):
+            raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
+        if A.nnz >= 2**31:
+            raise ValueError("nnz must fit int32")
+        return cls(A.indptr.astype(np.int32), A.indices.astype(np.int32),
+                   A.data.astype(np.float64), A.shape, device)
+
+    @classmethod
+    def from_dense(cls, A, device=None):
+        import scipy.sparse
+
+        A = np.asarray(A)
+        if np.iscomplexobj(A):
+            raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
+        return cls.from_scipy(scipy.sparse.csr_matrix(A.astype(np.float64)), device)
+
+    @classmethod
+    def from_torch(cls, A, device=None):
+        if A.layout != torch.sparse_csr:
+            A = A.to_sparse_csr()
+        return cls(A.crow_indices(), A.col_indices(), A.values(), A.shape,
+                   device or (A.device if A.is_cuda else None))
+
+    # ------------------------------------------------------------- queries --
+    def info(self):
+        nr, nc, nz = C.c_int64(), C.c_int64(), C.c_int64()
+        mx, sc = C.c_int(), C.c_int()
+        check(lib.kb_csr_get_info(self.handle, C.byref(nr), C.byref(nc), C.byref(nz), C.byref(mx),
+                                  C.byref(sc)))
+        return {"n_rows": nr.value, "n_cols": nc.value, "nnz": nz.value,
+                "max_row_len": mx.value,
+                "schedule": {1: "rowwise", 2: "stream"}[sc.value]}
+
+    def set_schedule(self, name: str):
+        check(lib.kb_csr_set_schedule(self.handle, _SCHEDULES[name]))
+        return self
+
+    def spmv_bytes(self, k=1):
+        """Algorithmic bytes of one product: 12 nnz + 4(n+1) + 16 n k."""
+        n = self.shape[0]
+        return 12 * self.nnz + 4 * (n + 1) + 16 * n * k
+
+    def to_scipy(self):
+        import scipy.sparse
+
+        return scipy.sparse.csr_matrix(
+            (self.vals[: self.nnz].cpu().numpy(), self.colidx[: self.nnz].cpu().numpy(),
+             self.rowptr.cpu().numpy()), shape=self.shape)
+
+    # -------------------------------------------------------------- product --
+    def _apply(self, ops: Ops, x, y, mode=0, z=None, coef=None, dot=0, w=None, out=None):
+        ops.launches += 1
+        check(lib.kb_spmv(self.handle, ops.ws.handle, ops.k, ptr(x), ptr(y), int(mode), ptr(z),
+                          ptr(coef), int(dot), ptr(w), ptr(out), cur_stream()))
+
+    def _ops_for(self, k):
+        o = self._ops.get(k)
+        if o is None:
+            o = self._ops[k] = Ops(self.shape[0], k, self.device)
+        return o
+
+    def matvec_device(self, x: torch.Tensor, out=None) -> torch.Tensor:
+        """y = A x for a CUDA fp64 tensor of shape (n,) or (n, k)."""
+        k = 1 if x.dim() == 1 else x.shape[1]
+        if x.shape[0] != self.shape[1]:
+            raise ValueError(f"dimension mismatch: {self.shape} @ {tuple(x.shape)}")
+        x = x.contiguous()
+        y = out if out is not None else torch.empty(
+            (self.shape[0],) + tuple(x.shape[1:]), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._apply(self._ops_for(k), x, y)
+        return y
+
+    def __matmul__(self, x):
+        if isinstance(x, torch.Tensor):
+            return self.matvec_device(as_device_matrix(x, self.device))
+        xd = as_device_matrix(x, self.device)
+        return self.matvec_device(xd).cpu().numpy()
+
+    matvec = __matmul__

@@ -1,0 +1,509 @@
+// libkrylov_b200.so -- extern "C" entry points (see include/krylov_b200.h).
+// Host code only validates arguments, picks the schedule and launches; no
+// entry point synchronises the device or allocates per call.
+#include <stdarg.h>
+
+#include <new>
+
+#include "kb_common.cuh"
+#include "kb_scalar.cuh"
+#include "kb_spmv.cuh"
+#include "kb_vec.cuh"
+
+thread_local char kb_errbuf[512] = {0};
+
+int kb_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(kb_errbuf, sizeof(kb_errbuf), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct kb_csr_s {
+  int64_t n_rows, n_cols, nnz;
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const double* vals;
+  int padded;
+  int max_row_len;
+  int schedule;  // 1 row-wise, 2 TMA stream
+  int forced;    // user override (0 = auto)
+};
+
+// stream-kernel configuration: 4 stages x 2048 nnz (24 KB/stage) -> 2 CTAs/SM
+#define KB_ST_STAGES 4
+#define KB_ST_CAP 2048
+#define KB_ST_CTAS_PER_SM 2
+
+static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+
+extern "C" {
+
+int kb_version(void) { return 100; }
+
+int kb_last_error(char* buf, size_t len) {
+  if (buf == nullptr || len == 0) return KB_EINVAL;
+  strncpy(buf, kb_errbuf, len - 1);
+  buf[len - 1] = 0;
+  return KB_OK;
+}
+
+int kb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  KB_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return KB_OK;
+}
+
+// ------------------------------------------------------------ workspace --
+int kb_ws_create(kb_ws_t* out, int max_k) {
+  KB_REQUIRE(out != nullptr, "null handle pointer");
+  KB_REQUIRE(max_k >= 1 && max_k <= KB_MAX_K, "max_k out of range [1, 256]");
+  int dev = 0, sms = 0, major = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  KB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  KB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10)
+    return kb_fail(KB_EUNSUPPORTED, "libkrylov_b200 is built for sm_100a only (device is sm_%d*)",
+                   major * 10);
+  kb_ws_s* ws = new (std::nothrow) kb_ws_s();
+  if (!ws) return kb_fail(KB_ENOMEM, "out of host memory");
+  ws->max_k = max_k;
+  ws->num_sms = sms;
+  ws->gate = nullptr;
+  ws->gate_tag = 0;
+  cudaError_t e = cudaMalloc(&ws->partials, sizeof(double) * KB_MAX_BLOCKS * (size_t)max_k);
+  if (e == cudaSuccess) e = cudaMalloc(&ws->ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(ws->ticket, 0, sizeof(unsigned int));
+  if (e != cudaSuccess) {
+    delete ws;
+    return kb_fail(KB_ECUDA, "workspace allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = ws;
+  return KB_OK;
+}
+
+int kb_ws_destroy(kb_ws_t ws) {
+  if (!ws) return KB_OK;
+  cudaFree(ws->partials);
+  cudaFree(ws->ticket);
+  delete ws;
+  return KB_OK;
+}
+
+int kb_ws_set_gate(kb_ws_t ws, const int* stop_at, int tag) {
+  KB_REQUIRE(ws != nullptr, "null workspace");
+  ws->gate = stop_at;
+  ws->gate_tag = tag;
+  return KB_OK;
+}
+
+// ------------------------------------------------------------------ CSR --
+static void kb_csr_pick(kb_csr_s* h) {
+  // Row-length statistics -> schedule (SURVEY.md 7 "short rows").  The stream
+  // kernel gives one thread one row: right for stencil-like matrices whose
+  // rows are short and even.  Long or very skewed rows go to the row-wise
+  // kernel.
+  const double mean = h->n_rows > 0 ? (double)h->nnz / (double)h->n_rows : 0.0;
+  int sched = 1;
+  if (h->padded && h->n_rows >= 1 && h->n_rows < (1ll << 31) - 512 && mean <= 32.0 &&
+      h->max_row_len <= 8 * (mean + 8.0))
+    sched = 2;
+  if (h->forced == 1) sched = 1;
+  if (h->forced == 2 && h->padded) sched = 2;
+  h->schedule = sched;
+}
+
+int kb_csr_create(kb_csr_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                  const int32_t* rowptr, const int32_t* colidx, const double* vals, int padded,
+                  void* stream) {
+  KB_REQUIRE(out != nullptr, "null handle pointer");
+  KB_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "negative size");
+  KB_REQUIRE(nnz < (1ll << 31), "nnz must fit int32 row pointers");
+  KB_REQUIRE(rowptr != nullptr, "null rowptr");
+  KB_REQUIRE(nnz == 0 || (colidx != nullptr && vals != nullptr), "null colidx/vals");
+  if (padded)
+    KB_REQUIRE(((uintptr_t)colidx % 16 == 0) && ((uintptr_t)vals % 16 == 0),
+               "padded CSR arrays must be 16-byte aligned");
+  kb_csr_s* h = new (std::nothrow) kb_csr_s();
+  if (!h) return kb_fail(KB_ENOMEM, "out of host memory");
+  h->n_rows = n_rows;
+  h->n_cols = n_cols;
+  h->nnz = nnz;
+  h->rowptr = rowptr;
+  h->colidx = colidx;
+  h->vals = vals;
+  h->padded = padded;
+  h->forced = 0;
+  h->max_row_len = 0;
+  if (n_rows > 0) {
+    int* d_max = nullptr;
+    cudaError_t e = cudaMalloc(&d_max, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_max, 0, sizeof(int), S(stream));
+    if (e == cudaSuccess) {
+      int grid = (int)((n_rows + 255) / 256);
+      if (grid > 1184) grid = 1184;
+      kb_max_row_len_kernel<<<grid, 256, 0, S(stream)>>>(n_rows, rowptr, d_max);
+      e = cudaMemcpyAsync(&h->max_row_len, d_max, sizeof(int), cudaMemcpyDeviceToHost, S(stream));
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(S(stream));  // creation is not on the hot path
+    if (d_max) cudaFree(d_max);
+    if (e != cudaSuccess) {
+      delete h;
+      return kb_fail(KB_ECUDA, "kb_csr_create: %s", cudaGetErrorString(e));
+    }
+  }
+  kb_csr_pick(h);
+  *out = h;
+  return KB_OK;
+}
+
+int kb_csr_destroy(kb_csr_t h) {
+  delete h;
+  return KB_OK;
+}
+
+int kb_csr_set_schedule(kb_csr_t h, int schedule) {
+  KB_REQUIRE(h != nullptr, "null matrix");
+  KB_REQUIRE(schedule >= 0 && schedule <= 2, "schedule must be 0, 1 or 2");
+  if (schedule == 2 && !h->padded)
+    return kb_fail(KB_EUNSUPPORTED, "stream schedule needs padded, 16-byte aligned CSR arrays");
+  h->forced = schedule;
+  kb_csr_pick(h);
+  return KB_OK;
+}
+
+int kb_csr_get_info(kb_csr_t h, int64_t* n_rows, int64_t* n_cols, int64_t* nnz, int* max_row_len,
+                    int* schedule) {
+  KB_REQUIRE(h != nullptr, "null matrix");
+  if (n_rows) *n_rows = h->n_rows;
+  if (n_cols) *n_cols = h->n_cols;
+  if (nnz) *nnz = h->nnz;
+  if (max_row_len) *max_row_len = h->max_row_len;
+  if (schedule) *schedule = h->schedule;
+  return KB_OK;
+}
+
+// ----------------------------------------------------------------- SpMV --
+}  // extern "C"
+
+template <int DOT>
+static int kb_launch_stream(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                            const double* z, const double* coef, const double* w, double* out,
+                            cudaStream_t st) {
+  typedef KbStreamSmem<KB_ST_STAGES, KB_ST_CAP> Smem;
+  static bool configured[64] = {false};  // per device (function attributes are per device)
+  auto kern = kb_spmv_stream_kernel<KB_ST_STAGES, KB_ST_CAP, DOT>;
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(Smem)));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const int n_tiles = (int)((A->n_rows + KB_ST_ROWS - 1) / KB_ST_ROWS);
+  int grid = ws->num_sms * KB_ST_CTAS_PER_SM;
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
+  kern<<<grid, KB_ST_THREADS, sizeof(Smem), st>>>((int)A->n_rows, n_tiles, A->rowptr, A->colidx,
+                                                  A->vals, x, y, mode, z, coef, w, out, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" {
+
+int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode, const double* z,
+            const double* coef, int dot, const double* w, double* out, void* stream) {
+  KB_REQUIRE(A != nullptr && ws != nullptr, "null handle");
+  KB_REQUIRE(k >= 1 && k <= ws->max_k, "k exceeds workspace max_k");
+  KB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+  KB_REQUIRE(dot >= 0 && dot <= 2, "dot must be 0, 1 or 2");
+  KB_REQUIRE(y != nullptr && (x != nullptr || A->n_cols == 0), "null vector");
+  KB_REQUIRE(mode == 0 || z != nullptr, "mode 1/2 need z");
+  KB_REQUIRE(mode != 1 || coef != nullptr, "mode 1 needs coef");
+  KB_REQUIRE(dot == 0 || out != nullptr, "dot needs out");
+  KB_REQUIRE(dot != 1 || w != nullptr, "dot 1 needs w");
+  cudaStream_t st = S(stream);
+  if (A->n_rows == 0) {
+    if (dot) KB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * k, st));
+    return KB_OK;
+  }
+  if (k == 1 && A->schedule == 2) {
+    if (dot == 0) return kb_launch_stream<0>(A, ws, x, y, mode, z, coef, w, out, st);
+    if (dot == 1) return kb_launch_stream<1>(A, ws, x, y, mode, z, coef, w, out, st);
+    return kb_launch_stream<2>(A, ws, x, y, mode, z, coef, w, out, st);
+  }
+  const int block = kb_block_for(k);
+  const int grid = kb_grid_for(ws, A->n_rows * (int64_t)k, block, 1);
+  KbRed rd = kb_red(ws);
+  if (dot == 0)
+    kb_spmv_rowwise_kernel<0><<<grid, block, 0, st>>>(A->n_rows, k, A->rowptr, A->colidx, A->vals,
+                                                      x, y, mode, z, coef, w, out, rd);
+  else if (dot == 1)
+    kb_spmv_rowwise_kernel<1><<<grid, block, 0, st>>>(A->n_rows, k, A->rowptr, A->colidx, A->vals,
+                                                      x, y, mode, z, coef, w, out, rd);
+  else
+    kb_spmv_rowwise_kernel<2><<<grid, block, 0, st>>>(A->n_rows, k, A->rowptr, A->colidx, A->vals,
+                                                      x, y, mode, z, coef, w, out, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_spmv_halo_add(kb_ws_t ws, int k, int64_t n_brows, const int32_t* rows,
+                     const int32_t* hrowptr, const int32_t* hcol, const double* hval,
+                     const double* xh, double* y, int dot, const double* w, double* out,
+                     void* stream) {
+  KB_REQUIRE(ws != nullptr, "null workspace");
+  KB_REQUIRE(k >= 1 && k <= ws->max_k, "k exceeds workspace max_k");
+  KB_REQUIRE(dot == 0 || dot == 1, "dot must be 0 or 1");
+  KB_REQUIRE(dot == 0 || (w != nullptr && out != nullptr), "dot 1 needs w and out");
+  cudaStream_t st = S(stream);
+  if (n_brows == 0) {
+    if (dot) KB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * k, st));
+    return KB_OK;
+  }
+  const int block = kb_block_for(k);
+  const int grid = kb_grid_for(ws, n_brows * (int64_t)k, block, 1);
+  KbRed rd = kb_red(ws);
+  if (dot == 0)
+    kb_spmv_halo_add_kernel<0><<<grid, block, 0, st>>>(n_brows, k, rows, hrowptr, hcol, hval, xh,
+                                                       y, w, out, rd);
+  else
+    kb_spmv_halo_add_kernel<1><<<grid, block, 0, st>>>(n_brows, k, rows, hrowptr, hcol, hval, xh,
+                                                       y, w, out, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_pack_rows(kb_ws_t ws, int k, int64_t n_idx, const int32_t* idx, const double* x,
+                 double* buf, void* stream) {
+  KB_REQUIRE(ws != nullptr, "null workspace");
+  KB_REQUIRE(k >= 1, "k must be positive");
+  if (n_idx == 0) return KB_OK;
+  const int grid = kb_grid_for(ws, n_idx * (int64_t)k, KB_BLOCK, 1);
+  kb_pack_rows_kernel<<<grid, KB_BLOCK, 0, S(stream)>>>(n_idx, k, idx, x, buf, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+// ------------------------------------------------------- vector kernels --
+#define KB_VEC_PROLOGUE()                                              \
+  KB_REQUIRE(ws != nullptr, "null workspace");                         \
+  KB_REQUIRE(k >= 1 && k <= ws->max_k, "k exceeds workspace max_k");   \
+  KB_REQUIRE(n >= 0, "negative length");                               \
+  const int64_t total = n * (int64_t)k;                                \
+  const int block = kb_block_for(k);                                   \
+  cudaStream_t st = S(stream);                                         \
+  KbRed rd = kb_red(ws);                                               \
+  (void)rd
+
+int kb_dot(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, double* out,
+           void* stream) {
+  KB_VEC_PROLOGUE();
+  KB_REQUIRE(out != nullptr, "null out");
+  const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
+  kb_dot_kernel<<<grid, block, 0, st>>>(total, k, x, y, out, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_cg_update_xr(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
+                    const double* pAp2, const double* p, const double* Ap, double* x, double* r,
+                    double* rr_out, void* stream) {
+  KB_VEC_PROLOGUE();
+  KB_REQUIRE(rho && pAp && p && Ap && x && r && rr_out, "null argument");
+  const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
+  kb_cg_update_xr_kernel<<<grid, block, 0, st>>>(total, k, rho, pAp, pAp2, p, Ap, x, r, rr_out, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new,
+                   const double* rho_old, const double* crit, double* hist, int* stop_at,
+                   const double* r, double* p, int what, void* stream) {
+  KB_VEC_PROLOGUE();
+  KB_REQUIRE(what >= 1 && what <= 3, "what must be 1 (update p), 2 (record) or 3");
+  KB_REQUIRE(rho_new != nullptr, "null rho_new");
+  KB_REQUIRE(!(what & 2) || (crit && hist && stop_at), "record needs crit, hist, stop_at");
+  KB_REQUIRE(!(what & 1) || (r && p && rho_old), "update needs r, p, rho_old");
+  const int grid = (what & 1) ? kb_grid_for(ws, total, block, KB_UNROLL) : 1;
+  kb_cg_update_p_kernel<<<grid, block, 0, st>>>(total, k, step, rho_new, rho_old, crit, hist,
+                                                stop_at, r, p, what, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_axpy(kb_ws_t ws, int64_t n, int k, double sign, const double* coef, const double* x,
+            double* y, void* stream) {
+  KB_VEC_PROLOGUE();
+  if (total == 0) return KB_OK;
+  const int grid = kb_grid_for(ws, total, block, 2);
+  kb_axpy_kernel<<<grid, block, 0, st>>>(total, k, sign, coef, x, y, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_xpby(kb_ws_t ws, int64_t n, int k, const double* x, const double* coef, double* y,
+            void* stream) {
+  KB_VEC_PROLOGUE();
+  if (total == 0) return KB_OK;
+  const int grid = kb_grid_for(ws, total, block, 2);
+  kb_xpby_kernel<<<grid, block, 0, st>>>(total, k, x, coef, y, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_div_scale(kb_ws_t ws, int64_t n, int k, const double* x, const double* coef, double* out,
+                 void* stream) {
+  KB_VEC_PROLOGUE();
+  if (total == 0) return KB_OK;
+  const int grid = kb_grid_for(ws, total, block, 2);
+  kb_div_scale_kernel<<<grid, block, 0, st>>>(total, k, x, coef, out, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_add(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, double* out,
+           void* stream) {
+  KB_VEC_PROLOGUE();
+  if (total == 0) return KB_OK;
+  const int grid = kb_grid_for(ws, total, block, 2);
+  kb_add_kernel<<<grid, block, 0, st>>>(total, x, y, out, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_axpy_dot(kb_ws_t ws, int64_t n, int k, const double* coef, const double* u, double* w,
+                int dot, const double* z, double* out, void* stream) {
+  KB_VEC_PROLOGUE();
+  KB_REQUIRE(coef && u && w, "null argument");
+  KB_REQUIRE(dot >= 0 && dot <= 2, "dot must be 0, 1 or 2");
+  KB_REQUIRE(dot == 0 || out != nullptr, "dot needs out");
+  KB_REQUIRE(dot != 1 || z != nullptr, "dot 1 needs z");
+  const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
+  if (dot == 0)
+    kb_axpy_dot_kernel<0><<<grid, block, 0, st>>>(total, k, coef, u, w, z, out, rd);
+  else if (dot == 1)
+    kb_axpy_dot_kernel<1><<<grid, block, 0, st>>>(total, k, coef, u, w, z, out, rd);
+  else
+    kb_axpy_dot_kernel<2><<<grid, block, 0, st>>>(total, k, coef, u, w, z, out, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_minres_scalar(kb_ws_t ws, int k, int iter, const kb_minres_state* stt, void* stream) {
+  KB_REQUIRE(ws != nullptr && stt != nullptr, "null argument");
+  KB_REQUIRE(k >= 1 && k <= ws->max_k, "k exceeds workspace max_k");
+  const int block = ((k + 31) / 32) * 32;
+  kb_minres_scalar_kernel<<<1, block, 0, S(stream)>>>(k, iter, *stt, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_minres_update(kb_ws_t ws, int64_t n, int k, const double* coefs, const double* v,
+                     double* W0, const double* W1, const double* Av, double* yk, double* vnext,
+                     void* stream) {
+  KB_VEC_PROLOGUE();
+  KB_REQUIRE(coefs && v && W0 && W1 && Av && yk && vnext, "null argument");
+  if (total == 0) return KB_OK;
+  const int grid = kb_grid_for(ws, total, block, 2);
+  kb_minres_update_kernel<<<grid, block, 0, st>>>(total, k, coefs, v, W0, W1, Av, yk, vnext, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_gmres_scalar(kb_ws_t ws, int k, int iter, const kb_gmres_state* stt, void* stream) {
+  KB_REQUIRE(ws != nullptr && stt != nullptr, "null argument");
+  KB_REQUIRE(k >= 1 && k <= ws->max_k, "k exceeds workspace max_k");
+  KB_REQUIRE(iter >= 0 && iter < stt->maxiter, "iter out of range");
+  const int block = ((k + 31) / 32) * 32;
+  kb_gmres_scalar_kernel<<<1, block, 0, S(stream)>>>(k, iter, *stt, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_gmres_solve_y(kb_ws_t ws, int k, int m, int maxiter, const double* R, const double* y,
+                     double* yy, void* stream) {
+  KB_REQUIRE(ws != nullptr && R && y && yy, "null argument");
+  KB_REQUIRE(m >= 0 && m <= maxiter, "m out of range");
+  if (m == 0) return KB_OK;
+  kb_gmres_solve_y_kernel<<<(k + 63) / 64, 64, 0, S(stream)>>>(k, m, maxiter, R, y, yy, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_basis_combine(kb_ws_t ws, int64_t n, int k, int m, const double* yy, const double* Vbuf,
+                     int64_t vstride, const double* x0, double* out, void* stream) {
+  KB_VEC_PROLOGUE();
+  KB_REQUIRE(x0 && out && (m == 0 || (yy && Vbuf)), "null argument");
+  if (total == 0) return KB_OK;
+  const int grid = kb_grid_for(ws, total, block, 1);
+  kb_basis_combine_kernel<<<grid, block, 0, st>>>(total, k, m, yy, Vbuf, vstride, x0, out, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_house_make(kb_ws_t ws, int64_t n, int64_t off, const double* x, double* v, double* params,
+                  double* scratch, void* stream) {
+  KB_REQUIRE(ws && x && v && params && scratch, "null argument");
+  KB_REQUIRE(off >= 0 && off < n, "offset out of range");
+  int rc = kb_dot(ws, n - off - 1, 1, x + off + 1, x + off + 1, scratch, stream);
+  if (rc != KB_OK) return rc;
+  kb_house_params_kernel<<<1, 32, 0, S(stream)>>>(x, off, scratch, params, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  const int grid = kb_grid_for(ws, n, KB_BLOCK, 2);
+  kb_house_fill_kernel<<<grid, KB_BLOCK, 0, S(stream)>>>(n, off, x, params, v, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_poke(kb_ws_t ws, int op, double* x, int64_t idx, const double* s, double val, double* dst,
+            void* stream) {
+  KB_REQUIRE(ws != nullptr && x != nullptr, "null argument");
+  KB_REQUIRE(op >= 0 && op <= 2, "op must be 0, 1 or 2");
+  kb_poke_kernel<<<1, 1, 0, S(stream)>>>(op, x, idx, s, val, dst, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_lartg(int n, const double* f, const double* g, double* out, void* stream) {
+  if (n <= 0) return KB_OK;
+  kb_lartg_kernel<<<(n + 127) / 128, 128, 0, S(stream)>>>(n, f, g, out);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_stencil7(int nx, int ny, int nz, int z_lo, int z_hi, const double* coeffs_host,
+                int32_t* rowptr, int32_t* colidx, double* vals, void* stream) {
+  KB_REQUIRE(nx > 0 && ny > 0 && nz > 0 && z_lo >= 0 && z_hi <= nz && z_lo < z_hi, "bad grid");
+  KB_REQUIRE(coeffs_host != nullptr && rowptr != nullptr, "null argument");
+  KB_REQUIRE((vals == nullptr) == (colidx == nullptr), "colidx and vals go together");
+  KbStencil7 p;
+  p.nx = nx;
+  p.ny = ny;
+  p.nz = nz;
+  p.z_lo = z_lo;
+  p.z_hi = z_hi;
+  // coeffs = {diag, lx, ly, lz, ux, uy, uz} -> entry order z-1,y-1,x-1,diag,x+1,y+1,z+1
+  p.c[0] = coeffs_host[3];
+  p.c[1] = coeffs_host[2];
+  p.c[2] = coeffs_host[1];
+  p.c[3] = coeffs_host[0];
+  p.c[4] = coeffs_host[4];
+  p.c[5] = coeffs_host[5];
+  p.c[6] = coeffs_host[6];
+  const int64_t n_loc = (int64_t)nx * ny * (z_hi - z_lo);
+  int64_t grid = (n_loc + KB_BLOCK - 1) / KB_BLOCK;
+  if (grid > 148 * 16) grid = 148 * 16;
+  kb_stencil7_kernel<<<(int)grid, KB_BLOCK, 0, S(stream)>>>(p, rowptr, colidx, vals);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,345 @@
+// CSR sparse products fused with the operation that follows them.
+//
+//   t = A x ;  y = t | t - coef*z | z - t ;  out = <w,y> | <y,y> | -
+//
+// Two schedules:
+//  * kb_spmv_rowwise_kernel  -- any k, any matrix: one thread per (row, column),
+//    k lanes share a row (its vals/cols loads are broadcast, the x row is one
+//    contiguous k*8-byte read).
+//  * kb_spmv_stream_kernel   -- k == 1, short rows (stencils): persistent CTAs;
+//    a producer lane streams each 256-row tile's colidx/vals into a shared-memory
+//    ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), 8
+//    consumer warps take one row per thread out of shared memory, gather x
+//    through L1/L2 and write y coalesced.  Matrix bytes are read from HBM exactly
+//    once, fully coalesced, independent of row length.
+//
+// Row sums are accumulated left to right with a rounded product and a rounded
+// add (no FMA): the same order and roundings as SciPy's csr_matvec(s)
+// (the routine behind `A @ x` at _helpers.py:47), so y is bit-identical to the
+// reference's product.
+#pragma once
+#include "kb_common.cuh"
+
+// ---------------------------------------------------------------- epilogue --
+__device__ __forceinline__ double kb_spmv_epilogue(double t, int mode, const double* z,
+                                                   double coef, size_t idx) {
+  if (mode == 1) return kb_mul_sub(coef, z[idx], t);  // t - coef*z
+  if (mode == 2) return __dsub_rn(z[idx], t);         // z - t
+  return t;
+}
+
+// ------------------------------------------------------------ row-wise k>=1 --
+template <int DOT>
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_spmv_rowwise_kernel(int64_t n_rows, int k, const int32_t* __restrict__ rowptr,
+                       const int32_t* __restrict__ colidx, const double* __restrict__ vals,
+                       const double* __restrict__ x, double* __restrict__ y, int mode,
+                       const double* __restrict__ z, const double* __restrict__ coef,
+                       const double* __restrict__ w, double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  __shared__ double sm[KB_BLOCK];
+  const int c = threadIdx.x % k;
+  const int rows_per_block = blockDim.x / k;
+  const int rsub = threadIdx.x / k;
+  const double cf = (mode == 1) ? coef[c] : 0.0;
+  double acc = 0.0;
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + rsub; row < n_rows;
+       row += (int64_t)gridDim.x * rows_per_block) {
+    const int lo = rowptr[row], hi = rowptr[row + 1];
+    double sum = 0.0;
+    for (int j = lo; j < hi; ++j)
+      sum = __dadd_rn(sum, __dmul_rn(vals[j], x[(size_t)colidx[j] * k + c]));
+    const size_t idx = (size_t)row * k + c;
+    const double yv = kb_spmv_epilogue(sum, mode, z, cf, idx);
+    y[idx] = yv;
+    if (DOT == 1) acc = fma(w[idx], yv, acc);
+    if (DOT == 2) acc = fma(yv, yv, acc);
+  }
+  if (DOT != 0) kb_grid_colsum(acc, k, rd, out, sm);
+}
+
+// ------------------------------------------------------------- PTX helpers --
+__device__ __forceinline__ uint32_t kb_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void kb_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(kb_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void kb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(kb_smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void kb_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(kb_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void kb_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "KB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra KB_DONE_%=;\n"
+      "bra KB_WAIT_%=;\n"
+      "KB_DONE_%=:\n"
+      "}\n" ::"r"(kb_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void kb_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(kb_smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(kb_smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------- TMA-staged stream k==1 --
+#define KB_ST_ROWS 256                 // rows per tile == consumer threads
+#define KB_ST_THREADS (KB_ST_ROWS + 32)  // + one producer warp
+
+template <int STAGES, int CAP>
+struct KbStreamSmem {
+  double vals[STAGES][CAP];
+  int32_t cols[STAGES][CAP];
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+};
+
+// chunk c of a tile whose nnz occupy [s, e): 4-aligned window of <= CAP entries
+__device__ __forceinline__ void kb_chunk_range(int s, int e, int cidx, int cap, int& a, int& b) {
+  const int a0 = s & ~3;
+  const int a1 = (e + 3) & ~3;
+  a = a0 + cidx * cap;
+  b = min(a + cap, a1);
+}
+
+template <int STAGES, int CAP, int DOT>
+__global__ void __launch_bounds__(KB_ST_THREADS)
+kb_spmv_stream_kernel(int n_rows, int n_tiles, const int32_t* __restrict__ rowptr,
+                      const int32_t* __restrict__ colidx, const double* __restrict__ vals,
+                      const double* __restrict__ x, double* __restrict__ y, int mode,
+                      const double* __restrict__ z, const double* __restrict__ coef,
+                      const double* __restrict__ w, double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  extern __shared__ __align__(128) unsigned char kb_dyn_smem[];
+  KbStreamSmem<STAGES, CAP>& S = *reinterpret_cast<KbStreamSmem<STAGES, CAP>*>(kb_dyn_smem);
+  __shared__ double red_sm[KB_ST_THREADS];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int nconsumer_warps = KB_ST_ROWS / 32;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      kb_mbar_init(&S.full[s], 1);                  // producer's expect_tx arrive
+      kb_mbar_init(&S.empty[s], nconsumer_warps);   // one arrive per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc = 0.0;
+
+  if (warp == nconsumer_warps) {
+    // ===================== producer warp ====================================
+    // All 32 lanes fetch the nnz bounds of this CTA's next 32 tiles at once (one
+    // round of latency per 32 tiles); lane 0 then issues the bulk copies.
+    const int lane = tid & 31;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t base = blockIdx.x; base < n_tiles; base += 32ll * gridDim.x) {
+      const int64_t my_tile = base + (int64_t)lane * gridDim.x;
+      int my_s = 0, my_e = 0;
+      if (my_tile < n_tiles) {
+        const int r0 = (int)my_tile * KB_ST_ROWS;
+        const int r1 = min(r0 + KB_ST_ROWS, n_rows);
+        my_s = rowptr[r0];
+        my_e = rowptr[r1];
+      }
+      for (int q = 0; q < 32; ++q) {
+        if (base + (int64_t)q * gridDim.x >= n_tiles) break;  // warp-uniform
+        const int s = __shfl_sync(0xffffffffu, my_s, q);
+        const int e = __shfl_sync(0xffffffffu, my_e, q);
+        if (lane == 0 && e > s) {
+          const int nch = (((e + 3) & ~3) - (s & ~3) + CAP - 1) / CAP;
+          for (int ci = 0; ci < nch; ++ci) {
+            int a, b;
+            kb_chunk_range(s, e, ci, CAP, a, b);
+            kb_mbar_wait(&S.empty[stage], phase ^ 1u);  // slot free (passes at once in round 0)
+            const uint32_t cnt = (uint32_t)(b - a);
+            kb_mbar_expect_tx(&S.full[stage], cnt * 12u);
+            kb_bulk_g2s(&S.vals[stage][0], vals + a, cnt * 8u, &S.full[stage]);
+            kb_bulk_g2s(&S.cols[stage][0], colidx + a, cnt * 4u, &S.full[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================ consumers: one row per thread ==============
+    int stage = 0;
+    uint32_t phase = 0;
+    const double cf = (mode == 1) ? coef[0] : 0.0;
+    int tile = blockIdx.x;
+    // software-pipelined row pointers of the next tile
+    int lo_n = 0, hi_n = 0, s_n = 0, e_n = 0;
+    if (tile < n_tiles) {
+      const int r0 = tile * KB_ST_ROWS;
+      const int r1 = min(r0 + KB_ST_ROWS, n_rows);
+      const int row = r0 + tid;
+      s_n = rowptr[r0];
+      e_n = rowptr[r1];
+      if (row < n_rows) {
+        lo_n = rowptr[row];
+        hi_n = rowptr[row + 1];
+      }
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
+      const int r0 = tile * KB_ST_ROWS;
+      const int row = r0 + tid;
+      const int lo = lo_n, hi = hi_n, s = s_n, e = e_n;
+      {
+        const int nt = tile + gridDim.x;
+        if (nt < n_tiles) {
+          const int q0 = nt * KB_ST_ROWS;
+          const int q1 = min(q0 + KB_ST_ROWS, n_rows);
+          const int qrow = q0 + tid;
+          s_n = rowptr[q0];
+          e_n = rowptr[q1];
+          lo_n = hi_n = 0;
+          if (qrow < n_rows) {
+            lo_n = rowptr[qrow];
+            hi_n = rowptr[qrow + 1];
+          }
+        }
+      }
+      double sum = 0.0;
+      if (e > s) {
+        const int nch = (((e + 3) & ~3) - (s & ~3) + CAP - 1) / CAP;
+        for (int ci = 0; ci < nch; ++ci) {
+          int a, b;
+          kb_chunk_range(s, e, ci, CAP, a, b);
+          kb_mbar_wait(&S.full[stage], phase);
+          const int jb = max(lo, a), je = min(hi, b);
+          const double* sv = &S.vals[stage][0];
+          const int32_t* sc = &S.cols[stage][0];
+          int j = jb - a;
+          const int jend = je - a;
+          // gathers first (independent), then the ordered sum
+          for (; j + 3 < jend; j += 4) {
+            const double x0 = __ldg(x + sc[j]);
+            const double x1 = __ldg(x + sc[j + 1]);
+            const double x2 = __ldg(x + sc[j + 2]);
+            const double x3 = __ldg(x + sc[j + 3]);
+            sum = __dadd_rn(sum, __dmul_rn(sv[j], x0));
+            sum = __dadd_rn(sum, __dmul_rn(sv[j + 1], x1));
+            sum = __dadd_rn(sum, __dmul_rn(sv[j + 2], x2));
+            sum = __dadd_rn(sum, __dmul_rn(sv[j + 3], x3));
+          }
+          for (; j < jend; ++j) sum = __dadd_rn(sum, __dmul_rn(sv[j], __ldg(x + sc[j])));
+          __syncwarp();
+          if ((tid & 31) == 0) kb_mbar_arrive(&S.empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      if (row < n_rows) {
+        const double yv = kb_spmv_epilogue(sum, mode, z, cf, (size_t)row);
+        y[row] = yv;
+        if (DOT == 1) acc = fma(w[row], yv, acc);
+        if (DOT == 2) acc = fma(yv, yv, acc);
+      }
+    }
+  }
+  if (DOT != 0) kb_grid_colsum(acc, 1, rd, out, red_sm);
+}
+
+// ------------------------------------------------- boundary rows (halo part) --
+// for i < n_brows: row = rows[i];  h = sum_j hval[j] * xh[hcol[j], c];
+//   y[row, c] += h ;  out[c] = sum w[row, c] * h      (dot 1)
+template <int DOT>
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_spmv_halo_add_kernel(int64_t n_brows, int k, const int32_t* __restrict__ rows,
+                        const int32_t* __restrict__ hrowptr, const int32_t* __restrict__ hcol,
+                        const double* __restrict__ hval, const double* __restrict__ xh,
+                        double* __restrict__ y, const double* __restrict__ w,
+                        double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  __shared__ double sm[KB_BLOCK];
+  const int c = threadIdx.x % k;
+  const int rows_per_block = blockDim.x / k;
+  const int rsub = threadIdx.x / k;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * rows_per_block + rsub; i < n_brows;
+       i += (int64_t)gridDim.x * rows_per_block) {
+    const int lo = hrowptr[i], hi = hrowptr[i + 1];
+    double h = 0.0;
+    for (int j = lo; j < hi; ++j)
+      h = __dadd_rn(h, __dmul_rn(hval[j], xh[(size_t)hcol[j] * k + c]));
+    const size_t idx = (size_t)rows[i] * k + c;
+    y[idx] = __dadd_rn(y[idx], h);
+    if (DOT == 1) acc = fma(w[idx], h, acc);
+  }
+  if (DOT != 0) kb_grid_colsum(acc, k, rd, out, sm);
+}
+
+// ----------------------------------------------------------- row statistics --
+__global__ void kb_max_row_len_kernel(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                                      int* out) {
+  int m = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, rowptr[r + 1] - rowptr[r]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// ------------------------------------------------------- 7-point generator --
+// Entry order per row: z-1, y-1, x-1, diag, x+1, y+1, z+1 (ascending column).
+struct KbStencil7 {
+  int nx, ny, nz, z_lo, z_hi;
+  double c[7];  // lz, ly, lx, diag, ux, uy, uz  (already in entry order)
+};
+
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_stencil7_kernel(KbStencil7 p, int32_t* __restrict__ rowptr, int32_t* __restrict__ colidx,
+                   double* __restrict__ vals) {
+  const int64_t plane = (int64_t)p.nx * p.ny;
+  const int64_t n_loc = plane * (p.z_hi - p.z_lo);
+  const int64_t offs[7] = {-plane, -(int64_t)p.nx, -1, 0, 1, (int64_t)p.nx, plane};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_loc;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = i + plane * p.z_lo;
+    const int ix = (int)(g % p.nx);
+    const int iy = (int)((g / p.nx) % p.ny);
+    const int iz = (int)(g / plane);
+    const bool ok[7] = {iz > 0, iy > 0, ix > 0, true, ix < p.nx - 1, iy < p.ny - 1, iz < p.nz - 1};
+    if (vals == nullptr) {
+      int cnt = 0;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) cnt += ok[q] ? 1 : 0;
+      rowptr[i + 1] = cnt;
+      if (i == 0) rowptr[0] = 0;
+    } else {
+      int j = rowptr[i];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        if (ok[q]) {
+          colidx[j] = (int32_t)(g + offs[q]);
+          vals[j] = p.c[q];
+          ++j;
+        }
+      }
+    }
+  }
+}

@@ -1,0 +1,302 @@
+// Streaming vector kernels: every one is a single pass over its operands
+// (HBM-bound; bytes per element are stated per kernel), vectors are (n, k)
+// row-major and flat-indexed, per-column scalars come from device memory.
+//
+// Indexing rule shared by all kernels here: blockDim.x % k == 0 and the grid
+// stride is a multiple of blockDim.x, so thread t only ever touches column
+// c = t % k.  That makes the per-column coefficients loop-invariant and the
+// column-wise reductions a plain per-thread accumulation.
+#pragma once
+#include "kb_common.cuh"
+
+#define KB_UNROLL 4
+
+// ---------------------------------------------------------------- dot ----
+// out[c] = sum_i x[i,c] * y[i,c]        16 B/element (8 when x == y)
+// reference: _helpers.py:101-110 (np.dot / einsum "i...,i...->...")
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_dot_kernel(int64_t total, int k, const double* __restrict__ x, const double* __restrict__ y,
+              double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  __shared__ double sm[KB_BLOCK];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  for (; e + (KB_UNROLL - 1) * stride < total; e += KB_UNROLL * stride) {
+    double a[KB_UNROLL], b[KB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      a[u] = x[e + u * stride];
+      b[u] = y[e + u * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) acc = fma(a[u], b[u], acc);
+  }
+  for (; e < total; e += stride) acc = fma(x[e], y[e], acc);
+  kb_grid_colsum(acc, k, rd, out, sm);
+}
+
+// ------------------------------------------------------------ CG: x, r ---
+// alpha = rho / nz(pAp [+ pAp2]);  x += alpha p;  r -= alpha Ap;  rr = <r,r>
+// 48 B/element (reads x p r Ap, writes x r).  cg.py:185,196,200,209
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
+                       const double* __restrict__ pAp, const double* __restrict__ pAp2,
+                       const double* __restrict__ p, const double* __restrict__ Ap,
+                       double* __restrict__ x, double* __restrict__ r, double* __restrict__ out,
+                       KbRed rd) {
+  if (kb_gated(rd)) return;
+  __shared__ double sm[KB_BLOCK];
+  const int c = threadIdx.x % k;
+  double d = pAp[c];
+  if (pAp2 != nullptr) d += pAp2[c];
+  const double alpha = rho[c] / kb_nz(d);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  for (; e + (KB_UNROLL - 1) * stride < total; e += KB_UNROLL * stride) {
+    double xv[KB_UNROLL], pv[KB_UNROLL], rv[KB_UNROLL], av[KB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      const int64_t i = e + u * stride;
+      xv[u] = x[i];
+      pv[u] = p[i];
+      rv[u] = r[i];
+      av[u] = Ap[i];
+    }
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      const int64_t i = e + u * stride;
+      x[i] = kb_mul_add(alpha, pv[u], xv[u]);
+      const double rn = kb_mul_sub(alpha, av[u], rv[u]);
+      r[i] = rn;
+      acc = fma(rn, rn, acc);
+    }
+  }
+  for (; e < total; e += stride) {
+    x[e] = kb_mul_add(alpha, p[e], x[e]);
+    const double rn = kb_mul_sub(alpha, Ap[e], r[e]);
+    r[e] = rn;
+    acc = fma(rn, rn, acc);
+  }
+  kb_grid_colsum(acc, k, rd, out, sm);
+}
+
+// ------------------------------------------------------------- CG: p -----
+// what & 2 (block 0): hist[step] = sqrt(rho_new); all columns <= crit -> *stop_at = step
+// what & 1 (all):     omega = rho_new / nz(rho_old);  p = r + omega p      24 B/element
+// cg.py:156,175-178,214-217
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_cg_update_p_kernel(int64_t total, int k, int step, const double* __restrict__ rho_new,
+                      const double* __restrict__ rho_old, const double* __restrict__ crit,
+                      double* __restrict__ hist, int* stop_at, const double* __restrict__ r,
+                      double* __restrict__ p, int what, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const int c = threadIdx.x % k;
+  if ((what & 2) && blockIdx.x == 0) {
+    int ok = 1;
+    if (threadIdx.x < k) {
+      const double nrm = sqrt(rho_new[c]);
+      hist[(size_t)step * k + c] = nrm;
+      ok = (nrm <= crit[c]) ? 1 : 0;
+    }
+    const int all_ok = __syncthreads_and(ok);
+    if (all_ok && threadIdx.x == 0) *stop_at = step;
+  }
+  if (!(what & 1)) return;
+  const double omega = rho_new[c] / kb_nz(rho_old[c]);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; e + (KB_UNROLL - 1) * stride < total; e += KB_UNROLL * stride) {
+    double rv[KB_UNROLL], pv[KB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      rv[u] = r[e + u * stride];
+      pv[u] = p[e + u * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) p[e + u * stride] = kb_mul_add(omega, pv[u], rv[u]);
+  }
+  for (; e < total; e += stride) p[e] = kb_mul_add(omega, p[e], r[e]);
+}
+
+// -------------------------------------------------------- generic axpy ---
+// y += sign * coef[c] * x     24 B/element
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_axpy_kernel(int64_t total, int k, double sign, const double* __restrict__ coef,
+               const double* __restrict__ x, double* __restrict__ y, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const double a = sign * coef[threadIdx.x % k];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
+    y[e] = kb_mul_add(a, x[e], y[e]);
+}
+
+// y = x + coef[c] * y         24 B/element
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_xpby_kernel(int64_t total, int k, const double* __restrict__ x,
+               const double* __restrict__ coef, double* __restrict__ y, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const double a = coef[threadIdx.x % k];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
+    y[e] = kb_mul_add(a, y[e], x[e]);
+}
+
+// out = x / nz(coef[c])       16 B/element   (arnoldi.py:191-196, 274-277)
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_div_scale_kernel(int64_t total, int k, const double* __restrict__ x,
+                    const double* __restrict__ coef, double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const double d = kb_nz(coef[threadIdx.x % k]);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
+    out[e] = x[e] / d;
+}
+
+// out = x + y                 24 B/element
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_add_kernel(int64_t total, const double* __restrict__ x, const double* __restrict__ y,
+              double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
+    out[e] = x[e] + y[e];
+}
+
+// ------------------------------------------------ MGS / Lanczos: axpy+dot -
+// w -= coef[c] * u; then out[c] = <z, w> (dot 1) | <w, w> (dot 2) | nothing
+// 32 B/element with dot 1, 24 otherwise.   arnoldi.py:157-162, 264-267
+template <int DOT>
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_axpy_dot_kernel(int64_t total, int k, const double* __restrict__ coef,
+                   const double* __restrict__ u, double* __restrict__ w,
+                   const double* __restrict__ z, double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  __shared__ double sm[KB_BLOCK];
+  const double a = coef[threadIdx.x % k];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  for (; e + (KB_UNROLL - 1) * stride < total; e += KB_UNROLL * stride) {
+    double uv[KB_UNROLL], wv[KB_UNROLL], zv[KB_UNROLL];
+#pragma unroll
+    for (int q = 0; q < KB_UNROLL; ++q) {
+      uv[q] = u[e + q * stride];
+      wv[q] = w[e + q * stride];
+      if (DOT == 1) zv[q] = z[e + q * stride];
+    }
+#pragma unroll
+    for (int q = 0; q < KB_UNROLL; ++q) {
+      const double wn = kb_mul_sub(a, uv[q], wv[q]);
+      w[e + q * stride] = wn;
+      if (DOT == 1) acc = fma(zv[q], wn, acc);
+      if (DOT == 2) acc = fma(wn, wn, acc);
+    }
+  }
+  for (; e < total; e += stride) {
+    const double wn = kb_mul_sub(a, u[e], w[e]);
+    w[e] = wn;
+    if (DOT == 1) acc = fma(z[e], wn, acc);
+    if (DOT == 2) acc = fma(wn, wn, acc);
+  }
+  if (DOT != 0) kb_grid_colsum(acc, k, rd, out, sm);
+}
+
+// --------------------------------------------------------- MINRES update -
+// coefs = [R0 | R1 | R2 | y0 | h2] (k each)
+// z = (v - R0 W0 - R1 W1) / nz(R2);  W0 <- z;  yk += y0 z;  vnext = Av / nz(h2)
+// 64 B/element (reads v W0 W1 Av yk, writes W0 yk vnext).
+// minres.py:219-221 ("take the longest"), arnoldi.py:274-277
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_minres_update_kernel(int64_t total, int k, const double* __restrict__ coefs,
+                        const double* __restrict__ v, double* __restrict__ W0,
+                        const double* __restrict__ W1, const double* __restrict__ Av,
+                        double* __restrict__ yk, double* __restrict__ vnext, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const int c = threadIdx.x % k;
+  const double R0 = coefs[c];
+  const double R1 = coefs[k + c];
+  const double R2 = kb_nz(coefs[2 * k + c]);
+  const double y0 = coefs[3 * k + c];
+  const double h2 = kb_nz(coefs[4 * k + c]);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; e + 1 * stride < total; e += 2 * stride) {
+    double vv[2], w0[2], w1[2], av[2], yv[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int64_t i = e + q * stride;
+      vv[q] = v[i];
+      w0[q] = W0[i];
+      w1[q] = W1[i];
+      av[q] = Av[i];
+      yv[q] = yk[i];
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int64_t i = e + q * stride;
+      const double zz = kb_mul_sub(R1, w1[q], kb_mul_sub(R0, w0[q], vv[q])) / R2;
+      W0[i] = zz;
+      yk[i] = kb_mul_add(y0, zz, yv[q]);
+      vnext[i] = av[q] / h2;
+    }
+  }
+  for (; e < total; e += stride) {
+    const double zz = kb_mul_sub(R1, W1[e], kb_mul_sub(R0, W0[e], v[e])) / R2;
+    W0[e] = zz;
+    yk[e] = kb_mul_add(y0, zz, yk[e]);
+    vnext[e] = Av[e] / h2;
+  }
+}
+
+// ------------------------------------------------------- basis combine ---
+// out = x0 + sum_{j<m} yy[j,c] * V[j]      8(m+2) B/element
+// gmres.py:96-98 (Python `sum` of scaled vectors, left to right from 0)
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_basis_combine_kernel(int64_t total, int k, int m, const double* __restrict__ yy,
+                        const double* __restrict__ Vbuf, int64_t vstride,
+                        const double* __restrict__ x0, double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const int c = threadIdx.x % k;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    double acc = 0.0;
+    int j = 0;
+    for (; j + 3 < m; j += 4) {
+      const double v0 = Vbuf[(size_t)j * vstride + e];
+      const double v1 = Vbuf[(size_t)(j + 1) * vstride + e];
+      const double v2 = Vbuf[(size_t)(j + 2) * vstride + e];
+      const double v3 = Vbuf[(size_t)(j + 3) * vstride + e];
+      acc = kb_mul_add(yy[(size_t)j * k + c], v0, acc);
+      acc = kb_mul_add(yy[(size_t)(j + 1) * k + c], v1, acc);
+      acc = kb_mul_add(yy[(size_t)(j + 2) * k + c], v2, acc);
+      acc = kb_mul_add(yy[(size_t)(j + 3) * k + c], v3, acc);
+    }
+    for (; j < m; ++j) acc = kb_mul_add(yy[(size_t)j * k + c], Vbuf[(size_t)j * vstride + e], acc);
+    out[e] = x0[e] + acc;
+  }
+}
+
+// gather rows: buf[i, :] = x[idx[i], :]   (halo send buffer)
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_pack_rows_kernel(int64_t n_idx, int k, const int32_t* __restrict__ idx,
+                    const double* __restrict__ x, double* __restrict__ buf, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const int64_t total = n_idx * k;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t i = e / k;
+    const int c = (int)(e - i * k);
+    buf[e] = x[(size_t)idx[i] * k + c];
+  }
+}
+
+// single-element edits (Householder Arnoldi bookkeeping, arnoldi.py:75-96)
+__global__ void kb_poke_kernel(int op, double* x, int64_t idx, const double* s, double val,
+                               double* dst, KbRed rd) {
+  if (kb_gated(rd)) return;
+  if (op == 0) x[idx] *= s[0];
+  else if (op == 1) x[idx] = val;
+  else if (op == 2) dst[0] = x[idx];
+}

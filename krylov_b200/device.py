@@ -1,0 +1,178 @@
+"""Device plumbing: PyTorch owns memory and streams, the C ABI does the work.
+
+`Ops` is a thin, allocation-free façade over the C entry points for vectors of
+a fixed logical shape (n, k); it exists so that the solver loops read like the
+reference's loops while every statement is one kernel launch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import GmresState, KrylovB200Error, MinresState, check, lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise KrylovB200Error(
+            "krylov_b200 needs an sm_100 CUDA device; there is no CPU fallback")
+
+
+def cur_stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def as_device_matrix(v, device=None) -> torch.Tensor:
+    """Any real array-like -> contiguous fp64 CUDA tensor."""
+    if isinstance(v, torch.Tensor):
+        if v.is_complex():
+            raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
+        return v.to(device=device or "cuda", dtype=torch.float64).contiguous()
+    a = np.asarray(v)
+    if np.iscomplexobj(a):
+        raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return torch.from_numpy(a).to(device or "cuda")
+
+
+class Workspace:
+    """Owns one kb_ws handle (block-partials buffer + arrival ticket)."""
+
+    def __init__(self, max_k: int = 1):
+        require_cuda()
+        self.max_k = int(max_k)
+        h = C.c_void_p()
+        check(lib.kb_ws_create(C.byref(h), self.max_k))
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib.kb_ws_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Ops:
+    """Kernel launches for (n, k) fp64 vectors on the current CUDA stream."""
+
+    def __init__(self, n: int, k: int, device=None):
+        require_cuda()
+        if k < 1 or k > 256:
+            raise ValueError("blocked right-hand sides: 1 <= k <= 256 columns supported")
+        self.n, self.k = int(n), int(k)
+        self.device = torch.device(device) if device is not None else torch.device(
+            "cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            self.ws = Workspace(k)
+        self.launches = 0  # kernels enqueued through this object (bench `gpu_launches`)
+
+    # -- allocation helpers (set-up only, never inside an iteration)
+    def vec(self, zero=True):
+        f = torch.zeros if zero else torch.empty
+        return f((self.n, self.k), dtype=torch.float64, device=self.device)
+
+    def slots(self, m=1):
+        return torch.zeros((m, self.k), dtype=torch.float64, device=self.device)
+
+    # -- gating
+    def gate(self, stop_at, tag):
+        check(lib.kb_ws_set_gate(self.ws.handle, ptr(stop_at), int(tag)))
+
+    # -- sparse products
+    def spmv(self, A, x, y, mode=0, z=None, coef=None, dot=0, w=None, out=None):
+        A._apply(self, x, y, mode, z, coef, dot, w, out)
+
+    # -- reductions
+    def dot(self, x, y, out, n=None):
+        self.launches += 1
+        check(lib.kb_dot(self.ws.handle, self.n if n is None else n, self.k, ptr(x), ptr(y),
+                         ptr(out), cur_stream()))
+
+    # -- CG
+    def cg_update_xr(self, rho, pAp, pAp2, p, Ap, x, r, rr_out):
+        self.launches += 1
+        check(lib.kb_cg_update_xr(self.ws.handle, self.n, self.k, ptr(rho), ptr(pAp), ptr(pAp2),
+                                  ptr(p), ptr(Ap), ptr(x), ptr(r), ptr(rr_out), cur_stream()))
+
+    def cg_update_p(self, rho_new, rho_old, r, p):
+        """p = r + (rho_new / nz(rho_old)) p"""
+        self.launches += 1
+        check(lib.kb_cg_update_p(self.ws.handle, self.n, self.k, 0, ptr(rho_new), ptr(rho_old),
+                                 None, None, None, ptr(r), ptr(p), 1, cur_stream()))
+
+    def cg_record(self, step, rho_new, crit, hist_ptr, stop_at):
+        """hist[step] = sqrt(rho_new); all columns <= crit -> stop_at = step.
+        `hist_ptr` is a raw device address (row 0 of the history)."""
+        self.launches += 1
+        check(lib.kb_cg_update_p(self.ws.handle, self.n, self.k, int(step), ptr(rho_new), None,
+                                 ptr(crit), hist_ptr, ptr(stop_at), None, None, 2, cur_stream()))
+
+    # -- generic vector kernels
+    def axpy(self, y, coef, x, sign=1.0):
+        self.launches += 1
+        check(lib.kb_axpy(self.ws.handle, self.n, self.k, float(sign), ptr(coef), ptr(x), ptr(y),
+                          cur_stream()))
+
+    def xpby(self, y, x, coef):
+        self.launches += 1
+        check(lib.kb_xpby(self.ws.handle, self.n, self.k, ptr(x), ptr(coef), ptr(y), cur_stream()))
+
+    def div_scale(self, out, x, coef):
+        self.launches += 1
+        check(lib.kb_div_scale(self.ws.handle, self.n, self.k, ptr(x), ptr(coef), ptr(out),
+                               cur_stream()))
+
+    def add(self, out, x, y):
+        self.launches += 1
+        check(lib.kb_add(self.ws.handle, self.n, self.k, ptr(x), ptr(y), ptr(out), cur_stream()))
+
+    def axpy_dot(self, coef, u, w, dot=0, z=None, out=None):
+        self.launches += 1
+        check(lib.kb_axpy_dot(self.ws.handle, self.n, self.k, ptr(coef), ptr(u), ptr(w), int(dot),
+                              ptr(z), ptr(out), cur_stream()))
+
+    # -- MINRES
+    def minres_scalar(self, it, state: MinresState):
+        self.launches += 1
+        check(lib.kb_minres_scalar(self.ws.handle, self.k, int(it), C.byref(state), cur_stream()))
+
+    def minres_update(self, coefs, v, W0, W1, Av, yk, vnext):
+        self.launches += 1
+        check(lib.kb_minres_update(self.ws.handle, self.n, self.k, ptr(coefs), ptr(v), ptr(W0),
+                                   ptr(W1), ptr(Av), ptr(yk), ptr(vnext), cur_stream()))
+
+    # -- GMRES
+    def gmres_scalar(self, it, state: GmresState):
+        self.launches += 1
+        check(lib.kb_gmres_scalar(self.ws.handle, self.k, int(it), C.byref(state), cur_stream()))
+
+    def gmres_solve_y(self, m, maxiter, R, y, yy):
+        self.launches += 1
+        check(lib.kb_gmres_solve_y(self.ws.handle, self.k, int(m), int(maxiter), ptr(R), ptr(y),
+                                   ptr(yy), cur_stream()))
+
+    def basis_combine(self, m, yy, Vbuf, x0, out):
+        self.launches += 1
+        check(lib.kb_basis_combine(self.ws.handle, self.n, self.k, int(m), ptr(yy), ptr(Vbuf),
+                                   Vbuf.stride(0) if Vbuf is not None and Vbuf.dim() == 3
+                                   else self.n * self.k,
+                                   ptr(x0), ptr(out), cur_stream()))
+
+    # -- Householder
+    def house_make(self, off, x, v, params, scratch):
+        self.launches += 3
+        check(lib.kb_house_make(self.ws.handle, self.n, int(off), ptr(x), ptr(v), ptr(params),
+                                ptr(scratch), cur_stream()))
+
+    def poke(self, op, x, idx, s=None, val=0.0, dst=None):
+        self.launches += 1
+        check(lib.kb_poke(self.ws.handle, int(op), ptr(x), int(idx), ptr(s), float(val), ptr(dst),
+                          cur_stream()))

@@ -1,0 +1,254 @@
+"""Operator / inner-product protocol of the reference (``_helpers.py``) and
+the adapters that let the device solvers call user objects.
+
+Public mirrors (same names and meaning as the reference): ``Identity``,
+``Product``, ``LinearOperatorWrapper``, ``aslinearoperator``, ``Info``,
+``get_default_inner``.
+
+Internal: ``Problem`` normalises ``(A, b, x0)`` into contiguous fp64 CUDA
+tensors of shape (n, k) and remembers how the caller's arrays looked, so
+results, callbacks, custom ``inner`` functions and duck-typed operators see
+exactly the array kind and shape the reference would hand them (NumPy arrays
+if ``b`` was NumPy, CUDA tensors if ``b`` was a CUDA tensor).
+"""
+from __future__ import annotations
+
+import collections
+
+import numpy as np
+import torch
+
+from .csr import CsrMatrix
+from .device import as_device_matrix, require_cuda
+
+# reference _helpers.py:93-98
+Info = collections.namedtuple(
+    "IterInfo",
+    ["success", "xk", "numsteps", "resnorms", "num_operations", "arnoldi"],
+    defaults=(None, None),
+)
+
+
+class Identity:
+    """reference _helpers.py:26-36"""
+
+    dtype = np.dtype("u1")
+
+    @staticmethod
+    def __matmul__(x):
+        return x
+
+    @staticmethod
+    def rmatvec(x):
+        return x
+
+
+class Product:
+    """reference _helpers.py:39-48: operators applied right to left."""
+
+    def __init__(self, *operators):
+        self.operators = operators
+        self.dtype = np.result_type(*[np.dtype(op.dtype) for op in operators])
+
+    def __matmul__(self, x):
+        out = x.clone() if isinstance(x, torch.Tensor) else x.copy()
+        for op in self.operators[::-1]:
+            out = op @ out
+        return out
+
+
+class LinearOperatorWrapper:
+    """reference _helpers.py:51-80: adds ``rmatvec`` to an array-like."""
+
+    def __init__(self, array):
+        self._array = array
+        self._adj_array = None
+        self.shape = array.shape
+        self.dtype = array.dtype
+
+    def __matmul__(self, x):
+        return self._array @ x
+
+    matvec = __matmul__
+
+    def rmatvec(self, x):
+        if isinstance(self._array, np.ndarray):
+            return (self._array.T @ x.conj()).conj()
+        if self._adj_array is None:
+            self._adj_array = self._array.T.conj()
+        return self._adj_array @ x
+
+
+def aslinearoperator(A):
+    """reference _helpers.py:83-90"""
+    if not hasattr(A, "__matmul__"):
+        raise ValueError(f"Unknown linear operator A = {A}")
+    if hasattr(A, "rmatvec"):
+        return A
+    return LinearOperatorWrapper(A)
+
+
+def get_default_inner(b_shape):
+    """reference _helpers.py:101-110, for NumPy arrays and torch tensors."""
+
+    def inner_dot(x, y):
+        if isinstance(x, torch.Tensor):
+            return torch.dot(x, y)
+        return np.dot(x.conj(), y)
+
+    def inner_einsum(x, y):
+        if isinstance(x, torch.Tensor):
+            return torch.einsum("i...,i...->...", x, y)
+        return np.einsum("i...,i...->...", x.conj(), y)
+
+    return inner_dot if len(b_shape) == 1 else inner_einsum
+
+
+# ---------------------------------------------------------------------------
+# internal adapters
+# ---------------------------------------------------------------------------
+def _is_scipy_sparse(A):
+    try:
+        import scipy.sparse
+
+        return scipy.sparse.issparse(A)
+    except Exception:  # pragma: no cover
+        return False
+
+
+def to_csr_or_none(A, device):
+    """CsrMatrix for anything that *is* a matrix; None for duck-typed operators."""
+    if isinstance(A, CsrMatrix):
+        return A
+    if _is_scipy_sparse(A):
+        return CsrMatrix.from_scipy(A, device)
+    if isinstance(A, np.ndarray) and A.ndim == 2:
+        return CsrMatrix.from_dense(A, device)
+    if isinstance(A, torch.Tensor) and A.dim() == 2:
+        if A.is_complex():
+            raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
+        return CsrMatrix.from_torch(A, device)
+    return None
+
+
+def _dtype_is_complex(A):
+    dt = getattr(A, "dtype", None)
+    if dt is None:
+        return False
+    if isinstance(dt, torch.dtype):
+        return dt.is_complex
+    try:
+        return np.issubdtype(np.dtype(dt), np.complexfloating)
+    except TypeError:
+        return False
+
+
+class Problem:
+    """Normalised linear system on the device."""
+
+    def __init__(self, A, b, x0=None):
+        require_cuda()
+        self.is_torch = isinstance(b, torch.Tensor)
+        if not self.is_torch:
+            b = np.asarray(b)
+        # reference cg.py:99-101 / minres.py:83-85 / gmres.py:116-118
+        assert len(A.shape) == 2
+        assert A.shape[0] == A.shape[1]
+        assert A.shape[1] == b.shape[0]
+        if _dtype_is_complex(b) or _dtype_is_complex(A):
+            raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
+        self.user_shape = tuple(b.shape)
+        self.n = int(b.shape[0])
+        self.k = int(np.prod(self.user_shape[1:])) if len(self.user_shape) > 1 else 1
+        if self.is_torch and b.is_cuda:
+            self.device = b.device
+        else:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.b = as_device_matrix(b, self.device).reshape(self.n, self.k)
+        if x0 is None:
+            self.x0 = torch.zeros_like(self.b)
+        else:
+            self.x0 = as_device_matrix(x0, self.device).reshape(self.n, self.k).clone()
+        self.A = self.operator(A)
+        if self.A is None:
+            raise ValueError("A must be a matrix or a linear operator")
+        self.A_csr = self.A.csr  # CsrMatrix, or None for a duck-typed operator
+
+    # user-facing views -----------------------------------------------------
+    def to_user(self, t: torch.Tensor):
+        t = t.reshape(self.user_shape)
+        if self.is_torch:
+            return t
+        return t.cpu().numpy()
+
+    def from_user(self, a) -> torch.Tensor:
+        return as_device_matrix(a, self.device).reshape(self.n, self.k)
+
+    def scalars_to_user(self, s):
+        """(k,) host array -> what the reference's inner product returns for this
+        shape of b: a NumPy scalar for 1-D b, an array of shape b.shape[1:] else."""
+        s = np.asarray(s, dtype=np.float64)
+        if len(self.user_shape) == 1:
+            return np.float64(s.reshape(-1)[0])
+        return s.reshape(self.user_shape[1:])
+
+    # operators ---------------------------------------------------------------
+    def operator(self, op):
+        """callable(device (n,k) tensor) -> new device (n,k) tensor, or None
+        for the identity."""
+        if op is None or isinstance(op, Identity):
+            return None
+        csr = op if isinstance(op, CsrMatrix) else to_csr_or_none(op, self.device)
+        if csr is not None:
+            if csr.shape[0] != self.n or csr.shape[1] != self.n:
+                raise ValueError("operator shape does not match the right-hand side")
+            return _CsrApply(csr)
+        if not hasattr(op, "__matmul__"):
+            raise ValueError(f"Unknown linear operator {op}")
+        return _UserApply(op, self)
+
+    def inner(self, fn):
+        """callable(x_dev, y_dev) -> host float64 array (k,) for a user inner product."""
+
+        def call(x, y):
+            v = fn(self.to_user(x), self.to_user(y))
+            if isinstance(v, torch.Tensor):
+                v = v.detach().cpu().numpy()
+            v = np.asarray(v)
+            if np.any(np.imag(v) != 0.0):
+                raise ValueError("inner product <x, M x> gave nonzero imaginary part")
+            v = np.real(v).astype(np.float64).reshape(-1)
+            if v.size == 1 and self.k > 1:
+                v = np.full(self.k, v[0])
+            if v.size != self.k:
+                raise ValueError(
+                    f"inner product returned {v.size} values for {self.k} right-hand sides")
+            return v
+
+        return call
+
+
+class _CsrApply:
+    def __init__(self, csr):
+        self.csr = csr
+
+    def __call__(self, x):
+        return self.csr.matvec_device(x)
+
+
+class _UserApply:
+    """Duck-typed operator (``shape``/``dtype``/``__matmul__``, reference
+    tests/test_solvers.py:212-243).  It is called with the caller's own array
+    kind: host arrays make a device->host->device trip per application, which
+    is the price of an opaque host operator, not a fallback of ours."""
+
+    csr = None
+
+    def __init__(self, op, prob):
+        self.op, self.prob = op, prob
+
+    def __call__(self, x):
+        y = self.prob.from_user(self.op @ self.prob.to_user(x))
+        if y.data_ptr() == x.data_ptr():  # identity-like operator: never alias the input
+            y = y.clone()
+        return y
