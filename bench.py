@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""Benchmark of the krylov hot path on B200 (contract: see the task brief).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm
+
+Workload (BASELINE.json configs[4], the one the metric is quoted on; it fits
+one GPU): fp64 CG on the 7-point 3-D Poisson matrix, 512^3 unknowns, CSR with
+int32 indices, row-partitioned in z-slabs over N GPUs (strong scaling: the
+problem is fixed as N grows).  A *step* is one CG iteration of the fused path
+(p update, SpMV fused with <p,Ap>, x/r update fused with <r,r>, record).
+
+* `value`  : iterations/s, K timed iterations with every operand resident in
+             HBM (CUDA events on the launching stream, barrier + synchronize on
+             both sides, max over ranks).  24 GB of operands per iteration, far
+             larger than L2.
+* `e2e`    : the same metric through the public API from HOST buffers:
+             `krylov_b200.cg(A_scipy_csr_on_host, b_host, tol=1e-8)` -- a
+             complete solve including the host->device copy of the CSR arrays
+             and b (pinned memory) and the device->host copy of the solution.
+             One solve; iterations/s = numsteps / wall time.
+* `roofline`: the dominant kernel (SpMV fused with the dot), algorithmic bytes
+             12 nnz + 4(n+1) + 16 n per launch over its CUDA-event duration,
+             against MEASURED_PEAKS.json's HBM copy bandwidth.
+* `cpu_baseline`: the oracle port (NumPy/SciPy restatement of the reference)
+             on the host cores, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cg_iterations_per_sec"
+UNIT = "it/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512, help="grid points per dimension")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-size", type=int, default=0, help="grid size of the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_name(n):
+    return (f"krylov.cg fp64, 7-point 3D Poisson {n}^3 ({n**3:,} unknowns), CSR int32, single RHS, "
+            "row-partitioned z-slabs")
+
+
+def cg_step_bytes(nnz, n, k=1):
+    """CG step (M = Ml = I) = 12 nnz + 4(n+1) + 92 n k."""
+    return 12 * nnz + 4 * (n + 1) + 92 * n * k
+
+
+# --------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample
+# --------------------------------------------------------------------------
+def cpu_sample_size(full, steps, forced=0):
+    if forced:
+        return forced
+    # ~0.035 us per unknown per iteration measured for the NumPy/SciPy loop
+    # (14.7 it/s at 128^3); keep the timed part near 20 s
+    for cand in (256, 192, 128, 96, 64):
+        if cand <= full and cand ** 3 * 3.5e-8 * max(steps, 1) <= 25.0:
+            return cand
+    return min(64, full)
+
+
+def run_cpu_oracle(full_n, steps, warmup, forced=0):
+    """Times `steps` CG iterations of the oracle (tol = atol = 0 so the stopping
+    test never fires) on the 3-D Poisson matrix of a smaller grid
+    and scales iterations/s by the ratio of unknowns (per-iteration work of the
+    NumPy/SciPy loop is linear in n once out of cache)."""
+    from krylov_b200 import stencils as st  # pure NumPy generators
+    from oracle import krylov_oracle as orc
+
+    m = cpu_sample_size(full_n, steps, forced)
+    A = st.poisson3d(m)
+    rng = np.random.default_rng(0)
+    b = A @ rng.standard_normal(A.shape[0])
+    orc.cg(A, b, tol=0.0, atol=0.0, maxiter=max(warmup, 1))
+    t0 = time.perf_counter()
+    _, info = orc.cg(A, b, tol=0.0, atol=0.0, maxiter=steps)
+    dt = time.perf_counter() - t0
+    assert info.numsteps == steps
+    its_sample = steps / dt
+    scale = (m / full_n) ** 3
+    try:
+        from threadpoolctl import threadpool_info
+
+        blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        blas_threads = os.cpu_count() or 1
+    return {
+        "value": its_sample * scale,
+        "unit": UNIT,
+        "cores": blas_threads,
+        "kind": "port",
+        "sample": (f"oracle/krylov_oracle.cg (NumPy {np.__version__} + SciPy CSR SpMV, which is "
+                   f"single-threaded; BLAS threads {blas_threads} of {os.cpu_count()} cores) on 3D "
+                   f"Poisson {m}^3, {steps} fixed iterations after {max(warmup,1)} warm-up: "
+                   f"{its_sample:.3f} it/s, scaled by ({m}/{full_n})^3 to the {full_n}^3 workload"),
+        "sample_its_per_s": its_sample,
+        "sample_grid": m,
+        "seconds": dt,
+    }
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(args.steps, 1)
+    cb = run_cpu_oracle(args.size, steps, args.warmup, args.cpu_size)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.size), "sample": cb["sample"]},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, measured)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import krylov_b200 as kb
+    from krylov_b200.cg import FusedCG
+    from krylov_b200.generate import device_stencil7
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: krylov_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N = args.size
+    K, W = max(args.steps, 1), max(args.warmup, 3)
+
+    # ---- synthetic input, generated in HBM (seeded): A (z-slab of this rank), b = A x*
+    if world > 1:
+        from krylov_b200.dist import dist_stencil7
+
+        A = dist_stencil7(N, N, N)
+        n_loc = A.shape[0]
+    else:
+        A = device_stencil7(N, N, N)
+        n_loc = A.shape[0]
+    n_glob = N ** 3
+    nnz_glob = 7 * n_glob - 6 * N * N
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    xs = torch.randn((n_loc, 1), generator=gen, dtype=torch.float64, device=dev)
+    b = A.matvec_device(xs)
+    x0 = torch.zeros_like(b)
+    del xs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: exactly K iterations of the fused CG path, operands resident
+    st = FusedCG(A, b, x0, tol=0.0, atol=0.0)  # criterion 0: the stopping test never fires
+    hist0 = st.hist.data_ptr()  # every record lands in history row 0 (not read in the bench)
+    it = 0
+    for _ in range(W):
+        st.enqueue(it, hist0 - (it + 1) * 8)
+        it += 1
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = st.ops.launches
+    st.spmv_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        st.enqueue(it, hist0 - (it + 1) * 8)
+        it += 1
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    spmv_ms = float(np.mean([a.elapsed_time(bb) for a, bb in st.spmv_events]))
+    st.spmv_events = None
+    launches = st.ops.launches - launches0
+    st.ops.gate(None, 0)
+    if world > 1:
+        t = torch.tensor([ms_total, spmv_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, spmv_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    its = K / (ms_total / 1e3)
+    rho_final = float(st.sl[it % 2][0])
+    if not np.isfinite(rho_final):
+        raise SystemExit("bench: CG produced a non-finite residual")
+    info_sched = A.info()
+    del st
+    torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant kernel (SpMV fused with <p, Ap>)
+    peak, peak_src = load_peaks()
+    spmv_bytes = A.spmv_bytes(1)  # per launch, this rank's rows
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tfile):
+        try:
+            tj = json.load(open(tfile))
+            if tj.get("grid") == N and world == 1:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    step_bytes = cg_step_bytes(nnz_glob, n_glob)
+    roofline = {
+        "bound": "hbm", "kernel": "kb_spmv_stream_kernel (A p fused with <p, Ap>)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": spmv_bytes, "launch_ms": spmv_ms,
+        "whole_step": {"algorithmic_bytes": step_bytes,
+                       "achieved_GBs_aggregate": step_bytes * its / 1e9,
+                       "frac_of_aggregate_peak": step_bytes * its / 1e9 / (peak * world)},
+    }
+
+    # ---- end to end: a full solve from host buffers through the public API
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, A, b, world, rank, dev, barrier)
+
+    # ---- CPU baseline (rank 0, N == 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = run_cpu_oracle(N, 10, 2, args.cpu_size)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(N), "n": n_glob, "nnz": nnz_glob,
+                       "parallelism": f"rows/{world}" if world > 1 else "single GPU",
+                       "spmv_schedule": info_sched.get("schedule"),
+                       "l2": "inputs larger than L2 (24 GB of operands per step)",
+                       "tol": "0 (fixed K iterations; the stopping test never fires)"},
+            "clocks": clk, "gpu_launches": launches, "roofline": roofline,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, A, b, world, rank, dev, barrier):
+    """One complete CG solve through the public API starting from host memory."""
+    import torch
+
+    import krylov_b200 as kb
+
+    if world > 1:
+        # the row blocks live on their GPUs by construction; the end-to-end call moves
+        # this rank's right-hand side and solution through pinned host memory
+        b_host = torch.empty(b.shape[0], dtype=torch.float64).pin_memory()
+        b_host.copy_(b.reshape(-1))
+        barrier()
+        t0 = time.perf_counter()
+        sol, info = kb.cg(A, b_host.to(dev, non_blocking=True), tol=1e-8, maxiter=20000)
+        x_host = torch.empty(b.shape[0], dtype=torch.float64).pin_memory()
+        x_host.copy_(info.xk.reshape(-1))
+        barrier()
+        dt = time.perf_counter() - t0
+        h2d, d2h = b.numel() * 8 * world, b.numel() * 8 * world
+        how = ("krylov_b200.cg(DistCsrMatrix resident, b from pinned host memory, tol=1e-8): "
+               "per-rank H2D of b and D2H of x inside the timed region")
+    else:
+        import scipy.sparse
+
+        n = A.shape[0]
+        # host copies of the CSR arrays in pinned memory (set-up, untimed)
+        rp = torch.empty(n + 1, dtype=torch.int32).pin_memory()
+        ci = torch.empty(A.nnz, dtype=torch.int32).pin_memory()
+        va = torch.empty(A.nnz, dtype=torch.float64).pin_memory()
+        rp.copy_(A.rowptr)
+        ci.copy_(A.colidx[: A.nnz])
+        va.copy_(A.vals[: A.nnz])
+        b_host = torch.empty(n, dtype=torch.float64).pin_memory()
+        b_host.copy_(b.reshape(-1))
+        torch.cuda.synchronize()
+        A_host = scipy.sparse.csr_matrix((va.numpy(), ci.numpy(), rp.numpy()), shape=(n, n),
+                                         copy=False)
+        A_host.has_canonical_format = True
+        b_np = b_host.numpy()
+        del A
+        torch.cuda.empty_cache()
+        barrier()
+        t0 = time.perf_counter()
+        sol, info = kb.cg(A_host, b_np, tol=1e-8, maxiter=20000)  # numpy in -> numpy out
+        dt = time.perf_counter() - t0
+        h2d = rp.numel() * 4 + ci.numel() * 4 + va.numel() * 8 + n * 8
+        d2h = n * 8
+        how = ("krylov_b200.cg(scipy.sparse.csr_matrix in pinned host memory, NumPy b, tol=1e-8) "
+               "-> NumPy x: CSR + b host->device and x device->host inside the timed region")
+    steps = int(info.numsteps)
+    res = np.asarray(info.resnorms, dtype=float)
+    return {"value": steps / dt, "unit": UNIT,
+            "h2d_bytes_per_step": h2d / max(steps, 1), "d2h_bytes_per_step": d2h / max(steps, 1),
+            "solve_seconds": dt, "numsteps": steps, "success": bool(info.success),
+            "relres": float(res[-1] / res[0]), "how": how}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

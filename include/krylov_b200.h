@@ -45,6 +45,9 @@ typedef struct kb_ws_s* kb_ws_t;   /* reduction workspace + gate  */
 int kb_version(void);
 int kb_last_error(char* buf, size_t len);
 int kb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* developer tunables: key 0 stream-kernel configuration (0..5), key 1 stream CTAs/SM
+ * (0 = default), key 2 CTAs/SM of the vector and row-wise grids */
+int kb_tune(int key, int value);
 
 /* --- workspace -------------------------------------------------------- */
 int kb_ws_create(kb_ws_t* ws, int max_k);
@@ -80,10 +83,12 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y,
             int mode, const double* z, const double* coef,
             int dot, const double* w, double* out, void* stream);
 
-/* boundary rows of a row-partitioned matrix: for i in rows[]:
- *   y[i] += sum_j hv[j] * xh[hc[j]];  out[c] = sum_i w[i,c] * (added part)  (dot 1)
- *   or, dot 2, out[c] = sum_i (2*y_old*h + h*h) correction is NOT used: dot 2 is unsupported here. */
-int kb_spmv_halo_add(kb_ws_t ws, int k, int64_t n_brows, const int32_t* rows,
+/* boundary rows of a row-partitioned matrix, after the halo
+ * entries xh have arrived: for i < n_brows, row = rows[i]:
+ *   h = sum_j hval[j] * xh[hcol[j], c];  y[row, c] += sign * h
+ *   dot 1: out[c] += sum_i w[row, c] * sign * h   (accumulates onto the slot the
+ *          local kb_spmv wrote, so one all-reduce covers the whole inner product) */
+int kb_spmv_halo_add(kb_ws_t ws, int k, int64_t n_brows, double sign, const int32_t* rows,
                      const int32_t* hrowptr, const int32_t* hcol, const double* hval,
                      const double* xh, double* y, int dot, const double* w, double* out,
                      void* stream);
@@ -123,10 +128,11 @@ int kb_add(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, doubl
            void* stream);
 
 /* --- Lanczos / MINRES (arnoldi.py:237-281, minres.py:168-236) ---------- */
-/* w -= sign*coef[c] * u, then out[c] = <z, w> (dot 1) or <w, w> (dot 2) or nothing.
- * MGS step (arnoldi.py:157-162) and Lanczos alpha-step (arnoldi.py:264-267). */
-int kb_axpy_dot(kb_ws_t ws, int64_t n, int k, const double* coef, const double* u, double* w,
-                int dot, const double* z, double* out, void* stream);
+/* w -= (scale[0]*coef[c]) * u, then out[c] = <z, w> (dot 1) or <w, w> (dot 2) or nothing.
+ * scale may be NULL (= 1).  MGS step (arnoldi.py:157-162), Lanczos alpha-step
+ * (arnoldi.py:264-267); with scale = beta a Householder reflector (householder.py:62). */
+int kb_axpy_dot(kb_ws_t ws, int64_t n, int k, const double* coef, const double* scale,
+                const double* u, double* w, int dot, const double* z, double* out, void* stream);
 /* per-column state of the MINRES recurrences; all device arrays of k doubles
  * unless noted.  One launch of one block. (minres.py:190-228, givens.py:35-45) */
 typedef struct {
@@ -179,6 +185,10 @@ int kb_basis_combine(kb_ws_t ws, int64_t n, int k, int m, const double* yy, cons
  * params[0..3] = alpha, beta, xnorm, sigma2-taken-from-slot.  Two launches. */
 int kb_house_make(kb_ws_t ws, int64_t n, int64_t off, const double* x, double* v,
                   double* params, double* scratch, void* stream);
+/* h_out[0] = |(w[off] - beta v[off] tau) * alpha|, params = output of kb_house_make,
+ * tau = <v, w>  (arnoldi.py:83-85) */
+int kb_house_hlast(kb_ws_t ws, const double* w, int64_t off, const double* v, const double* params,
+                   const double* tau, double* h_out, void* stream);
 /* single-element edits used by the Householder Arnoldi step:
  *  op 0: x[idx] *= s[0];  op 1: x[idx] = val;  op 2: dst[0] = x[idx] */
 int kb_poke(kb_ws_t ws, int op, double* x, int64_t idx, const double* s, double val,

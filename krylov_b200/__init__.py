@@ -17,6 +17,11 @@ from .operators import (  # noqa: F401
     get_default_inner,
 )
 from .cg import cg  # noqa: F401
+from .minres import minres  # noqa: F401
+from .gmres import gmres  # noqa: F401
+from .givens import givens  # noqa: F401
+from .householder import Householder  # noqa: F401
+from .arnoldi import ArnoldiHouseholder, ArnoldiLanczos, ArnoldiMGS  # noqa: F401
 from . import stencils  # noqa: F401
 
 __version__ = "0.1.0"

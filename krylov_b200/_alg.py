@@ -18,7 +18,7 @@ from .device import Ops
 class Alg:
     def __init__(self, prob, inner=None):
         self.prob = prob
-        self.ops = Ops(prob.n, prob.k, prob.device)
+        self.ops = Ops(prob.n, prob.k, prob.device, comm=prob.comm)
         self._user_inner = None if inner is None else prob.inner(inner)
         self._slot = self.ops.slots(1)[0]
         self._cbuf = self.ops.slots(1)[0]
@@ -27,8 +27,9 @@ class Alg:
     def coef(self, a):
         """host (k,) -> device (k,) coefficient tensor (a fresh one per call:
         launches are asynchronous and must not see a later overwrite)."""
-        a = np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(-1), (self.prob.k,))
-        return torch.from_numpy(np.ascontiguousarray(a)).to(self.prob.device)
+        a = np.array(np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(-1),
+                                     (self.prob.k,)))  # writable copy
+        return torch.from_numpy(a).to(self.prob.device)
 
     def inner(self, x, y):
         """<x, y> column-wise -> host float64 (k,).  Default: deterministic

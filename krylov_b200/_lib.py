@@ -51,6 +51,7 @@ class GmresState(C.Structure):
 SIGNATURES = {
     "kb_version": [],
     "kb_last_error": [C.c_char_p, C.c_size_t],
+    "kb_tune": [i32, i32],
     "kb_device_info": [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
     "kb_ws_create": [C.POINTER(vp), i32],
     "kb_ws_destroy": [vp],
@@ -61,7 +62,7 @@ SIGNATURES = {
     "kb_csr_get_info": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32),
                         C.POINTER(i32)],
     "kb_spmv": [vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp],
-    "kb_spmv_halo_add": [vp, i32, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
+    "kb_spmv_halo_add": [vp, i32, i64, f64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
     "kb_pack_rows": [vp, i32, i64, vp, vp, vp, vp],
     "kb_dot": [vp, i64, i32, vp, vp, vp, vp],
     "kb_cg_update_xr": [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
@@ -70,7 +71,8 @@ SIGNATURES = {
     "kb_xpby": [vp, i64, i32, vp, vp, vp, vp],
     "kb_div_scale": [vp, i64, i32, vp, vp, vp, vp],
     "kb_add": [vp, i64, i32, vp, vp, vp, vp],
-    "kb_axpy_dot": [vp, i64, i32, vp, vp, vp, i32, vp, vp, vp],
+    "kb_axpy_dot": [vp, i64, i32, vp, vp, vp, vp, i32, vp, vp, vp],
+    "kb_house_hlast": [vp, vp, i64, vp, vp, vp, vp, vp],
     "kb_minres_scalar": [vp, i32, i32, C.POINTER(MinresState), vp],
     "kb_minres_update": [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     "kb_gmres_scalar": [vp, i32, i32, C.POINTER(GmresState), vp],

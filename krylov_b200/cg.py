@@ -90,86 +90,127 @@ class _LanczosLog:
 
 
 # ---------------------------------------------------------------------------
-def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback):
-    A, b, x0 = prob.A_csr, prob.b, prob.x0
-    n, k, dev = prob.n, prob.k, prob.device
-    ops = Ops(n, k, dev)
-    r = ops.vec(zero=False)
-    Ap = ops.vec(zero=False)
-    yk = ops.vec(zero=True)
-    sl = ops.slots(4)  # rho (ping-pong: rho_i lives in sl[i % 2]), <p,Ap>, scratch
-    stop_at = torch.full((1,), INT_MAX, dtype=torch.int32, device=dev)
-    hist = torch.zeros((_BATCH_MAX, k), dtype=torch.float64, device=dev)
+class FusedCG:
+    """Device-resident state of the fused CG iteration (M = Ml = I, default
+    inner product).  ``enqueue(i)`` launches iteration i (no host sync);
+    ``run(nb)`` enqueues a gated batch and reads back once.
 
-    # initial residual r0 = b - A x0 fused with <r0, r0>  (cg.py:116)
-    ops.gate(None, 0)
-    ops.spmv(A, x0, r, mode=2, z=b, dot=2, out=sl[0])
-    rho0 = sl[0].cpu().numpy().copy()
-    nrm0 = np.sqrt(rho0)
+    ``A`` is a CsrMatrix or a row-partitioned DistCsrMatrix; in the latter case
+    every reduction slot is summed over ranks by ``A.comm`` right after the
+    kernel that produced it (one small all-reduce per inner product)."""
+
+    def __init__(self, A, b, x0, tol, atol):
+        n, k = b.shape
+        self.A, self.b, self.x0 = A, b, x0
+        self.n, self.k, self.dev = n, k, b.device
+        self.comm = getattr(A, "comm", None)
+        self.ops = ops = Ops(n, k, self.dev, comm=self.comm)
+        self.r = ops.vec(zero=False)
+        self.Ap = ops.vec(zero=False)
+        self.yk = ops.vec(zero=True)
+        # rho ping-pong (rho_i in sl[i % 2]), <p,Ap>, scratch
+        self.sl = ops.slots(4)
+        self.stop_at = torch.full((1,), INT_MAX, dtype=torch.int32, device=self.dev)
+        self.hist = torch.zeros((_BATCH_MAX, k), dtype=torch.float64, device=self.dev)
+        self.spmv_events = None  # bench hook: list of (start, end) CUDA events around A @ p
+        # initial residual r0 = b - A x0 fused with <r0, r0>  (cg.py:116)
+        ops.gate(None, 0)
+        self.rho0 = self._residual_norm2(x0, self.r, self.sl[0])
+        self.nrm0 = np.sqrt(self.rho0)
+        self.crit = np.maximum(tol * self.nrm0, atol)  # cg.py:154
+        self.crit_d = torch.from_numpy(np.ascontiguousarray(self.crit)).to(self.dev)
+        self.p = self.r.clone()
+        self.kk = 0
+
+    def _residual_norm2(self, x, out_vec, slot):
+        """out_vec = b - A x; returns host <out_vec, out_vec> (k,)."""
+        self.ops.spmv(self.A, x, out_vec, mode=2, z=self.b, dot=2, out=slot)
+        return slot.cpu().numpy().copy()
+
+    def explicit_resnorm(self, xk):
+        return np.sqrt(self._residual_norm2(xk, self.Ap, self.sl[3]))
+
+    def current_x(self):
+        xk = torch.empty_like(self.yk)
+        self.ops.add(xk, self.x0, self.yk)
+        return xk
+
+    def enqueue(self, i, hist_ptr):
+        ops, sl = self.ops, self.sl
+        cur, nxt = sl[i % 2], sl[(i + 1) % 2]
+        ops.gate(self.stop_at, i)  # iteration i is a no-op once a step <= i converged
+        if i > 0:
+            ops.cg_update_p(cur, nxt, self.r, self.p)  # omega = rho_i / rho_{i-1}; p = r + omega p
+        if self.spmv_events is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        ops.spmv(self.A, self.p, self.Ap, dot=1, w=self.p, out=sl[2])  # Ap = A p, <p, Ap>
+        if self.spmv_events is not None:
+            e1.record()
+            self.spmv_events.append((e0, e1))
+        ops.cg_update_xr(cur, sl[2], None, self.p, self.Ap, self.yk, self.r, nxt)  # rho_{i+1}
+        ops.cg_record(i + 1, nxt, self.crit_d, hist_ptr, self.stop_at)
+
+    def run(self, nb):
+        """Enqueue iterations kk .. kk+nb-1, then one host read.  Returns the
+        residual norms of the steps that actually ran (the rest were gated)."""
+        kk, k = self.kk, self.k
+        self.stop_at.fill_(INT_MAX)
+        hist_ptr = self.hist.data_ptr() - (kk + 1) * k * 8  # history row kk+1 == hist[0]
+        for i in range(kk, kk + nb):
+            self.enqueue(i, hist_ptr)
+        self.ops.gate(None, 0)
+        s = int(self.stop_at.item())  # one host read per batch
+        done = min(s, kk + nb) - kk
+        rows = self.hist[:done].cpu().numpy()
+        self.kk += done
+        return [rows[j].copy() for j in range(done)]
+
+
+def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback):
+    st = FusedCG(prob.A_csr, prob.b, prob.x0, tol, atol)
+    ops, crit = st.ops, st.crit
     if callback is not None:
-        callback(prob.to_user(x0), prob.to_user(r))
-    resn = [nrm0]
-    crit = np.maximum(tol * nrm0, atol)  # cg.py:154
-    crit_d = torch.from_numpy(crit).to(dev)
-    p = r.clone()
-    log = _LanczosLog(prob, ops, maxiter, r, r, nrm0) if return_arnoldi else None
+        callback(prob.to_user(prob.x0), prob.to_user(st.r))
+    resn = [st.nrm0]
+    log = _LanczosLog(prob, ops, maxiter, st.r, st.r, st.nrm0) if return_arnoldi else None
 
     step_by_step = callback is not None or return_arnoldi
     batch = 1 if step_by_step else _BATCH_MIN
-    kk = 0
     success = False
     xk = None
     while True:
         if np.all(resn[-1] <= crit):
             # "oh really?" -- explicit residual of xk = x0 + yk  (cg.py:156-164)
-            if xk is None:
-                xk = torch.empty_like(yk)
-                ops.add(xk, x0, yk)
-            ops.spmv(A, xk, Ap, mode=2, z=b, dot=2, out=sl[3])
-            resn[-1] = np.sqrt(sl[3].cpu().numpy().copy())
+            xk = st.current_x() if xk is None else xk
+            resn[-1] = st.explicit_resnorm(xk)
             if np.all(resn[-1] <= crit):
                 success = True
                 break
-        if kk == maxiter:
+        if st.kk == maxiter:
             break
-        nb = min(batch, maxiter - kk)
-        stop_at.fill_(INT_MAX)
-        hist_ptr = hist.data_ptr() - (kk + 1) * k * 8  # row (kk+1) of the history == hist[0]
-        for i in range(kk, kk + nb):
-            cur, nxt = sl[i % 2], sl[(i + 1) % 2]
-            ops.gate(stop_at, i)  # iteration i is a no-op once a step <= i converged
-            if i > 0:
-                ops.cg_update_p(cur, nxt, r, p)  # omega = rho_i / rho_{i-1}; p = r + omega p
-            ops.spmv(A, p, Ap, dot=1, w=p, out=sl[2])  # Ap = A p, <p, Ap>
-            ops.cg_update_xr(cur, sl[2], None, p, Ap, yk, r, nxt)  # rho_{i+1} -> nxt
-            ops.cg_record(i + 1, nxt, crit_d, hist_ptr, stop_at)
-        ops.gate(None, 0)
-        s = int(stop_at.item())  # one host read per batch
-        done = min(s, kk + nb) - kk
-        rows = hist[:done].cpu().numpy()
+        kk = st.kk
+        resn.extend(st.run(min(batch, maxiter - kk)))
+        xk = None
         if log is not None:  # batch == 1 here
-            sv = sl.cpu().numpy()
+            sv = st.sl.cpu().numpy()
             rho_i, rho_n, pAp = sv[kk % 2], sv[(kk + 1) % 2], sv[2]
             alpha = rho_i / nz(pAp)
             omega = rho_i / nz(log.rho_prev) if kk > 0 else None
-            log.step(kk, r, r, alpha, omega, rho_n, rho_i)
+            log.step(kk, st.r, st.r, alpha, omega, rho_n, rho_i)
             log.rho_prev = rho_i
-        for j in range(done):
-            resn.append(rows[j].copy())
-        kk += done
-        xk = None
         if callback is not None:
-            xk = torch.empty_like(yk)
-            ops.add(xk, x0, yk)
-            callback(prob.to_user(xk), prob.to_user(r))
+            xk = st.current_x()
+            callback(prob.to_user(xk), prob.to_user(st.r))
         if not step_by_step:
             batch = min(2 * batch, _BATCH_MAX)
 
     if xk is None:
-        xk = torch.empty_like(yk)
-        ops.add(xk, x0, yk)
+        xk = st.current_x()
     prob.launches = ops.launches
-    return _finish(prob, success, xk, kk, resn, log.result(kk) if log is not None else None)
+    return _finish(prob, success, xk, st.kk, resn,
+                   log.result(st.kk) if log is not None else None)
 
 
 # ---------------------------------------------------------------------------

@@ -86,8 +86,9 @@ class CsrMatrix:
             raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
         if A.nnz >= 2**31:
             raise ValueError("nnz must fit int32")
-        return cls(A.indptr.astype(np.int32), A.indices.astype(np.int32),
-                   A.data.astype(np.float64), A.shape, device)
+        # no host-side copies when the dtypes already match (pinned arrays stay pinned)
+        return cls(np.asarray(A.indptr, dtype=np.int32), np.asarray(A.indices, dtype=np.int32),
+                   np.asarray(A.data, dtype=np.float64), A.shape, device)
 
     @classmethod
     def from_dense(cls, A, device=None):
@@ -136,6 +137,8 @@ class CsrMatrix:
         ops.launches += 1
         check(lib.kb_spmv(self.handle, ops.ws.handle, ops.k, ptr(x), ptr(y), int(mode), ptr(z),
                           ptr(coef), int(dot), ptr(w), ptr(out), cur_stream()))
+        if dot:
+            ops.reduce_over_ranks(out)
 
     def _ops_for(self, k):
         o = self._ops.get(k)

@@ -31,12 +31,13 @@ struct kb_csr_s {
   int forced;    // user override (0 = auto)
 };
 
-// stream-kernel configuration: 4 stages x 2048 nnz (24 KB/stage) -> 2 CTAs/SM
-#define KB_ST_STAGES 4
-#define KB_ST_CAP 2048
-#define KB_ST_CTAS_PER_SM 2
 
 static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+
+// runtime tunables (kb_tune): stream-kernel configuration and grid sizing
+static int g_stream_cfg = 0;
+static int g_stream_ctas = 0;  // 0 = configuration default
+int g_vec_ctas = KB_CTAS_PER_SM;
 
 extern "C" {
 
@@ -47,6 +48,15 @@ int kb_last_error(char* buf, size_t len) {
   strncpy(buf, kb_errbuf, len - 1);
   buf[len - 1] = 0;
   return KB_OK;
+}
+
+int kb_tune(int key, int value) {
+  switch (key) {
+    case 0: g_stream_cfg = value; return KB_OK;
+    case 1: g_stream_ctas = value; return KB_OK;
+    case 2: g_vec_ctas = value > 0 ? value : KB_CTAS_PER_SM; return KB_OK;
+    default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
+  }
 }
 
 int kb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
@@ -192,13 +202,13 @@ int kb_csr_get_info(kb_csr_t h, int64_t* n_rows, int64_t* n_cols, int64_t* nnz, 
 // ----------------------------------------------------------------- SpMV --
 }  // extern "C"
 
-template <int DOT>
-static int kb_launch_stream(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
-                            const double* z, const double* coef, const double* w, double* out,
-                            cudaStream_t st) {
-  typedef KbStreamSmem<KB_ST_STAGES, KB_ST_CAP> Smem;
+template <int ROWS, int STAGES, int CAP, int DOT>
+static int kb_launch_stream_cfg(kb_csr_s* A, kb_ws_s* ws, int ctas_default, const double* x,
+                                double* y, int mode, const double* z, const double* coef,
+                                const double* w, double* out, cudaStream_t st) {
+  typedef KbStreamSmem<STAGES, CAP> Smem;
   static bool configured[64] = {false};  // per device (function attributes are per device)
-  auto kern = kb_spmv_stream_kernel<KB_ST_STAGES, KB_ST_CAP, DOT>;
+  auto kern = kb_spmv_stream_kernel<ROWS, STAGES, CAP, DOT>;
   int dev = 0;
   KB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !configured[dev]) {
@@ -206,14 +216,30 @@ static int kb_launch_stream(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y
                                  (int)sizeof(Smem)));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  const int n_tiles = (int)((A->n_rows + KB_ST_ROWS - 1) / KB_ST_ROWS);
-  int grid = ws->num_sms * KB_ST_CTAS_PER_SM;
+  const int n_tiles = (int)((A->n_rows + ROWS - 1) / ROWS);
+  int grid = ws->num_sms * (g_stream_ctas > 0 ? g_stream_ctas : ctas_default);
   if (grid > n_tiles) grid = n_tiles;
   if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
-  kern<<<grid, KB_ST_THREADS, sizeof(Smem), st>>>((int)A->n_rows, n_tiles, A->rowptr, A->colidx,
-                                                  A->vals, x, y, mode, z, coef, w, out, kb_red(ws));
+  kern<<<grid, ROWS + 32, sizeof(Smem), st>>>((int)A->n_rows, n_tiles, A->rowptr, A->colidx,
+                                              A->vals, x, y, mode, z, coef, w, out, kb_red(ws));
   KB_LAUNCH_CHECK();
   return KB_OK;
+}
+
+template <int DOT>
+static int kb_launch_stream(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                            const double* z, const double* coef, const double* w, double* out,
+                            cudaStream_t st) {
+  // default: 512-row tiles, 2 stages x 4096 nnz (96 KB smem), 2 CTAs/SM = 1088 threads/SM:
+  // best of the sweep in profiles/r1_spmv_sweep.txt (occupancy, not stage depth, was the lever)
+  switch (g_stream_cfg) {
+    case 1: return kb_launch_stream_cfg<256, 2, 2048, DOT>(A, ws, 4, x, y, mode, z, coef, w, out, st);
+    case 2: return kb_launch_stream_cfg<256, 3, 2048, DOT>(A, ws, 3, x, y, mode, z, coef, w, out, st);
+    case 3: return kb_launch_stream_cfg<128, 3, 1024, DOT>(A, ws, 4, x, y, mode, z, coef, w, out, st);
+    case 4: return kb_launch_stream_cfg<256, 4, 2048, DOT>(A, ws, 2, x, y, mode, z, coef, w, out, st);
+    case 5: return kb_launch_stream_cfg<128, 2, 1024, DOT>(A, ws, 8, x, y, mode, z, coef, w, out, st);
+    default: return kb_launch_stream_cfg<512, 2, 4096, DOT>(A, ws, 2, x, y, mode, z, coef, w, out, st);
+  }
 }
 
 extern "C" {
@@ -255,7 +281,7 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
   return KB_OK;
 }
 
-int kb_spmv_halo_add(kb_ws_t ws, int k, int64_t n_brows, const int32_t* rows,
+int kb_spmv_halo_add(kb_ws_t ws, int k, int64_t n_brows, double sign, const int32_t* rows,
                      const int32_t* hrowptr, const int32_t* hcol, const double* hval,
                      const double* xh, double* y, int dot, const double* w, double* out,
                      void* stream) {
@@ -264,19 +290,16 @@ int kb_spmv_halo_add(kb_ws_t ws, int k, int64_t n_brows, const int32_t* rows,
   KB_REQUIRE(dot == 0 || dot == 1, "dot must be 0 or 1");
   KB_REQUIRE(dot == 0 || (w != nullptr && out != nullptr), "dot 1 needs w and out");
   cudaStream_t st = S(stream);
-  if (n_brows == 0) {
-    if (dot) KB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * k, st));
-    return KB_OK;
-  }
+  if (n_brows == 0) return KB_OK;  // nothing to add (the dot slot keeps the local part)
   const int block = kb_block_for(k);
   const int grid = kb_grid_for(ws, n_brows * (int64_t)k, block, 1);
   KbRed rd = kb_red(ws);
   if (dot == 0)
-    kb_spmv_halo_add_kernel<0><<<grid, block, 0, st>>>(n_brows, k, rows, hrowptr, hcol, hval, xh,
-                                                       y, w, out, rd);
+    kb_spmv_halo_add_kernel<0><<<grid, block, 0, st>>>(n_brows, k, sign, rows, hrowptr, hcol, hval,
+                                                       xh, y, w, out, rd);
   else
-    kb_spmv_halo_add_kernel<1><<<grid, block, 0, st>>>(n_brows, k, rows, hrowptr, hcol, hval, xh,
-                                                       y, w, out, rd);
+    kb_spmv_halo_add_kernel<1><<<grid, block, 0, st>>>(n_brows, k, sign, rows, hrowptr, hcol, hval,
+                                                       xh, y, w, out, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -343,7 +366,7 @@ int kb_axpy(kb_ws_t ws, int64_t n, int k, double sign, const double* coef, const
             double* y, void* stream) {
   KB_VEC_PROLOGUE();
   if (total == 0) return KB_OK;
-  const int grid = kb_grid_for(ws, total, block, 2);
+  const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
   kb_axpy_kernel<<<grid, block, 0, st>>>(total, k, sign, coef, x, y, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
@@ -353,7 +376,7 @@ int kb_xpby(kb_ws_t ws, int64_t n, int k, const double* x, const double* coef, d
             void* stream) {
   KB_VEC_PROLOGUE();
   if (total == 0) return KB_OK;
-  const int grid = kb_grid_for(ws, total, block, 2);
+  const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
   kb_xpby_kernel<<<grid, block, 0, st>>>(total, k, x, coef, y, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
@@ -363,7 +386,7 @@ int kb_div_scale(kb_ws_t ws, int64_t n, int k, const double* x, const double* co
                  void* stream) {
   KB_VEC_PROLOGUE();
   if (total == 0) return KB_OK;
-  const int grid = kb_grid_for(ws, total, block, 2);
+  const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
   kb_div_scale_kernel<<<grid, block, 0, st>>>(total, k, x, coef, out, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
@@ -373,14 +396,14 @@ int kb_add(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, doubl
            void* stream) {
   KB_VEC_PROLOGUE();
   if (total == 0) return KB_OK;
-  const int grid = kb_grid_for(ws, total, block, 2);
+  const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
   kb_add_kernel<<<grid, block, 0, st>>>(total, x, y, out, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
 
-int kb_axpy_dot(kb_ws_t ws, int64_t n, int k, const double* coef, const double* u, double* w,
-                int dot, const double* z, double* out, void* stream) {
+int kb_axpy_dot(kb_ws_t ws, int64_t n, int k, const double* coef, const double* scale,
+                const double* u, double* w, int dot, const double* z, double* out, void* stream) {
   KB_VEC_PROLOGUE();
   KB_REQUIRE(coef && u && w, "null argument");
   KB_REQUIRE(dot >= 0 && dot <= 2, "dot must be 0, 1 or 2");
@@ -388,11 +411,11 @@ int kb_axpy_dot(kb_ws_t ws, int64_t n, int k, const double* coef, const double* 
   KB_REQUIRE(dot != 1 || z != nullptr, "dot 1 needs z");
   const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
   if (dot == 0)
-    kb_axpy_dot_kernel<0><<<grid, block, 0, st>>>(total, k, coef, u, w, z, out, rd);
+    kb_axpy_dot_kernel<0><<<grid, block, 0, st>>>(total, k, coef, scale, u, w, z, out, rd);
   else if (dot == 1)
-    kb_axpy_dot_kernel<1><<<grid, block, 0, st>>>(total, k, coef, u, w, z, out, rd);
+    kb_axpy_dot_kernel<1><<<grid, block, 0, st>>>(total, k, coef, scale, u, w, z, out, rd);
   else
-    kb_axpy_dot_kernel<2><<<grid, block, 0, st>>>(total, k, coef, u, w, z, out, rd);
+    kb_axpy_dot_kernel<2><<<grid, block, 0, st>>>(total, k, coef, scale, u, w, z, out, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -412,7 +435,7 @@ int kb_minres_update(kb_ws_t ws, int64_t n, int k, const double* coefs, const do
   KB_VEC_PROLOGUE();
   KB_REQUIRE(coefs && v && W0 && W1 && Av && yk && vnext, "null argument");
   if (total == 0) return KB_OK;
-  const int grid = kb_grid_for(ws, total, block, 2);
+  const int grid = kb_grid_for(ws, total, block, KB_MR_UNROLL);
   kb_minres_update_kernel<<<grid, block, 0, st>>>(total, k, coefs, v, W0, W1, Av, yk, vnext, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
@@ -443,7 +466,7 @@ int kb_basis_combine(kb_ws_t ws, int64_t n, int k, int m, const double* yy, cons
   KB_VEC_PROLOGUE();
   KB_REQUIRE(x0 && out && (m == 0 || (yy && Vbuf)), "null argument");
   if (total == 0) return KB_OK;
-  const int grid = kb_grid_for(ws, total, block, 1);
+  const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
   kb_basis_combine_kernel<<<grid, block, 0, st>>>(total, k, m, yy, Vbuf, vstride, x0, out, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
@@ -459,6 +482,14 @@ int kb_house_make(kb_ws_t ws, int64_t n, int64_t off, const double* x, double* v
   KB_LAUNCH_CHECK();
   const int grid = kb_grid_for(ws, n, KB_BLOCK, 2);
   kb_house_fill_kernel<<<grid, KB_BLOCK, 0, S(stream)>>>(n, off, x, params, v, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_house_hlast(kb_ws_t ws, const double* w, int64_t off, const double* v, const double* params,
+                   const double* tau, double* h_out, void* stream) {
+  KB_REQUIRE(ws && w && v && params && tau && h_out, "null argument");
+  kb_house_hlast_kernel<<<1, 32, 0, S(stream)>>>(w, off, v, params, tau, h_out, kb_red(ws));
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

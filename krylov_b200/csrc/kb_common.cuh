@@ -9,7 +9,7 @@
 
 #define KB_BLOCK 256         // nominal threads per block of the vector kernels
 #define KB_MAX_K 256         // widest block of right-hand sides
-#define KB_CTAS_PER_SM 4     // resident CTAs per SM the vector grids are sized for
+#define KB_CTAS_PER_SM 8     // resident CTAs per SM the vector grids are sized for
 #define KB_MAX_BLOCKS 2048   // upper bound of any reduction grid (partials buffer)
 
 // ---------------------------------------------------------------- errors --
@@ -66,9 +66,11 @@ static inline KbRed kb_red(const kb_ws_s* ws) {
 // threads per block so that blockDim % k == 0 (each thread keeps one column)
 static inline int kb_block_for(int k) { return (KB_BLOCK / k) * k; }
 
+extern int g_vec_ctas;  // kb_tune key 2
+
 static inline int kb_grid_for(const kb_ws_s* ws, int64_t total, int block, int per_thread) {
   int64_t need = (total + (int64_t)block * per_thread - 1) / ((int64_t)block * per_thread);
-  int64_t cap = (int64_t)ws->num_sms * KB_CTAS_PER_SM;
+  int64_t cap = (int64_t)ws->num_sms * g_vec_ctas;
   if (cap > KB_MAX_BLOCKS) cap = KB_MAX_BLOCKS;
   if (need > cap) need = cap;
   if (need < 1) need = 1;
@@ -133,7 +135,7 @@ __device__ __forceinline__ double kb_block_colsum(double acc, int k, double* sm)
 // in block order and writes out[0..k).  `acc` follows the kb_block_colsum
 // precondition.  All threads of all blocks must call this.
 __device__ __forceinline__ void kb_grid_colsum(double acc, int k, const KbRed& rd, double* out,
-                                               double* sm) {
+                                               double* sm, bool accumulate = false) {
   __shared__ int s_last;
   const int t = threadIdx.x;
   double tot = kb_block_colsum(acc, k, sm);
@@ -170,7 +172,8 @@ __device__ __forceinline__ void kb_grid_colsum(double acc, int k, const KbRed& r
         for (int i = 0; i < Q; ++i) fin += sm[i * k + t];
       }
     }
-    if (t < k) out[t] = fin;
+    // accumulate: add to what an earlier launch on this stream left in out[]
+    if (t < k) out[t] = accumulate ? out[t] + fin : fin;
     if (t == 0) *rd.ticket = 0u;  // ready for the next launch on this stream
   }
 }

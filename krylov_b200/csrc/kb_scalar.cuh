@@ -101,8 +101,10 @@ __global__ void kb_minres_scalar_kernel(int k, int iter, kb_minres_state st, KbR
   const int all_conv = __syncthreads_and(conv);
   const int all_inv = __syncthreads_and(inv);
   if (threadIdx.x == 0) {
+    // an invariant subspace also ends the enqueued batch: the next Arnoldi/Lanczos
+    // step would raise ArgumentError in the reference (arnoldi.py:168-171, 239-242)
     if (all_inv) atomicOr(st.flags, 1);
-    if (all_conv) *st.stop_at = iter + 1;
+    if (all_conv || all_inv) *st.stop_at = iter + 1;
   }
 }
 
@@ -160,8 +162,10 @@ __global__ void kb_gmres_scalar_kernel(int k, int iter, kb_gmres_state st, KbRed
   const int all_conv = __syncthreads_and(conv);
   const int all_inv = __syncthreads_and(inv);
   if (threadIdx.x == 0) {
+    // an invariant subspace also ends the enqueued batch: the next Arnoldi/Lanczos
+    // step would raise ArgumentError in the reference (arnoldi.py:168-171, 239-242)
     if (all_inv) atomicOr(st.flags, 1);
-    if (all_conv) *st.stop_at = iter + 1;
+    if (all_conv || all_inv) *st.stop_at = iter + 1;
   }
 }
 
@@ -235,4 +239,17 @@ kb_house_fill_kernel(int64_t n, int64_t off, const double* __restrict__ x,
     else val = x[e] / d;
     v[e] = val;
   }
+}
+
+// h[k+1] of the Householder Arnoldi step (arnoldi.py:83-85): first entry of
+// (H w)[off:] * alpha, taken in absolute value; tau = <v, w> already reduced.
+__global__ void kb_house_hlast_kernel(const double* w, int64_t off, const double* v,
+                                      const double* params, const double* tau, double* h_out,
+                                      KbRed rd) {
+  if (kb_gated(rd)) return;
+  if (threadIdx.x != 0) return;
+  const double alpha = params[0], beta = params[1];
+  double val = w[off];
+  if (beta != 0.0) val = __dsub_rn(val, __dmul_rn(__dmul_rn(beta, v[off]), tau[0]));
+  h_out[0] = fabs(__dmul_rn(val, alpha));
 }

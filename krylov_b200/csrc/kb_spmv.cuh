@@ -98,8 +98,8 @@ __device__ __forceinline__ void kb_bulk_g2s(void* dst, const void* src, uint32_t
 }
 
 // ---------------------------------------------------- TMA-staged stream k==1 --
-#define KB_ST_ROWS 256                 // rows per tile == consumer threads
-#define KB_ST_THREADS (KB_ST_ROWS + 32)  // + one producer warp
+// rows per tile == consumer threads (template parameter ROWS); + one producer warp
+#define KB_ST_MAX_THREADS (512 + 32)
 
 template <int STAGES, int CAP>
 struct KbStreamSmem {
@@ -117,8 +117,8 @@ __device__ __forceinline__ void kb_chunk_range(int s, int e, int cidx, int cap, 
   b = min(a + cap, a1);
 }
 
-template <int STAGES, int CAP, int DOT>
-__global__ void __launch_bounds__(KB_ST_THREADS)
+template <int ROWS, int STAGES, int CAP, int DOT>
+__global__ void __launch_bounds__(ROWS + 32)
 kb_spmv_stream_kernel(int n_rows, int n_tiles, const int32_t* __restrict__ rowptr,
                       const int32_t* __restrict__ colidx, const double* __restrict__ vals,
                       const double* __restrict__ x, double* __restrict__ y, int mode,
@@ -127,11 +127,11 @@ kb_spmv_stream_kernel(int n_rows, int n_tiles, const int32_t* __restrict__ rowpt
   if (kb_gated(rd)) return;
   extern __shared__ __align__(128) unsigned char kb_dyn_smem[];
   KbStreamSmem<STAGES, CAP>& S = *reinterpret_cast<KbStreamSmem<STAGES, CAP>*>(kb_dyn_smem);
-  __shared__ double red_sm[KB_ST_THREADS];
+  __shared__ double red_sm[ROWS + 32];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int nconsumer_warps = KB_ST_ROWS / 32;
+  const int nconsumer_warps = ROWS / 32;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -155,8 +155,8 @@ kb_spmv_stream_kernel(int n_rows, int n_tiles, const int32_t* __restrict__ rowpt
       const int64_t my_tile = base + (int64_t)lane * gridDim.x;
       int my_s = 0, my_e = 0;
       if (my_tile < n_tiles) {
-        const int r0 = (int)my_tile * KB_ST_ROWS;
-        const int r1 = min(r0 + KB_ST_ROWS, n_rows);
+        const int r0 = (int)my_tile * ROWS;
+        const int r1 = min(r0 + ROWS, n_rows);
         my_s = rowptr[r0];
         my_e = rowptr[r1];
       }
@@ -192,8 +192,8 @@ kb_spmv_stream_kernel(int n_rows, int n_tiles, const int32_t* __restrict__ rowpt
     // software-pipelined row pointers of the next tile
     int lo_n = 0, hi_n = 0, s_n = 0, e_n = 0;
     if (tile < n_tiles) {
-      const int r0 = tile * KB_ST_ROWS;
-      const int r1 = min(r0 + KB_ST_ROWS, n_rows);
+      const int r0 = tile * ROWS;
+      const int r1 = min(r0 + ROWS, n_rows);
       const int row = r0 + tid;
       s_n = rowptr[r0];
       e_n = rowptr[r1];
@@ -203,14 +203,14 @@ kb_spmv_stream_kernel(int n_rows, int n_tiles, const int32_t* __restrict__ rowpt
       }
     }
     for (; tile < n_tiles; tile += gridDim.x) {
-      const int r0 = tile * KB_ST_ROWS;
+      const int r0 = tile * ROWS;
       const int row = r0 + tid;
       const int lo = lo_n, hi = hi_n, s = s_n, e = e_n;
       {
         const int nt = tile + gridDim.x;
         if (nt < n_tiles) {
-          const int q0 = nt * KB_ST_ROWS;
-          const int q1 = min(q0 + KB_ST_ROWS, n_rows);
+          const int q0 = nt * ROWS;
+          const int q1 = min(q0 + ROWS, n_rows);
           const int qrow = q0 + tid;
           s_n = rowptr[q0];
           e_n = rowptr[q1];
@@ -265,11 +265,14 @@ kb_spmv_stream_kernel(int n_rows, int n_tiles, const int32_t* __restrict__ rowpt
 }
 
 // ------------------------------------------------- boundary rows (halo part) --
-// for i < n_brows: row = rows[i];  h = sum_j hval[j] * xh[hcol[j], c];
-//   y[row, c] += h ;  out[c] = sum w[row, c] * h      (dot 1)
+// Row-partitioned matrices: the local product runs on the
+// columns a rank owns while the halo entries travel; this kernel then finishes
+// the boundary rows.  for i < n_brows: row = rows[i];
+//   h = sum_j hval[j] * xh[hcol[j], c];   y[row, c] += sign * h
+//   DOT 1: out[c] += sum_i w[row, c] * sign * h     (added to the local product's dot)
 template <int DOT>
 __global__ void __launch_bounds__(KB_BLOCK)
-kb_spmv_halo_add_kernel(int64_t n_brows, int k, const int32_t* __restrict__ rows,
+kb_spmv_halo_add_kernel(int64_t n_brows, int k, double sign, const int32_t* __restrict__ rows,
                         const int32_t* __restrict__ hrowptr, const int32_t* __restrict__ hcol,
                         const double* __restrict__ hval, const double* __restrict__ xh,
                         double* __restrict__ y, const double* __restrict__ w,
@@ -286,11 +289,12 @@ kb_spmv_halo_add_kernel(int64_t n_brows, int k, const int32_t* __restrict__ rows
     double h = 0.0;
     for (int j = lo; j < hi; ++j)
       h = __dadd_rn(h, __dmul_rn(hval[j], xh[(size_t)hcol[j] * k + c]));
+    h *= sign;
     const size_t idx = (size_t)rows[i] * k + c;
     y[idx] = __dadd_rn(y[idx], h);
     if (DOT == 1) acc = fma(w[idx], h, acc);
   }
-  if (DOT != 0) kb_grid_colsum(acc, k, rd, out, sm);
+  if (DOT != 0) kb_grid_colsum(acc, k, rd, out, sm, /*accumulate=*/true);
 }
 
 // ----------------------------------------------------------- row statistics --

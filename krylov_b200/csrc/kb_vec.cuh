@@ -2,14 +2,32 @@
 // (HBM-bound; bytes per element are stated per kernel), vectors are (n, k)
 // row-major and flat-indexed, per-column scalars come from device memory.
 //
-// Indexing rule shared by all kernels here: blockDim.x % k == 0 and the grid
-// stride is a multiple of blockDim.x, so thread t only ever touches column
+// Indexing rule shared by all kernels here: blockDim.x % k == 0 and every tile
+// starts at a multiple of blockDim.x, so thread t only ever touches column
 // c = t % k.  That makes the per-column coefficients loop-invariant and the
 // column-wise reductions a plain per-thread accumulation.
+//
+// Work split: tiles of blockDim.x * KB_UNROLL contiguous elements, tile t goes
+// to block t % gridDim.x.  At any moment the resident blocks stream one
+// contiguous window of every operand (DRAM-page and TLB friendly; a plain
+// grid-stride loop with megabyte strides between a thread's loads was 2x
+// slower for some grid sizes at n = 512^3), and a thread's KB_UNROLL loads per
+// operand are issued before the first use.
 #pragma once
 #include "kb_common.cuh"
 
 #define KB_UNROLL 4
+
+// for (tiles of this block) { full tile: FULL(i) unrolled over u ; tail: guarded }
+#define KB_TILE_LOOP_BEGIN(total) KB_TILE_LOOP_BEGIN_U(total, KB_UNROLL)
+#define KB_TILE_LOOP_BEGIN_U(total, U)                                                \
+  const int64_t kb_tile = (int64_t)blockDim.x * (U);                                  \
+  for (int64_t kb_base = (int64_t)blockIdx.x * kb_tile; kb_base < (total);            \
+       kb_base += (int64_t)gridDim.x * kb_tile) {                                     \
+    const int64_t kb_e0 = kb_base + threadIdx.x;                                      \
+    const bool kb_full = kb_base + kb_tile <= (total);
+#define KB_TILE_LOOP_END }
+#define KB_IDX(u) (kb_e0 + (int64_t)(u) * blockDim.x)
 
 // ---------------------------------------------------------------- dot ----
 // out[c] = sum_i x[i,c] * y[i,c]        16 B/element (8 when x == y)
@@ -19,27 +37,29 @@ kb_dot_kernel(int64_t total, int k, const double* __restrict__ x, const double* 
               double* __restrict__ out, KbRed rd) {
   if (kb_gated(rd)) return;
   __shared__ double sm[KB_BLOCK];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double acc = 0.0;
-  for (; e + (KB_UNROLL - 1) * stride < total; e += KB_UNROLL * stride) {
+  KB_TILE_LOOP_BEGIN(total)
+  if (kb_full) {
     double a[KB_UNROLL], b[KB_UNROLL];
 #pragma unroll
     for (int u = 0; u < KB_UNROLL; ++u) {
-      a[u] = x[e + u * stride];
-      b[u] = y[e + u * stride];
+      a[u] = x[KB_IDX(u)];
+      b[u] = y[KB_IDX(u)];
     }
 #pragma unroll
     for (int u = 0; u < KB_UNROLL; ++u) acc = fma(a[u], b[u], acc);
+  } else {
+    for (int u = 0; u < KB_UNROLL; ++u)
+      if (KB_IDX(u) < total) acc = fma(x[KB_IDX(u)], y[KB_IDX(u)], acc);
   }
-  for (; e < total; e += stride) acc = fma(x[e], y[e], acc);
+  KB_TILE_LOOP_END
   kb_grid_colsum(acc, k, rd, out, sm);
 }
 
 // ------------------------------------------------------------ CG: x, r ---
 // alpha = rho / nz(pAp [+ pAp2]);  x += alpha p;  r -= alpha Ap;  rr = <r,r>
 // 48 B/element (reads x p r Ap, writes x r).  cg.py:185,196,200,209
-__global__ void __launch_bounds__(KB_BLOCK)
+__global__ void __launch_bounds__(KB_BLOCK, 4)
 kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
                        const double* __restrict__ pAp, const double* __restrict__ pAp2,
                        const double* __restrict__ p, const double* __restrict__ Ap,
@@ -51,14 +71,13 @@ kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
   double d = pAp[c];
   if (pAp2 != nullptr) d += pAp2[c];
   const double alpha = rho[c] / kb_nz(d);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double acc = 0.0;
-  for (; e + (KB_UNROLL - 1) * stride < total; e += KB_UNROLL * stride) {
+  KB_TILE_LOOP_BEGIN(total)
+  if (kb_full) {
     double xv[KB_UNROLL], pv[KB_UNROLL], rv[KB_UNROLL], av[KB_UNROLL];
 #pragma unroll
     for (int u = 0; u < KB_UNROLL; ++u) {
-      const int64_t i = e + u * stride;
+      const int64_t i = KB_IDX(u);
       xv[u] = x[i];
       pv[u] = p[i];
       rv[u] = r[i];
@@ -66,19 +85,24 @@ kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
     }
 #pragma unroll
     for (int u = 0; u < KB_UNROLL; ++u) {
-      const int64_t i = e + u * stride;
+      const int64_t i = KB_IDX(u);
       x[i] = kb_mul_add(alpha, pv[u], xv[u]);
       const double rn = kb_mul_sub(alpha, av[u], rv[u]);
       r[i] = rn;
       acc = fma(rn, rn, acc);
     }
+  } else {
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      const int64_t i = KB_IDX(u);
+      if (i < total) {
+        x[i] = kb_mul_add(alpha, p[i], x[i]);
+        const double rn = kb_mul_sub(alpha, Ap[i], r[i]);
+        r[i] = rn;
+        acc = fma(rn, rn, acc);
+      }
+    }
   }
-  for (; e < total; e += stride) {
-    x[e] = kb_mul_add(alpha, p[e], x[e]);
-    const double rn = kb_mul_sub(alpha, Ap[e], r[e]);
-    r[e] = rn;
-    acc = fma(rn, rn, acc);
-  }
+  KB_TILE_LOOP_END
   kb_grid_colsum(acc, k, rd, out, sm);
 }
 
@@ -105,19 +129,21 @@ kb_cg_update_p_kernel(int64_t total, int k, int step, const double* __restrict__
   }
   if (!(what & 1)) return;
   const double omega = rho_new[c] / kb_nz(rho_old[c]);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; e + (KB_UNROLL - 1) * stride < total; e += KB_UNROLL * stride) {
+  KB_TILE_LOOP_BEGIN(total)
+  if (kb_full) {
     double rv[KB_UNROLL], pv[KB_UNROLL];
 #pragma unroll
     for (int u = 0; u < KB_UNROLL; ++u) {
-      rv[u] = r[e + u * stride];
-      pv[u] = p[e + u * stride];
+      rv[u] = r[KB_IDX(u)];
+      pv[u] = p[KB_IDX(u)];
     }
 #pragma unroll
-    for (int u = 0; u < KB_UNROLL; ++u) p[e + u * stride] = kb_mul_add(omega, pv[u], rv[u]);
+    for (int u = 0; u < KB_UNROLL; ++u) p[KB_IDX(u)] = kb_mul_add(omega, pv[u], rv[u]);
+  } else {
+    for (int u = 0; u < KB_UNROLL; ++u)
+      if (KB_IDX(u) < total) p[KB_IDX(u)] = kb_mul_add(omega, p[KB_IDX(u)], r[KB_IDX(u)]);
   }
-  for (; e < total; e += stride) p[e] = kb_mul_add(omega, p[e], r[e]);
+  KB_TILE_LOOP_END
 }
 
 // -------------------------------------------------------- generic axpy ---
@@ -127,9 +153,21 @@ kb_axpy_kernel(int64_t total, int k, double sign, const double* __restrict__ coe
                const double* __restrict__ x, double* __restrict__ y, KbRed rd) {
   if (kb_gated(rd)) return;
   const double a = sign * coef[threadIdx.x % k];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
-    y[e] = kb_mul_add(a, x[e], y[e]);
+  KB_TILE_LOOP_BEGIN(total)
+  if (kb_full) {
+    double xv[KB_UNROLL], yv[KB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      xv[u] = x[KB_IDX(u)];
+      yv[u] = y[KB_IDX(u)];
+    }
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) y[KB_IDX(u)] = kb_mul_add(a, xv[u], yv[u]);
+  } else {
+    for (int u = 0; u < KB_UNROLL; ++u)
+      if (KB_IDX(u) < total) y[KB_IDX(u)] = kb_mul_add(a, x[KB_IDX(u)], y[KB_IDX(u)]);
+  }
+  KB_TILE_LOOP_END
 }
 
 // y = x + coef[c] * y         24 B/element
@@ -138,9 +176,21 @@ kb_xpby_kernel(int64_t total, int k, const double* __restrict__ x,
                const double* __restrict__ coef, double* __restrict__ y, KbRed rd) {
   if (kb_gated(rd)) return;
   const double a = coef[threadIdx.x % k];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
-    y[e] = kb_mul_add(a, y[e], x[e]);
+  KB_TILE_LOOP_BEGIN(total)
+  if (kb_full) {
+    double xv[KB_UNROLL], yv[KB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      xv[u] = x[KB_IDX(u)];
+      yv[u] = y[KB_IDX(u)];
+    }
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) y[KB_IDX(u)] = kb_mul_add(a, yv[u], xv[u]);
+  } else {
+    for (int u = 0; u < KB_UNROLL; ++u)
+      if (KB_IDX(u) < total) y[KB_IDX(u)] = kb_mul_add(a, y[KB_IDX(u)], x[KB_IDX(u)]);
+  }
+  KB_TILE_LOOP_END
 }
 
 // out = x / nz(coef[c])       16 B/element   (arnoldi.py:191-196, 274-277)
@@ -149,9 +199,18 @@ kb_div_scale_kernel(int64_t total, int k, const double* __restrict__ x,
                     const double* __restrict__ coef, double* __restrict__ out, KbRed rd) {
   if (kb_gated(rd)) return;
   const double d = kb_nz(coef[threadIdx.x % k]);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
-    out[e] = x[e] / d;
+  KB_TILE_LOOP_BEGIN(total)
+  if (kb_full) {
+    double xv[KB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) xv[u] = x[KB_IDX(u)];
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) out[KB_IDX(u)] = xv[u] / d;
+  } else {
+    for (int u = 0; u < KB_UNROLL; ++u)
+      if (KB_IDX(u) < total) out[KB_IDX(u)] = x[KB_IDX(u)] / d;
+  }
+  KB_TILE_LOOP_END
 }
 
 // out = x + y                 24 B/element
@@ -159,47 +218,66 @@ __global__ void __launch_bounds__(KB_BLOCK)
 kb_add_kernel(int64_t total, const double* __restrict__ x, const double* __restrict__ y,
               double* __restrict__ out, KbRed rd) {
   if (kb_gated(rd)) return;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
-    out[e] = x[e] + y[e];
+  KB_TILE_LOOP_BEGIN(total)
+  if (kb_full) {
+    double xv[KB_UNROLL], yv[KB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      xv[u] = x[KB_IDX(u)];
+      yv[u] = y[KB_IDX(u)];
+    }
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) out[KB_IDX(u)] = xv[u] + yv[u];
+  } else {
+    for (int u = 0; u < KB_UNROLL; ++u)
+      if (KB_IDX(u) < total) out[KB_IDX(u)] = x[KB_IDX(u)] + y[KB_IDX(u)];
+  }
+  KB_TILE_LOOP_END
 }
 
 // ------------------------------------------------ MGS / Lanczos: axpy+dot -
-// w -= coef[c] * u; then out[c] = <z, w> (dot 1) | <w, w> (dot 2) | nothing
-// 32 B/element with dot 1, 24 otherwise.   arnoldi.py:157-162, 264-267
+// w -= (scale * coef[c]) * u; then out[c] = <z, w> (dot 1) | <w, w> (dot 2) | nothing
+// 32 B/element with dot 1, 24 otherwise.   arnoldi.py:157-162, 264-267;
+// with scale = beta it is a Householder reflector application (householder.py:62)
 template <int DOT>
 __global__ void __launch_bounds__(KB_BLOCK)
 kb_axpy_dot_kernel(int64_t total, int k, const double* __restrict__ coef,
-                   const double* __restrict__ u, double* __restrict__ w,
-                   const double* __restrict__ z, double* __restrict__ out, KbRed rd) {
+                   const double* __restrict__ scale, const double* __restrict__ u,
+                   double* __restrict__ w, const double* __restrict__ z,
+                   double* __restrict__ out, KbRed rd) {
   if (kb_gated(rd)) return;
   __shared__ double sm[KB_BLOCK];
-  const double a = coef[threadIdx.x % k];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double a = coef[threadIdx.x % k];
+  if (scale != nullptr) a = __dmul_rn(scale[0], a);
   double acc = 0.0;
-  for (; e + (KB_UNROLL - 1) * stride < total; e += KB_UNROLL * stride) {
+  KB_TILE_LOOP_BEGIN(total)
+  if (kb_full) {
     double uv[KB_UNROLL], wv[KB_UNROLL], zv[KB_UNROLL];
 #pragma unroll
     for (int q = 0; q < KB_UNROLL; ++q) {
-      uv[q] = u[e + q * stride];
-      wv[q] = w[e + q * stride];
-      if (DOT == 1) zv[q] = z[e + q * stride];
+      uv[q] = u[KB_IDX(q)];
+      wv[q] = w[KB_IDX(q)];
+      if (DOT == 1) zv[q] = z[KB_IDX(q)];
     }
 #pragma unroll
     for (int q = 0; q < KB_UNROLL; ++q) {
       const double wn = kb_mul_sub(a, uv[q], wv[q]);
-      w[e + q * stride] = wn;
+      w[KB_IDX(q)] = wn;
       if (DOT == 1) acc = fma(zv[q], wn, acc);
       if (DOT == 2) acc = fma(wn, wn, acc);
     }
+  } else {
+    for (int q = 0; q < KB_UNROLL; ++q) {
+      const int64_t i = KB_IDX(q);
+      if (i < total) {
+        const double wn = kb_mul_sub(a, u[i], w[i]);
+        w[i] = wn;
+        if (DOT == 1) acc = fma(z[i], wn, acc);
+        if (DOT == 2) acc = fma(wn, wn, acc);
+      }
+    }
   }
-  for (; e < total; e += stride) {
-    const double wn = kb_mul_sub(a, u[e], w[e]);
-    w[e] = wn;
-    if (DOT == 1) acc = fma(z[e], wn, acc);
-    if (DOT == 2) acc = fma(wn, wn, acc);
-  }
+  KB_TILE_LOOP_END
   if (DOT != 0) kb_grid_colsum(acc, k, rd, out, sm);
 }
 
@@ -208,7 +286,8 @@ kb_axpy_dot_kernel(int64_t total, int k, const double* __restrict__ coef,
 // z = (v - R0 W0 - R1 W1) / nz(R2);  W0 <- z;  yk += y0 z;  vnext = Av / nz(h2)
 // 64 B/element (reads v W0 W1 Av yk, writes W0 yk vnext).
 // minres.py:219-221 ("take the longest"), arnoldi.py:274-277
-__global__ void __launch_bounds__(KB_BLOCK)
+#define KB_MR_UNROLL 2
+__global__ void __launch_bounds__(KB_BLOCK, 4)
 kb_minres_update_kernel(int64_t total, int k, const double* __restrict__ coefs,
                         const double* __restrict__ v, double* __restrict__ W0,
                         const double* __restrict__ W1, const double* __restrict__ Av,
@@ -220,13 +299,12 @@ kb_minres_update_kernel(int64_t total, int k, const double* __restrict__ coefs,
   const double R2 = kb_nz(coefs[2 * k + c]);
   const double y0 = coefs[3 * k + c];
   const double h2 = kb_nz(coefs[4 * k + c]);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; e + 1 * stride < total; e += 2 * stride) {
-    double vv[2], w0[2], w1[2], av[2], yv[2];
+  KB_TILE_LOOP_BEGIN_U(total, KB_MR_UNROLL)
+  if (kb_full) {
+    double vv[KB_MR_UNROLL], w0[KB_MR_UNROLL], w1[KB_MR_UNROLL], av[KB_MR_UNROLL], yv[KB_MR_UNROLL];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int64_t i = e + q * stride;
+    for (int q = 0; q < KB_MR_UNROLL; ++q) {
+      const int64_t i = KB_IDX(q);
       vv[q] = v[i];
       w0[q] = W0[i];
       w1[q] = W1[i];
@@ -234,20 +312,25 @@ kb_minres_update_kernel(int64_t total, int k, const double* __restrict__ coefs,
       yv[q] = yk[i];
     }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int64_t i = e + q * stride;
+    for (int q = 0; q < KB_MR_UNROLL; ++q) {
+      const int64_t i = KB_IDX(q);
       const double zz = kb_mul_sub(R1, w1[q], kb_mul_sub(R0, w0[q], vv[q])) / R2;
       W0[i] = zz;
       yk[i] = kb_mul_add(y0, zz, yv[q]);
       vnext[i] = av[q] / h2;
     }
+  } else {
+    for (int q = 0; q < KB_MR_UNROLL; ++q) {
+      const int64_t i = KB_IDX(q);
+      if (i < total) {
+        const double zz = kb_mul_sub(R1, W1[i], kb_mul_sub(R0, W0[i], v[i])) / R2;
+        W0[i] = zz;
+        yk[i] = kb_mul_add(y0, zz, yk[i]);
+        vnext[i] = Av[i] / h2;
+      }
+    }
   }
-  for (; e < total; e += stride) {
-    const double zz = kb_mul_sub(R1, W1[e], kb_mul_sub(R0, W0[e], v[e])) / R2;
-    W0[e] = zz;
-    yk[e] = kb_mul_add(y0, zz, yk[e]);
-    vnext[e] = Av[e] / h2;
-  }
+  KB_TILE_LOOP_END
 }
 
 // ------------------------------------------------------- basis combine ---
@@ -259,8 +342,11 @@ kb_basis_combine_kernel(int64_t total, int k, int m, const double* __restrict__ 
                         const double* __restrict__ x0, double* __restrict__ out, KbRed rd) {
   if (kb_gated(rd)) return;
   const int c = threadIdx.x % k;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+  KB_TILE_LOOP_BEGIN(total)
+  (void)kb_full;
+  for (int u = 0; u < KB_UNROLL; ++u) {
+    const int64_t e = KB_IDX(u);
+    if (e >= total) break;
     double acc = 0.0;
     int j = 0;
     for (; j + 3 < m; j += 4) {
@@ -276,6 +362,7 @@ kb_basis_combine_kernel(int64_t total, int k, int m, const double* __restrict__ 
     for (; j < m; ++j) acc = kb_mul_add(yy[(size_t)j * k + c], Vbuf[(size_t)j * vstride + e], acc);
     out[e] = x0[e] + acc;
   }
+  KB_TILE_LOOP_END
 }
 
 // gather rows: buf[i, :] = x[idx[i], :]   (halo send buffer)

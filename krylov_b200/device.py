@@ -63,8 +63,12 @@ class Workspace:
 class Ops:
     """Kernel launches for (n, k) fp64 vectors on the current CUDA stream."""
 
-    def __init__(self, n: int, k: int, device=None):
+    def __init__(self, n: int, k: int, device=None, comm=None):
+        """`comm`: optional communicator of a row-partitioned problem; every
+        reduction slot is then summed over ranks right after the kernel that
+        produced the local part (one small all-reduce per inner product)."""
         require_cuda()
+        self.comm = comm
         if k < 1 or k > 256:
             raise ValueError("blocked right-hand sides: 1 <= k <= 256 columns supported")
         self.n, self.k = int(n), int(k)
@@ -91,16 +95,22 @@ class Ops:
         A._apply(self, x, y, mode, z, coef, dot, w, out)
 
     # -- reductions
+    def reduce_over_ranks(self, slot):
+        if self.comm is not None:
+            self.comm.allreduce(slot)
+
     def dot(self, x, y, out, n=None):
         self.launches += 1
         check(lib.kb_dot(self.ws.handle, self.n if n is None else n, self.k, ptr(x), ptr(y),
                          ptr(out), cur_stream()))
+        self.reduce_over_ranks(out)
 
     # -- CG
     def cg_update_xr(self, rho, pAp, pAp2, p, Ap, x, r, rr_out):
         self.launches += 1
         check(lib.kb_cg_update_xr(self.ws.handle, self.n, self.k, ptr(rho), ptr(pAp), ptr(pAp2),
                                   ptr(p), ptr(Ap), ptr(x), ptr(r), ptr(rr_out), cur_stream()))
+        self.reduce_over_ranks(rr_out)
 
     def cg_update_p(self, rho_new, rho_old, r, p):
         """p = r + (rho_new / nz(rho_old)) p"""
@@ -134,10 +144,12 @@ class Ops:
         self.launches += 1
         check(lib.kb_add(self.ws.handle, self.n, self.k, ptr(x), ptr(y), ptr(out), cur_stream()))
 
-    def axpy_dot(self, coef, u, w, dot=0, z=None, out=None):
+    def axpy_dot(self, coef, u, w, dot=0, z=None, out=None, scale=None):
         self.launches += 1
-        check(lib.kb_axpy_dot(self.ws.handle, self.n, self.k, ptr(coef), ptr(u), ptr(w), int(dot),
-                              ptr(z), ptr(out), cur_stream()))
+        check(lib.kb_axpy_dot(self.ws.handle, self.n, self.k, ptr(coef), ptr(scale), ptr(u), ptr(w),
+                              int(dot), ptr(z), ptr(out), cur_stream()))
+        if dot:
+            self.reduce_over_ranks(out)
 
     # -- MINRES
     def minres_scalar(self, it, state: MinresState):
@@ -168,9 +180,16 @@ class Ops:
 
     # -- Householder
     def house_make(self, off, x, v, params, scratch):
+        if self.comm is not None:
+            raise NotImplementedError("Householder orthogonalisation is single-GPU in this round")
         self.launches += 3
         check(lib.kb_house_make(self.ws.handle, self.n, int(off), ptr(x), ptr(v), ptr(params),
                                 ptr(scratch), cur_stream()))
+
+    def house_hlast(self, w, off, v, params, tau, h_out):
+        self.launches += 1
+        check(lib.kb_house_hlast(self.ws.handle, ptr(w), int(off), ptr(v), ptr(params), ptr(tau),
+                                 ptr(h_out), cur_stream()))
 
     def poke(self, op, x, idx, s=None, val=0.0, dst=None):
         self.launches += 1

@@ -1,0 +1,257 @@
+"""Row-partitioned sparse matrices over several GPUs (one process per GPU).
+
+The reference has no distributed layer; this is the
+B200-native addition BASELINE.json asks for.  Design:
+
+* 1-D contiguous row partition: rank p owns rows [offsets[p], offsets[p+1]) of
+  A and the matching slices of every vector, so all vector kernels are local.
+* The local rows are split PETSc-style into ``A_loc`` (columns the rank owns,
+  renumbered locally) and a compressed halo part (boundary rows only, columns
+  renumbered into a receive buffer ordered by owner rank).
+* One product = pack boundary entries -> grouped NCCL send/recv over
+  NVLink/NVSwitch (``torch.distributed`` P2P, asynchronous on NCCL's stream)
+  -> ``A_loc x`` on the compute stream *while the halo is in flight* -> wait ->
+  ``kb_spmv_halo_add`` finishes the boundary rows and adds its share of the
+  fused inner product to the same reduction slot.
+* Every inner product is a local deterministic partial followed by ONE small
+  all-reduce of k doubles (``Ops.reduce_over_ranks``); Givens/Hessenberg
+  scalar kernels run replicated on every rank.
+
+``HaloPlan`` is pure torch (CPU or CUDA tensors) so the partition/halo logic is
+tested with the gloo backend on CPU (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition_rows(n, size):
+    """Contiguous, balanced row offsets (size+1,)."""
+    base, rem = divmod(n, size)
+    off = np.zeros(size + 1, dtype=np.int64)
+    for p in range(size):
+        off[p + 1] = off[p] + base + (1 if p < rem else 0)
+    return off
+
+
+class Comm:
+    """Thin wrapper over a torch.distributed process group."""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+        self.allreduces = 0
+
+    def allreduce(self, t):
+        """In-place sum over ranks; stream-ordered for NCCL (no host sync)."""
+        self.allreduces += 1
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def allgather_object(self, obj):
+        out = [None] * self.size
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+
+class HaloPlan:
+    """Splits this rank's CSR rows (global column indices) into a local part
+    and a halo part, and works out who sends what to whom.
+
+    Inputs are torch tensors on any device: rowptr (n_loc+1, int32/64),
+    colidx (nnz), vals (nnz), the global row offsets of all ranks."""
+
+    def __init__(self, rowptr, colidx, vals, offsets, comm):
+        self.comm = comm
+        rank = comm.rank
+        self.offsets = np.asarray(offsets, dtype=np.int64)
+        r0, r1 = int(self.offsets[rank]), int(self.offsets[rank + 1])
+        self.row_start, self.row_end = r0, r1
+        n_loc = r1 - r0
+        assert rowptr.numel() == n_loc + 1
+        dev = colidx.device
+        nnz = int(vals.numel())
+        colidx = colidx[:nnz]
+        rp = rowptr.to(torch.int64)
+        is_halo = (colidx < r0) | (colidx >= r1)
+        # ---- local part: drop halo entries, renumber columns
+        owned_prefix = torch.zeros(nnz + 1, dtype=torch.int64, device=dev)
+        owned_prefix[1:] = torch.cumsum((~is_halo).to(torch.int64), 0)
+        self.loc_rowptr = owned_prefix[rp].to(torch.int32)
+        keep = ~is_halo
+        self.loc_colidx = (colidx[keep] - r0).to(torch.int32)
+        self.loc_vals = vals[:nnz][keep]
+        del owned_prefix, keep
+        # ---- halo part: boundary rows only
+        hidx = torch.nonzero(is_halo).reshape(-1)  # ascending nnz index => ascending row
+        hcols_g = colidx[hidx].to(torch.int64)
+        self.halo_globals = torch.unique(hcols_g)  # sorted => grouped by owner rank
+        self.n_halo = int(self.halo_globals.numel())
+        self.h_col = torch.searchsorted(self.halo_globals, hcols_g).to(torch.int32)
+        self.h_val = vals[:nnz][hidx]
+        rows_of = torch.searchsorted(rp, hidx, right=True) - 1
+        self.h_rows, counts = torch.unique_consecutive(rows_of, return_counts=True)
+        self.h_rows = self.h_rows.to(torch.int32)
+        self.n_brows = int(self.h_rows.numel())
+        self.h_rowptr = torch.zeros(self.n_brows + 1, dtype=torch.int32, device=dev)
+        if self.n_brows:
+            self.h_rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        # ---- who owns my halo columns / who needs my rows
+        hg = self.halo_globals.cpu().numpy()
+        owner = np.searchsorted(self.offsets, hg, side="right") - 1
+        self.recv_counts = np.bincount(owner, minlength=comm.size).astype(np.int64)
+        assert self.recv_counts[rank] == 0
+        wanted = [hg[owner == p] for p in range(comm.size)]  # global ids I need from p
+        everyone = comm.allgather_object(wanted)              # everyone[q][p]: q needs from p
+        send_lists = [np.asarray(everyone[q][rank], dtype=np.int64) - r0 for q in range(comm.size)]
+        self.send_counts = np.array([len(s) for s in send_lists], dtype=np.int64)
+        cat = np.concatenate(send_lists) if sum(self.send_counts) else np.zeros(0, np.int64)
+        assert cat.size == 0 or (cat.min() >= 0 and cat.max() < n_loc)
+        self.send_idx = torch.from_numpy(cat.astype(np.int32)).to(dev)
+        self.n_send = int(cat.size)
+        self.peers = [p for p in range(comm.size)
+                      if p != rank and (self.send_counts[p] or self.recv_counts[p])]
+
+    def exchange(self, send_buf, recv_buf):
+        """Post the grouped P2P transfers of one product; returns the works.
+        send_buf: (n_send, k) packed rows, grouped by destination rank;
+        recv_buf: (n_halo, k), grouped by source rank."""
+        ops = []
+        so = np.concatenate([[0], np.cumsum(self.send_counts)])
+        ro = np.concatenate([[0], np.cumsum(self.recv_counts)])
+        for p in self.peers:
+            if self.recv_counts[p]:
+                ops.append(dist.P2POp(dist.irecv, recv_buf[ro[p]:ro[p + 1]], p,
+                                      group=self.comm.group))
+            if self.send_counts[p]:
+                ops.append(dist.P2POp(dist.isend, send_buf[so[p]:so[p + 1]], p,
+                                      group=self.comm.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+
+class DistCsrMatrix:
+    """This rank's rows of a row-partitioned CSR matrix, on its GPU.
+
+    Behaves like a (n_loc x n_loc) operator on the rank's vector slices:
+    ``cg(A_dist, b_local)`` returns the local slice of the solution, with
+    residual norms / step counts identical on every rank."""
+
+    is_dist_csr = True
+    dtype = np.dtype(np.float64)
+
+    def __init__(self, local_csr, offsets, comm=None):
+        """local_csr: CsrMatrix holding rows [offsets[rank], offsets[rank+1])
+        with *global* column indices."""
+        from .csr import CsrMatrix
+
+        self.comm = comm if comm is not None else Comm()
+        self.device = local_csr.device
+        self.global_shape = (int(offsets[-1]), int(offsets[-1]))
+        plan = HaloPlan(local_csr.rowptr, local_csr.colidx, local_csr.vals[: local_csr.nnz],
+                        offsets, self.comm)
+        self.plan = plan
+        n_loc = plan.row_end - plan.row_start
+        self.shape = (n_loc, n_loc)
+        self.nnz = local_csr.nnz
+        self.A_loc = CsrMatrix(plan.loc_rowptr, plan.loc_colidx, plan.loc_vals, (n_loc, n_loc),
+                               self.device)
+        plan.loc_rowptr = plan.loc_colidx = plan.loc_vals = None
+        self._bufs = {}
+        self._ops = {}
+        self.halo_bytes_per_product = 8 * (plan.n_send + plan.n_halo)
+
+    def spmv_bytes(self, k=1):
+        n = self.shape[0]
+        return 12 * self.nnz + 4 * (n + 1) + 16 * n * k
+
+    def info(self):
+        d = self.A_loc.info()
+        d.update(n_halo=self.plan.n_halo, n_send=self.plan.n_send, n_brows=self.plan.n_brows,
+                 peers=list(self.plan.peers))
+        return d
+
+    def set_schedule(self, name):
+        self.A_loc.set_schedule(name)
+        return self
+
+    def _buffers(self, k):
+        b = self._bufs.get(k)
+        if b is None:
+            p = self.plan
+            b = self._bufs[k] = (
+                torch.empty((max(p.n_send, 1), k), dtype=torch.float64, device=self.device),
+                torch.empty((max(p.n_halo, 1), k), dtype=torch.float64, device=self.device))
+        return b
+
+    def _apply(self, ops, x, y, mode=0, z=None, coef=None, dot=0, w=None, out=None):
+        from ._lib import check, lib
+        from .device import cur_stream, ptr
+
+        p = self.plan
+        k = ops.k
+        send_buf, recv_buf = self._buffers(k)
+        works = []
+        if p.n_send or p.n_halo:
+            if p.n_send:
+                ops.launches += 1
+                check(lib.kb_pack_rows(ops.ws.handle, k, p.n_send, ptr(p.send_idx), ptr(x),
+                                       ptr(send_buf), cur_stream()))
+            works = p.exchange(send_buf[: p.n_send], recv_buf[: p.n_halo])
+        # local rows/columns while the halo is in flight; <y,y> cannot be split
+        # into a local and a halo share, so dot 2 is taken after the halo part
+        ldot = dot if dot == 1 else 0
+        ops.launches += 1
+        check(lib.kb_spmv(self.A_loc.handle, ops.ws.handle, k, ptr(x), ptr(y), int(mode), ptr(z),
+                          ptr(coef), ldot, ptr(w), ptr(out), cur_stream()))
+        for wk in works:
+            wk.wait()  # compute stream waits for NCCL's stream; the host does not block
+        if p.n_brows:
+            ops.launches += 1
+            check(lib.kb_spmv_halo_add(ops.ws.handle, k, p.n_brows, -1.0 if mode == 2 else 1.0,
+                                       ptr(p.h_rows), ptr(p.h_rowptr), ptr(p.h_col), ptr(p.h_val),
+                                       ptr(recv_buf), ptr(y), ldot, ptr(w), ptr(out),
+                                       cur_stream()))
+        if dot == 2:
+            ops.launches += 1
+            check(lib.kb_dot(ops.ws.handle, ops.n, k, ptr(y), ptr(y), ptr(out), cur_stream()))
+        if dot:
+            ops.reduce_over_ranks(out)
+
+    def matvec_device(self, x, out=None):
+        from .device import Ops
+
+        k = 1 if x.dim() == 1 else x.shape[1]
+        o = self._ops.get(k)
+        if o is None:
+            o = self._ops[k] = Ops(self.shape[0], k, self.device, comm=self.comm)
+        x = x.contiguous()
+        y = out if out is not None else torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            self._apply(o, x, y)
+        return y
+
+    def __matmul__(self, x):
+        from .device import as_device_matrix
+
+        if isinstance(x, torch.Tensor):
+            return self.matvec_device(as_device_matrix(x, self.device))
+        return self.matvec_device(as_device_matrix(x, self.device)).cpu().numpy()
+
+
+def dist_stencil7(nx, ny, nz, coeffs=None, shift=0.0, comm=None, device=None):
+    """z-slab partition of the 7-point operator: rank p builds planes
+    [nz*p/P, nz*(p+1)/P) on its own GPU."""
+    from .generate import device_stencil7
+    from .stencils import STENCIL_POISSON
+
+    comm = comm if comm is not None else Comm()
+    zoff = partition_rows(nz, comm.size)
+    z_lo, z_hi = int(zoff[comm.rank]), int(zoff[comm.rank + 1])
+    local = device_stencil7(nx, ny, nz, coeffs or STENCIL_POISSON, shift, z_lo, z_hi, device)
+    A = DistCsrMatrix(local, zoff * nx * ny, comm)
+    del local
+    return A

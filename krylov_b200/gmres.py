@@ -1,0 +1,269 @@
+"""Preconditioned GMRES on the device -- drop-in for ``krylov.gmres``
+(gmres.py:41-251): full (non-restarted) GMRES with ``ortho`` in
+``"mgs"``, ``"mgs<N>"`` (N sweeps of modified Gram-Schmidt), ``"householder"``;
+Hessenberg QR by Givens rotations; the solution is only formed when needed.
+``restart=`` is an additive extension: GMRES(m) as an outer loop
+of ``gmres(maxiter=m, x0=xk)`` cycles.
+
+Device layout: the Arnoldi basis is one (m+1, n, k) buffer; the Hessenberg
+column, all previous rotations, the new rotation (LAPACK ``dlartg``
+semantics), the projected right-hand side, the residual norm and the
+convergence flag are updated by a one-block kernel -- no host round-trip per
+Arnoldi step.  MGS step j is ``w -= h_j V_j`` fused with the next dot
+``<V_{j+1}, w>`` (32 B/element); the last one carries ``<w, w>``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._alg import Alg, nz
+from ._lib import GmresState
+from .arnoldi import _DevHouseholder
+from .device import Ops, ptr
+from .errors import ArgumentError
+from .operators import Identity, Info, Problem
+
+INT_MAX = 2**31 - 1
+_BATCH_MIN, _BATCH_MAX = 4, 64
+_INVARIANT_MSG = "Krylov subspace was found to be invariant in the previous iteration."
+
+
+def gmres(A, b, M=None, Ml=None, Mr=None, inner=None, ortho="mgs", x0=None, tol=1e-5,
+          atol=1.0e-15, maxiter=None, callback=None, restart=None, inner_product=None):
+    if inner is None and inner_product is not None:
+        inner = inner_product
+    if restart is not None:
+        return _gmres_restarted(A, b, M, Ml, Mr, inner, ortho, x0, tol, atol, maxiter, callback,
+                                int(restart))
+    prob = Problem(A, b, x0)
+    maxiter = prob.n if maxiter is None else int(maxiter)
+    with torch.cuda.device(prob.device):
+        return _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback)
+
+
+def _num_operations(k):
+    # gmres.py:240-247
+    return {"A": 1 + k, "M": 2 + k, "Ml": 2 + k, "Mr": 1 + k,
+            "inner": 2 + k + k * (k + 1) / 2, "axpy": 4 + 2 * k + k * (k + 1) / 2}
+
+
+def _callback_resnorm(prob, callback, xk, rn):
+    arr = np.array(prob.scalars_to_user(rn))  # gmres.py:223-233: may be overwritten
+    callback(prob.to_user(xk), arr)
+    return np.broadcast_to(np.asarray(arr[()], dtype=np.float64).reshape(-1), (prob.k,)).copy()
+
+
+def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
+    alg = Alg(prob, inner)
+    ops = alg.ops
+    A, b, x0 = prob.A, prob.b, prob.x0
+    n, k, dev = prob.n, prob.k, prob.device
+    M_is_identity = M is None or isinstance(M, Identity)
+    M, Ml, Mr = prob.operator(M), prob.operator(Ml), prob.operator(Mr)
+    chain = [Mr, A, Ml]  # Product(Ml, A, Mr)   (gmres.py:136)
+
+    if ortho.startswith("mgs"):  # gmres.py:147-157
+        nre = 1 if len(ortho) == 3 else int(ortho[3:])
+        householder = False
+    else:  # gmres.py:158-162
+        assert ortho == "householder"
+        assert inner is None
+        assert M_is_identity
+        nre = 1
+        householder = True
+    # everything device-resident <=> default inner product (no host callable in the loop)
+    fused_dots = inner is None
+    csr_only = prob.A_csr is not None and Ml is None and Mr is None
+
+    def residual_triple(z):  # gmres.py:105-114
+        Ml_r = alg.apply(Ml, alg.residual(A, b, z))
+        M_Ml_r = alg.apply(M, Ml_r)
+        return M_Ml_r, Ml_r, np.sqrt(alg.inner(Ml_r, M_Ml_r))
+
+    z0, r0, nrm0 = residual_triple(x0)
+    resn = [nrm0]
+    if callback is not None:
+        callback(prob.to_user(x0), prob.to_user(r0))
+
+    m = maxiter
+    # Arnoldi bases: V (and P = M^-1-dual basis when M is given; arnoldi.py:131-150)
+    Vbuf = torch.empty((m + 1, n, k), dtype=torch.float64, device=dev)
+    Pbuf = Vbuf if M is None else torch.empty((m + 1, n, k), dtype=torch.float64, device=dev)
+    R = torch.zeros((m + 1, max(m, 1), k), dtype=torch.float64, device=dev)
+    Gc = torch.zeros((max(m, 1), k), dtype=torch.float64, device=dev)
+    Gs = torch.zeros((max(m, 1), k), dtype=torch.float64, device=dev)
+    y = torch.zeros((m + 1, k), dtype=torch.float64, device=dev)
+    yy = torch.zeros((m + 1, k), dtype=torch.float64, device=dev)
+    dots = torch.zeros((nre * (m + 1) + 2, k), dtype=torch.float64, device=dev)
+    ww = ops.slots(1)[0]
+    hlast = ops.slots(1)[0]
+    ctl = torch.tensor([INT_MAX, 0], dtype=torch.int32, device=dev)  # stop_at, flags
+    hist = torch.zeros((_BATCH_MAX, k), dtype=torch.float64, device=dev)
+    nrm0_d = torch.from_numpy(np.ascontiguousarray(nrm0)).to(dev)
+    y[0].copy_(nrm0_d)  # gmres.py:171
+    crit = np.maximum(tol * resn[0], atol)
+    crit_d = torch.from_numpy(np.ascontiguousarray(crit)).to(dev)
+
+    hh = None
+    if householder:
+        hh = _DevHouseholder(alg, chain, r0, m)  # arnoldi.py:34-56
+    else:
+        ops.div_scale(Pbuf[0], r0, nrm0_d)  # arnoldi.py:147-150
+        if M is not None:
+            ops.div_scale(Vbuf[0], z0, nrm0_d)
+
+    st = GmresState(dots=ptr(dots), ww=ptr(ww), num_reorthos=nre, maxiter=max(m, 1), R=ptr(R),
+                    Gc=ptr(Gc), Gs=ptr(Gs), y=ptr(y), hlast=ptr(hlast), crit=ptr(crit_d), hist=0,
+                    stop_at=ctl.data_ptr(), flags=ctl.data_ptr() + 4, have_h=1 if householder else 0)
+    stop_at = ctl[0:1]
+
+    def basis(j):
+        return hh.V[j] if householder else Vbuf[j]
+
+    def solution(kk):  # gmres.py:89-99
+        if kk == 0:
+            return x0.clone()
+        ops.gmres_solve_y(kk, max(m, 1), R, y, yy)
+        out = torch.empty_like(x0)
+        if householder:
+            comb = torch.zeros_like(x0)
+            for j in range(kk):  # sum(c * v ...) one axpy per basis vector
+                ops.axpy(comb, yy[j], hh.V[j])
+        elif Mr is None:
+            ops.basis_combine(kk, yy, Vbuf, x0, out)
+            return out
+        else:
+            comb = torch.empty_like(x0)
+            ops.basis_combine(kk, yy, Vbuf, torch.zeros_like(x0), comb)
+        ops.add(out, x0, alg.apply(Mr, comb))
+        return out
+
+    def arnoldi_step(i):
+        """One Arnoldi step with device scalars; enqueue only."""
+        if householder:
+            hh.step()
+            st.dots = ptr(hh.h_dev)
+            ops.gmres_scalar(i, st)
+            return
+        w = Wbuf
+        # w = Ml A Mr V[i]  (+ first MGS dot <V[0], w> fused into the product)
+        if csr_only and fused_dots:
+            ops.spmv(prob.A_csr, Vbuf[i], w, dot=1, w=Vbuf[0], out=dots[0])
+        else:
+            w.copy_(alg.apply_chain(chain, Vbuf[i]))
+            _dot(Vbuf[0], w, dots[0])
+        idx = 0
+        last_fused = False
+        for sweep in range(nre):
+            for j in range(i + 1):  # arnoldi.py:157-162
+                last = sweep == nre - 1 and j == i
+                if last:
+                    if fused_dots and M is None:
+                        ops.axpy_dot(dots[idx], Pbuf[j], w, dot=2, out=ww)
+                        last_fused = True
+                    else:
+                        ops.axpy_dot(dots[idx], Pbuf[j], w, dot=0)
+                else:
+                    nxt = Vbuf[j + 1] if j < i else Vbuf[0]
+                    if fused_dots:
+                        ops.axpy_dot(dots[idx], Pbuf[j], w, dot=1, z=nxt, out=dots[idx + 1])
+                    else:
+                        ops.axpy_dot(dots[idx], Pbuf[j], w, dot=0)
+                        _dot(nxt, w, dots[idx + 1])
+                idx += 1
+        if not last_fused:  # h[k+1]^2 = <w, M w>   (arnoldi.py:184-185)
+            Mw = alg.apply(M, w)
+            _dot(w, Mw, ww)
+        else:
+            Mw = w
+        ops.gmres_scalar(i, st)  # gmres.py:206-221 on the device
+        ops.div_scale(Pbuf[i + 1], w, hlast)  # arnoldi.py:191-193
+        if M is not None:
+            ops.div_scale(Vbuf[i + 1], Mw, hlast)
+
+    def _dot(xv, yv, out):
+        if fused_dots:
+            ops.dot(xv, yv, out)
+        else:  # user inner product: host value -> device slot
+            out.copy_(torch.from_numpy(alg.inner(xv, yv)))
+
+    Wbuf = None if householder else ops.vec(zero=False)
+    step_by_step = callback is not None or not fused_dots
+    batch = 1 if step_by_step else _BATCH_MIN
+    kk = 0
+    success = False
+    xk = None
+    while True:
+        if np.all(resn[-1] <= crit):  # gmres.py:180-187
+            xk = solution(kk) if xk is None else xk
+            resn[-1] = residual_triple(xk)[2]
+            if np.all(resn[-1] <= crit):
+                success = True
+                break
+        if kk == maxiter:
+            break
+        c = ctl.cpu().numpy()
+        if c[1] & 1:
+            raise ArgumentError(_INVARIANT_MSG)  # arnoldi.py:67-70, 168-171
+        nb = min(batch, maxiter - kk)
+        stop_at.fill_(INT_MAX)
+        st.hist = hist.data_ptr() - (kk + 1) * k * 8
+        for i in range(kk, kk + nb):
+            ops.gate(stop_at, i)
+            arnoldi_step(i)
+        ops.gate(None, 0)
+        s = int(stop_at.item())
+        done = min(s, kk + nb) - kk
+        rows = hist[:done].cpu().numpy()
+        for j in range(done):
+            resn.append(rows[j].copy())
+        kk += done
+        xk = None
+        if callback is not None:
+            xk = solution(kk)
+            resn[-1] = _callback_resnorm(prob, callback, xk, resn[-1])
+        if not step_by_step:
+            batch = min(2 * batch, _BATCH_MAX)
+
+    if xk is None:
+        xk = solution(kk)
+    prob.launches = ops.launches
+    xk_user = prob.to_user(xk)
+    resnorms = [prob.scalars_to_user(r) for r in resn]
+    return (xk_user if success else None), Info(
+        success, xk_user, kk, resnorms, num_operations=_num_operations(kk))
+
+
+def _gmres_restarted(A, b, M, Ml, Mr, inner, ortho, x0, tol, atol, maxiter, callback, restart):
+    """GMRES(restart): cycles of ``gmres(maxiter=restart, x0=xk)`` against one
+    fixed target ``max(tol*||r0||, atol)`` taken from the first cycle
+    (the user loop of SURVEY.md: the reference has no restart parameter).
+    ``maxiter`` bounds the total number of Arnoldi steps."""
+    total_cap = int(b.shape[0]) if maxiter is None else int(maxiter)
+    x = x0
+    hist = None
+    target = None
+    total = 0
+    ok = False
+    while True:
+        m = restart if total_cap is None else min(restart, total_cap - total)
+        if m <= 0 and target is not None:
+            break
+        if target is None:
+            sol, info = gmres(A, b, M=M, Ml=Ml, Mr=Mr, inner=inner, ortho=ortho, x0=x, tol=tol,
+                              atol=atol, maxiter=m, callback=callback)
+            target = np.maximum(tol * np.asarray(info.resnorms[0]), atol)
+            hist = list(info.resnorms)
+        else:
+            sol, info = gmres(A, b, M=M, Ml=Ml, Mr=Mr, inner=inner, ortho=ortho, x0=x, tol=0.0,
+                              atol=target, maxiter=m, callback=callback)
+            hist.extend(info.resnorms[1:])
+        total += info.numsteps
+        x = info.xk
+        if info.success:
+            ok = True
+            break
+        if info.numsteps == 0:
+            break
+    return (x if ok else None), Info(ok, x, total, hist, num_operations=_num_operations(total))

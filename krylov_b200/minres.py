@@ -65,7 +65,7 @@ def _callback_resnorm(prob, callback, xk, rn):
 def _minres_fused(prob, tol, atol, maxiter, callback):
     A, b, x0 = prob.A_csr, prob.b, prob.x0
     n, k, dev = prob.n, prob.k, prob.device
-    ops = Ops(n, k, dev)
+    ops = Ops(n, k, dev, comm=prob.comm)
     Vb = [ops.vec(zero=True), ops.vec(zero=True)]  # v_i in Vb[i % 2], v_{i-1} in the other
     Wb = [ops.vec(zero=True), ops.vec(zero=True)]  # W0 in Wb[i % 2], W1 in the other
     Av = ops.vec(zero=False)

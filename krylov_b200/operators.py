@@ -118,7 +118,7 @@ def _is_scipy_sparse(A):
 
 def to_csr_or_none(A, device):
     """CsrMatrix for anything that *is* a matrix; None for duck-typed operators."""
-    if isinstance(A, CsrMatrix):
+    if isinstance(A, CsrMatrix) or getattr(A, "is_dist_csr", False):
         return A
     if _is_scipy_sparse(A):
         return CsrMatrix.from_scipy(A, device)
@@ -173,6 +173,8 @@ class Problem:
         if self.A is None:
             raise ValueError("A must be a matrix or a linear operator")
         self.A_csr = self.A.csr  # CsrMatrix, or None for a duck-typed operator
+        # row-partitioned matrix: b, x0 and every vector are this rank's rows
+        self.comm = getattr(self.A_csr, "comm", None)
 
     # user-facing views -----------------------------------------------------
     def to_user(self, t: torch.Tensor):
@@ -198,7 +200,7 @@ class Problem:
         for the identity."""
         if op is None or isinstance(op, Identity):
             return None
-        csr = op if isinstance(op, CsrMatrix) else to_csr_or_none(op, self.device)
+        csr = to_csr_or_none(op, self.device)
         if csr is not None:
             if csr.shape[0] != self.n or csr.shape[1] != self.n:
                 raise ValueError("operator shape does not match the right-hand side")

@@ -1,0 +1,142 @@
+"""-m gpu kernel-level parity: every C-ABI primitive against NumPy/SciPy on
+seeded inputs.  SpMV/SpMM is bit-exact against SciPy's csr_matvec(s) (same
+summation order, no FMA); reductions are checked to rounding and for bitwise
+run-to-run reproducibility."""
+import numpy as np
+import pytest
+import scipy.sparse
+import torch
+
+import krylov_b200 as kb
+from krylov_b200 import stencils as st
+from krylov_b200.device import Ops
+from krylov_b200.generate import device_stencil7
+
+pytestmark = pytest.mark.gpu
+rng = np.random.default_rng(11)
+
+
+def _mats():
+    yield "poisson3d_7", st.poisson3d(7)
+    yield "poisson2d_33", st.poisson2d(33)
+    yield "convdiff_12", st.convection_diffusion3d(12)
+    yield "random_sparse", scipy.sparse.random(3000, 3000, density=0.01, random_state=1, format="csr")
+    yield "dense_rows", scipy.sparse.random(600, 600, density=0.6, random_state=2, format="csr")
+    yield "empty_rows", scipy.sparse.csr_matrix(
+        (np.array([1.0, 2.0]), np.array([0, 3]), np.array([0, 0, 1, 1, 2, 2])), shape=(5, 5))
+    yield "one_by_one", scipy.sparse.csr_matrix(np.array([[3.0]]))
+    yield "rect", scipy.sparse.random(257, 513, density=0.05, random_state=3, format="csr")
+
+
+@pytest.mark.parametrize("name,A", list(_mats()))
+@pytest.mark.parametrize("k", [1, 2, 3, 16])
+def test_spmv_bit_exact_vs_scipy(name, A, k):
+    x = rng.standard_normal((A.shape[1], k)) if k > 1 else rng.standard_normal(A.shape[1])
+    ref = A @ x
+    for sched in ("rowwise", "stream", "auto"):
+        Ad = kb.CsrMatrix.from_scipy(A).set_schedule(sched)
+        np.testing.assert_array_equal(Ad @ x, ref)
+
+
+@pytest.mark.parametrize("sched", ["rowwise", "stream"])
+@pytest.mark.parametrize("k", [1, 4])
+def test_spmv_fused_modes(sched, k):
+    A = st.convection_diffusion3d(9)
+    n = A.shape[0]
+    Ad = kb.CsrMatrix.from_scipy(A).set_schedule(sched)
+    ops = Ops(n, k)
+    X, Z, W = (rng.standard_normal((n, k)) for _ in range(3))
+    coef = rng.standard_normal(k)
+    x, z, w = (torch.from_numpy(a).cuda() for a in (X, Z, W))
+    cf = torch.from_numpy(coef).cuda()
+    y = torch.empty_like(x)
+    out = ops.slots(1)[0]
+    t = A @ X
+    for mode, ref in ((0, t), (1, t - coef * Z), (2, Z - t)):
+        for dot, dref in ((0, None), (1, np.einsum("ij,ij->j", W, ref)), (2, np.einsum("ij,ij->j", ref, ref))):
+            ops.spmv(Ad, x, y, mode=mode, z=z, coef=cf, dot=dot, w=w, out=out)
+            np.testing.assert_array_equal(y.cpu().numpy(), ref)
+            if dot:
+                np.testing.assert_allclose(out.cpu().numpy(), dref, rtol=1e-13)
+
+
+@pytest.mark.parametrize("k", [1, 3, 16, 100])
+@pytest.mark.parametrize("n", [1, 255, 4099, 300001])
+def test_dot_and_determinism(n, k):
+    if n * k > 40_000_000:
+        pytest.skip("size")
+    ops = Ops(n, k)
+    X, Y = rng.standard_normal((n, k)), rng.standard_normal((n, k))
+    x, y = torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda()
+    out = ops.slots(2)
+    ops.dot(x, y, out[0])
+    ops.dot(x, y, out[1])
+    o = out.cpu().numpy()
+    np.testing.assert_array_equal(o[0], o[1])  # bitwise repeatable
+    ref = np.einsum("ij,ij->j", X, Y)
+    np.testing.assert_allclose(o[0], ref, rtol=1e-12, atol=1e-12 * np.sqrt(n))
+
+
+@pytest.mark.parametrize("k", [1, 5])
+def test_vector_kernels(k):
+    n = 10007
+    ops = Ops(n, k)
+    a = {nm: rng.standard_normal((n, k)) for nm in "xprAw"}
+    d = {nm: torch.from_numpy(v).cuda() for nm, v in a.items()}
+    rho, pAp, c1 = rng.standard_normal(k) ** 2 + 0.1, rng.standard_normal(k) ** 2 + 0.1, rng.standard_normal(k)
+    rho_d, pAp_d, c1_d = (torch.from_numpy(v).cuda() for v in (rho, pAp, c1))
+    out = ops.slots(1)[0]
+    # cg_update_xr (cg.py:185-209)
+    alpha = rho / pAp
+    x_ref = a["x"] + alpha * a["p"]
+    r_ref = a["r"] - alpha * a["A"]
+    ops.cg_update_xr(rho_d, pAp_d, None, d["p"], d["A"], d["x"], d["r"], out)
+    np.testing.assert_array_equal(d["x"].cpu().numpy(), x_ref)
+    np.testing.assert_array_equal(d["r"].cpu().numpy(), r_ref)
+    np.testing.assert_allclose(out.cpu().numpy(), np.einsum("ij,ij->j", r_ref, r_ref), rtol=1e-13)
+    # zero-division guard (cg.py:185): pAp == 0 -> alpha = rho
+    z0 = torch.zeros(k, dtype=torch.float64, device="cuda")
+    xb = d["x"].clone()
+    ops.cg_update_xr(rho_d, z0, None, d["p"], d["A"], xb, d["r"].clone(), out)
+    np.testing.assert_array_equal(xb.cpu().numpy(), x_ref + rho * a["p"])
+    # cg_update_p (cg.py:175-178)
+    p_ref = r_ref + (rho / pAp) * a["p"]
+    ops.cg_update_p(rho_d, pAp_d, d["r"], d["p"])
+    np.testing.assert_array_equal(d["p"].cpu().numpy(), p_ref)
+    # axpy_dot (arnoldi.py:157-162)
+    w_ref = a["w"] - c1 * a["A"]
+    ops.axpy_dot(c1_d, d["A"], d["w"], dot=1, z=d["x"], out=out)
+    np.testing.assert_array_equal(d["w"].cpu().numpy(), w_ref)
+    np.testing.assert_allclose(out.cpu().numpy(), np.einsum("ij,ij->j", x_ref, w_ref), rtol=1e-12, atol=1e-10)
+    # div_scale with zero guard (arnoldi.py:191)
+    dd = c1.copy()
+    dd[0] = 0.0
+    o2 = torch.empty_like(d["w"])
+    ops.div_scale(o2, d["w"], torch.from_numpy(dd).cuda())
+    np.testing.assert_array_equal(o2.cpu().numpy(), w_ref / np.where(dd != 0, dd, 1.0))
+
+
+def test_gate_skips_launches():
+    n = 1000
+    ops = Ops(n, 1)
+    x = torch.ones(n, 1, dtype=torch.float64, device="cuda")
+    y = torch.ones_like(x)
+    one = torch.ones(1, dtype=torch.float64, device="cuda")
+    stop = torch.tensor([5], dtype=torch.int32, device="cuda")
+    ops.gate(stop, 4)      # 5 <= 4 false -> runs
+    ops.axpy(y, one, x)
+    ops.gate(stop, 5)      # 5 <= 5 -> skipped
+    ops.axpy(y, one, x)
+    ops.gate(None, 0)
+    assert float(y.sum()) == 2.0 * n
+
+
+def test_device_generator_equals_host_generator():
+    for (nx, ny, nz, zl, zh) in [(9, 7, 5, 0, 5), (6, 6, 6, 2, 4), (1, 1, 3, 0, 3)]:
+        Ad = device_stencil7(nx, ny, nz, coeffs=st.convdiff_coeffs(), shift=0.25, z_lo=zl, z_hi=zh)
+        Ah = st.to_scipy(st.stencil7_csr(nx, ny, nz, coeffs=st.convdiff_coeffs(), shift=0.25, z_lo=zl, z_hi=zh),
+                         n_cols=nx * ny * nz)
+        B = Ad.to_scipy()
+        np.testing.assert_array_equal(B.indptr, Ah.indptr)
+        np.testing.assert_array_equal(B.indices, Ah.indices)
+        np.testing.assert_array_equal(B.data, Ah.data)

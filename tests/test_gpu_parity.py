@@ -1,0 +1,297 @@
+"""-m gpu parity tests: the CUDA product (through the C ABI) against
+  (1) outputs of the unmodified reference on the same seeded inputs
+      (tests/golden/*.npz, written by make_golden.py),
+  (2) the reference's own known-answer vectors and test invariants,
+  (3) the oracle run live on the same inputs.
+
+Tolerances are BASELINE.json's: final solution relative error <= 1e-10,
+per-iteration residual norms within 1e-8 relative until the residual has
+dropped by 1e-6, iteration counts within +-2 %.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import krylov_b200 as kb
+from oracle import krylov_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+SOL = np.load(os.path.join(G, "solvers.npz"))
+ARN = np.load(os.path.join(G, "arnoldi.npz"))
+SML = np.load(os.path.join(G, "small.npz"))
+CASES = cases.solver_cases()
+
+RES_RTOL = 1e-8     # residual-norm history
+RES_FLOOR = 1e-6    # ... compared while resnorm/resnorm[0] >= this
+SOL_RTOL = 1e-10    # final solution
+
+
+def check_history(res, ref_res, explicit_noise=0.0):
+    """`explicit_noise`: absolute rounding floor of an *explicitly* computed
+    residual ||b - A x|| (8 eps ||A||_inf ||x||): when a solver stops, the last
+    entry is overwritten by that quantity (cg.py:156-164), which no
+    implementation can reproduce more precisely than its own rounding."""
+    res, ref_res = np.asarray(res, float), np.asarray(ref_res, float)
+    assert res.shape == ref_res.shape
+    r0 = np.where(ref_res[0] > 0, ref_res[0], 1.0)
+    live = ref_res / r0 >= RES_FLOOR
+    abs_err = np.abs(res - ref_res)
+    abs_err[-1] = np.maximum(abs_err[-1] - explicit_noise, 0.0)
+    err = abs_err / np.where(ref_res > 0, ref_res, 1.0)
+    assert np.all(err[live] <= RES_RTOL), f"max rel err {err[live].max():.3e}"
+    # below the floor rounding noise dominates; stay within 1e-3
+    assert np.all(err[~live & (ref_res > 1e-300)] <= 1e-3)
+
+
+def check_steps(n, n_ref):
+    assert abs(n - n_ref) <= max(0.02 * n_ref, 0), (n, n_ref)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_solver_matches_reference(name):
+    solver, A, b, kw = CASES[name]
+    sol, info = getattr(kb, solver)(A, b, **kw)
+    n_ref = int(SOL[name + "_numsteps"])
+    check_steps(info.numsteps, n_ref)
+    assert bool(info.success) == bool(SOL[name + "_success"])
+    assert (sol is None) == bool(SOL[name + "_solnone"])
+    ref_x = SOL[name + "_xk"]
+    if info.numsteps == n_ref:
+        Ainf = abs(A).sum(axis=1).max()
+        noise = 8 * np.finfo(float).eps * Ainf * np.linalg.norm(ref_x) if info.success else 0.0
+        check_history(info.resnorms, SOL[name + "_resnorms"], noise)
+    scale = max(np.linalg.norm(ref_x), 1e-300)
+    assert np.linalg.norm(np.asarray(info.xk) - ref_x) <= SOL_RTOL * scale
+    # reference tests/helpers.py:4-23 invariants
+    if sol is not None:
+        assert sol.shape == b.shape
+        assert np.may_share_memory(sol, info.xk)
+    rn = np.asarray(info.resnorms)
+    assert np.issubdtype(rn.dtype, np.floating)
+    assert rn.shape == (info.numsteps + 1, *b.shape[1:])
+
+
+# reference tests/test_solvers.py:123-144
+@pytest.mark.parametrize(
+    "method, ref",
+    [
+        ("cg", [1004.1873775173957, 1000.0003174916551, 999.9999999997555]),
+        ("gmres", [1004.1873724888546, 1000.0003124630923, 999.999994971191]),
+        ("minres", [1004.187372488912, 1000.0003124632159, 999.9999949713145]),
+    ],
+)
+@pytest.mark.parametrize("shape", [(100,), (100, 1)])
+def test_reference_known_answers(method, ref, shape):
+    tol = 1.0e-11
+    A = cases.kat_matrix(shape[0])
+    b = np.ones(shape)
+    sol, info = getattr(kb, method)(A, b)
+    assert sol.shape == b.shape
+    assert info.numsteps == 55
+    assert abs(np.sum(np.abs(sol)) - ref[0]) < tol * ref[0]
+    assert abs(np.sqrt(np.dot(sol.T, sol)) - ref[1]) < tol * ref[1]
+    assert abs(np.max(np.abs(sol)) - ref[2]) < tol * ref[2]
+
+
+def _consistent(A, b, info, sol, tol):
+    """reference tests/helpers.py:4-23"""
+    res = b - A @ info.xk
+    resnorm = np.sqrt(np.einsum("i...,i...->...", res, res))
+    bnorm = np.sqrt(np.einsum("i...,i...->...", b, b))
+    if info.success:
+        assert sol.shape == b.shape
+        assert np.all(resnorm < tol * (1.0 + bnorm))
+        assert np.may_share_memory(sol, info.xk)
+    assert np.all(np.abs(resnorm - info.resnorms[-1]) <= 1.0e-12 * (1 + resnorm))
+    assert np.asarray(info.resnorms).shape == (info.numsteps + 1, *b.shape[1:])
+
+
+def _spd(shape):
+    a = np.linspace(1.0, 2.0, shape[0])
+    a[-1] = 1e-2
+    return np.diag(a), np.ones(shape)
+
+
+def _spd_rhs_0sol0():
+    a = np.linspace(1.0, 2.0, 5)
+    a[-1] = 1e-2
+    A = np.diag(a)
+    np.random.seed(0)
+    b = np.column_stack([np.zeros(5), np.random.rand(5), np.random.rand(5)])
+    sol = np.linalg.solve(A, b[:, 1])
+    return A, np.column_stack([np.zeros(5), sol, np.zeros(5)])
+
+
+def _sym_indef():
+    a = np.linspace(1.0, 2.0, 5)
+    a[-1] = -1.0
+    return np.diag(a), np.ones(5)
+
+
+def _unsym():
+    a = np.arange(1, 6, dtype=float)
+    a[-1] = -10.0
+    A = np.diag(a)
+    A[0, -1] = 10.0
+    return A, np.ones(5)
+
+
+REAL_PROBLEMS = [_spd((5,)), _spd((5, 1)), _spd((5, 3)), (np.diag(np.linspace(1, 2, 5)), np.zeros(5)),
+                 _spd_rhs_0sol0(), _sym_indef()]
+
+
+# reference tests/test_cg.py, test_minres.py, test_gmres.py (real-valued problems)
+@pytest.mark.parametrize("idx", range(len(REAL_PROBLEMS)))
+@pytest.mark.parametrize("solver", ["cg", "minres", "gmres", "gmres_mgs2"])
+def test_reference_test_problems(solver, idx):
+    A, b = REAL_PROBLEMS[idx]
+    count = 0
+
+    def callback(x, r):
+        nonlocal count
+        count += 1
+
+    kw = {"ortho": "mgs2"} if solver == "gmres_mgs2" else {}
+    fn = kb.gmres if solver.startswith("gmres") else getattr(kb, solver)
+    sol, info = fn(A, b, tol=1.0e-7, callback=callback, **kw)
+    assert count == info.numsteps + 1
+    assert info.success
+    _consistent(A, b, info, sol, 1.0e-7)
+
+
+def test_gmres_unsymmetric_and_householder():
+    A, b = _unsym()
+    for ortho in ("mgs", "mgs2", "householder"):
+        sol, info = kb.gmres(A, b, tol=1e-7, ortho=ortho)
+        assert info.success
+        _consistent(A, b, info, sol, 1e-7)
+    with pytest.raises(AssertionError):
+        kb.gmres(A, np.ones((5, 3)), ortho="householder")
+
+
+# reference tests/test_solvers.py:80-87, 199-243
+@pytest.mark.parametrize("solver", ["cg", "minres", "gmres"])
+def test_operator_kinds_and_exact_x0(solver):
+    import scipy.sparse
+    import scipy.sparse.linalg
+
+    fn = getattr(kb, solver)
+    A = np.diag([1.0e-3] + list(range(2, 11))).astype(float)
+    b = np.ones(10)
+    _, info = fn(A, b, x0=np.linalg.solve(A, b))
+    assert len(info.resnorms) == 1
+    n = 5
+    a = np.linspace(1.0, 2.0, n)
+    a[-1] = 1e-2
+    b = np.ones(n)
+    _, info = fn(scipy.sparse.spdiags(a, [0], n, n), b, tol=1e-12)
+    assert info.resnorms[-1] <= 1e-12
+    _, info = fn(scipy.sparse.linalg.LinearOperator((n, n), lambda x: a * x), b, tol=1e-12)
+    assert info.resnorms[-1] <= 1e-12
+
+    class MyOp:
+        shape = (n, n)
+        dtype = float
+
+        def __matmul__(self, x):
+            return a * x
+
+    _, info = fn(MyOp(), b, tol=1e-12)
+    assert info.resnorms[-1] <= 1e-12
+    # torch in -> torch out, device-resident
+    At = kb.CsrMatrix.from_dense(np.diag(a))
+    bt = torch.ones(n, dtype=torch.float64, device="cuda")
+    sol, info = fn(At, bt, tol=1e-12)
+    assert isinstance(sol, torch.Tensor) and sol.is_cuda and sol.data_ptr() == info.xk.data_ptr()
+    np.testing.assert_allclose(sol.cpu().numpy(), 1.0 / a, rtol=1e-10)
+    with pytest.raises(AssertionError):
+        fn(np.eye(4), np.ones(5))
+    with pytest.raises(NotImplementedError):
+        fn(np.eye(3) * 1j, np.ones(3))
+
+
+def test_cg_return_arnoldi():
+    _, A, b, _ = CASES["p2d32_cg"]
+    _, info = kb.cg(A, b, tol=1e-10, maxiter=40, return_arnoldi=True)
+    V, H, P = info.arnoldi
+    np.testing.assert_allclose(H, SOL["p2d32_cg_arn_H"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(V[5], SOL["p2d32_cg_arn_V5"], rtol=0, atol=1e-11)
+    assert len(V) == 41 and len(P) == 41
+
+
+def test_gmres_restart_extension():
+    _, A, b, _ = CASES["cd10_gmres_mgs"]
+    _, info = kb.gmres(A, b, tol=0.0, atol=0.0, maxiter=40, restart=10)
+    assert info.numsteps == 40
+    ref = SOL["cd10_gmres_restart10_hist"]
+    flat = np.concatenate([ref[0]] + [h[1:] for h in ref[1:]])
+    np.testing.assert_allclose(np.asarray(info.resnorms), flat, rtol=1e-8)
+    np.testing.assert_allclose(info.xk, SOL["cd10_gmres_restart10_xk"], rtol=0, atol=1e-10)
+
+
+def test_arnoldi_builders_match_reference():
+    A, As, v = cases.arnoldi_inputs()
+    for nre in (1, 2):
+        arn = kb.ArnoldiMGS(A, v.copy(), num_reorthos=nre)
+        H = np.zeros((21, 20))
+        for k in range(20):
+            _, h = next(arn)
+            H[: k + 2, k] = h
+        np.testing.assert_allclose(H, ARN[f"mgs{nre}_H"], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(np.column_stack(arn.V), ARN[f"mgs{nre}_V"], rtol=0, atol=1e-11)
+    arn = kb.ArnoldiHouseholder(A, v.copy())
+    H = np.zeros((21, 20))
+    for k in range(20):
+        _, h = next(arn)
+        H[: k + 2, k] = h
+    np.testing.assert_allclose(H, ARN["house_H"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(np.column_stack(arn.V), ARN["house_V"], rtol=0, atol=1e-11)
+    lan = kb.ArnoldiLanczos(As, v.copy())
+    T, Vs = [], [lan.v.copy()]
+    for k in range(20):
+        vv, h, _ = next(lan)
+        T.append(h.copy())
+        Vs.append(vv.copy())
+    np.testing.assert_allclose(np.array(T), ARN["lanczos_h"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(np.column_stack(Vs), ARN["lanczos_V"], rtol=0, atol=1e-10)
+    # invariant subspace -> ArgumentError on the next step (arnoldi.py:168-171)
+    arn = kb.ArnoldiMGS(np.diag([1.0, 2.0, 3.0]), np.array([1.0, 0.0, 0.0]))
+    next(arn)
+    assert arn.is_invariant
+    with pytest.raises(kb.ArgumentError):
+        next(arn)
+
+
+def test_givens_bit_exact():
+    fg = SML["givens_fg"]
+    Gm, r = kb.givens(np.ascontiguousarray(fg.T))
+    np.testing.assert_array_equal(Gm[0, 0], SML["givens_csr"][:, 0])
+    np.testing.assert_array_equal(Gm[0, 1], SML["givens_csr"][:, 1])
+    np.testing.assert_array_equal(r, SML["givens_csr"][:, 2])
+    np.testing.assert_array_equal(Gm[1, 0], -SML["givens_csr"][:, 1])
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((2, 4000)) * 10.0 ** rng.integers(-150, 150, (2, 4000))
+    Gm, r = kb.givens(X)
+    ref = np.array([orc.lartg_f64(f, g) for f, g in X.T])
+    np.testing.assert_array_equal(Gm[0, 0], ref[:, 0])
+    np.testing.assert_array_equal(Gm[0, 1], ref[:, 1])
+    np.testing.assert_array_equal(r, ref[:, 2])
+    Gb, rb = kb.givens(np.array([[1.0, 0.0, 3.0], [2.0, 5.0, -4.0]]))
+    np.testing.assert_array_equal(Gb, SML["givens_block_G"])
+    np.testing.assert_array_equal(rb, SML["givens_block_r"])
+
+
+def test_householder_matches_reference():
+    for i, x in enumerate(cases.householder_inputs()):
+        H = kb.Householder(x.copy())
+        np.testing.assert_allclose(H.v, SML[f"house{i}_v"], rtol=0, atol=2e-15)
+        np.testing.assert_allclose(
+            np.array([H.alpha, H.beta, H.xnorm], dtype=float), SML[f"house{i}_abx"], rtol=4e-16)
+        np.testing.assert_allclose(H @ x, SML[f"house{i}_Hx"], rtol=0, atol=4e-15)
+    with pytest.raises(AssertionError):
+        kb.Householder(np.ones((4, 2)))
