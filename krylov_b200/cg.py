@@ -64,8 +64,8 @@ class _LanczosLog:
         self._push(z0, r0, np.where(nrm0 > 0.0, nrm0, 1.0))
 
     def _push(self, z, r, d):
-        cd = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(d, (self.prob.k,)),
-                                                   dtype=np.float64)).to(self.prob.device)
+        cd = torch.from_numpy(np.array(np.broadcast_to(d, (self.prob.k,)),
+                                       dtype=np.float64)).to(self.prob.device)
         for lst, vec in ((self.V, z), (self.P, r)):
             out = torch.empty_like(vec)
             self.ops.div_scale(out, vec, cd)

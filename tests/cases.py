@@ -81,9 +81,13 @@ def solver_cases():
     a, A, b, Md = _pre_problem()
     n = len(b)
     w = 10.0 / np.arange(1, n + 1)
+    # Ml A must stay self-adjoint for cg/minres: diagonal A like the reference's test_ml
+    Adiag = np.diag(a)
+    Adiag[0, 0] = 1e-2
+    Mld = np.diag(1.0 / np.sqrt(a))
     for name in ["cg", "minres", "gmres"]:
         cases["pre_M_" + name] = (name, A, b, dict(M=Md, tol=1e-10))
-        cases["pre_Ml_" + name] = (name, A, b, dict(Ml=Md, tol=1e-10))
+        cases["pre_Ml_" + name] = (name, Adiag, b, dict(Ml=Mld, tol=1e-10))
         if name != "cg":
             cases["pre_Mr_" + name] = (name, A, b, dict(Mr=Md, tol=1e-10))
         cases["inner_" + name] = (

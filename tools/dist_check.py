@@ -1,0 +1,70 @@
+"""Run under torchrun: every rank solves its slab of a 3-D stencil problem with
+the row-partitioned matrix; rank 0 also solves the whole problem on one GPU and
+compares histories and solutions.  usage: dist_check.py out.json [N]"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+import krylov_b200 as kb
+from krylov_b200 import stencils as st
+from krylov_b200.dist import Comm, dist_stencil7, partition_rows
+from krylov_b200.generate import device_stencil7
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=dev)
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+comm = Comm()
+zoff = partition_rows(N, world) * N * N
+r0, r1 = int(zoff[rank]), int(zoff[rank + 1])
+g = torch.Generator(device=dev).manual_seed(0)
+xs = torch.randn(N ** 3, generator=g, dtype=torch.float64, device=dev)  # same on every rank
+results = {}
+
+def gather(xloc):
+    parts = [torch.empty(int(zoff[p + 1] - zoff[p]), dtype=torch.float64, device=dev) for p in range(world)]
+    dist.all_gather(parts, xloc.reshape(-1).contiguous())
+    return torch.cat(parts)
+
+cases = [
+    ("cg", st.STENCIL_POISSON, 0.0, lambda A, b: kb.cg(A, b, tol=1e-9, maxiter=3000)),
+    ("cg_k4", st.STENCIL_POISSON, 0.0, None),
+    ("minres", st.STENCIL_POISSON, st.mild_shift(N), lambda A, b: kb.minres(A, b, tol=1e-8, maxiter=5000)),
+    ("gmres_mgs", st.convdiff_coeffs(), 0.0, lambda A, b: kb.gmres(A, b, tol=1e-8, maxiter=40)),
+    ("gmres_mgs2", st.convdiff_coeffs(), 0.0, lambda A, b: kb.gmres(A, b, tol=1e-8, maxiter=40, ortho="mgs2")),
+]
+for name, coeffs, shift, fn in cases:
+    Ad = dist_stencil7(N, N, N, coeffs, shift, comm)
+    Afull = device_stencil7(N, N, N, coeffs, shift)
+    if name == "cg_k4":
+        X = torch.randn((N ** 3, 4), generator=g, dtype=torch.float64, device=dev)
+        bfull = Afull.matvec_device(X)
+        sol_d, info_d = kb.cg(Ad, bfull[r0:r1].contiguous(), tol=1e-9, maxiter=3000)
+        sol_f, info_f = kb.cg(Afull, bfull, tol=1e-9, maxiter=3000)
+        xd = torch.stack([gather(info_d.xk[:, c]) for c in range(4)], dim=1)
+    else:
+        bfull = Afull.matvec_device(xs)
+        sol_d, info_d = fn(Ad, bfull[r0:r1].contiguous())
+        sol_f, info_f = fn(Afull, bfull)
+        xd = gather(info_d.xk)
+    # product parity of the partitioned matrix itself
+    yd = gather(Ad.matvec_device(xs[r0:r1].contiguous()))
+    yf = Afull.matvec_device(xs)
+    hd, hf = np.asarray(info_d.resnorms, float), np.asarray(info_f.resnorms, float)
+    m = min(len(hd), len(hf))
+    live = hf[:m] / hf[0] >= 1e-6
+    rel = float(np.max((np.abs(hd[:m] - hf[:m]) / hf[:m])[live]))
+    results[name] = {
+        "steps": [int(info_d.numsteps), int(info_f.numsteps)],
+        "steps_equal": abs(info_d.numsteps - info_f.numsteps) <= max(1, 0.02 * info_f.numsteps),
+        "hist_rel": rel,
+        "sol_rel": float(torch.linalg.norm(xd - info_f.xk) / torch.linalg.norm(info_f.xk)),
+        "spmv_rel": float(torch.linalg.norm(yd - yf) / torch.linalg.norm(yf)),
+        "success": [bool(info_d.success), bool(info_f.success)],
+    }
+    del Ad, Afull
+if rank == 0:
+    json.dump(results, open(sys.argv[1], "w"), indent=1)
+    print(json.dumps(results, indent=1))
+dist.barrier()
+dist.destroy_process_group()
