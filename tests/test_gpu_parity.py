@@ -242,7 +242,7 @@ def _self_noise_envelope(make, extract, ncols):
     import math
 
     base = extract(make(lambda x, y: np.dot(x, y)))
-    env = [np.zeros(ncols) for _ in base]
+    env = [np.zeros(np.asarray(a).shape[-1]) for a in base]
     for inner in (lambda x, y: np.sum(x * y), lambda x, y: math.fsum(x * y)):
         alt = extract(make(inner))
         for i, (a, b) in enumerate(zip(alt, base)):
