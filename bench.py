@@ -361,20 +361,41 @@ def run_e2e(args, A, b, world, rank, dev, barrier):
     import krylov_b200 as kb
 
     if world > 1:
-        # the row blocks live on their GPUs by construction; the end-to-end call moves
-        # this rank's right-hand side and solution through pinned host memory
-        b_host = torch.empty(b.shape[0], dtype=torch.float64).pin_memory()
+        # every rank starts from ITS rows in pinned host memory (CSR slab with global
+        # column indices + its slice of b); the timed region uploads them, builds the
+        # row-partitioned operator (halo plan included), solves, and downloads x
+        from krylov_b200.csr import CsrMatrix
+        from krylov_b200.dist import DistCsrMatrix, partition_rows
+        from krylov_b200.generate import device_stencil7
+
+        N = args.size
+        zoff = partition_rows(N, world)
+        slab = device_stencil7(N, N, N, z_lo=int(zoff[rank]), z_hi=int(zoff[rank + 1]))
+        n_loc = slab.shape[0]
+        rp = torch.empty(n_loc + 1, dtype=torch.int32).pin_memory()
+        ci = torch.empty(slab.nnz, dtype=torch.int32).pin_memory()
+        va = torch.empty(slab.nnz, dtype=torch.float64).pin_memory()
+        rp.copy_(slab.rowptr)
+        ci.copy_(slab.colidx[: slab.nnz])
+        va.copy_(slab.vals[: slab.nnz])
+        b_host = torch.empty(n_loc, dtype=torch.float64).pin_memory()
         b_host.copy_(b.reshape(-1))
+        x_host = torch.empty(n_loc, dtype=torch.float64).pin_memory()
+        shape = slab.shape
+        del slab, A
+        torch.cuda.empty_cache()
         barrier()
         t0 = time.perf_counter()
-        sol, info = kb.cg(A, b_host.to(dev, non_blocking=True), tol=1e-8, maxiter=20000)
-        x_host = torch.empty(b.shape[0], dtype=torch.float64).pin_memory()
+        A2 = DistCsrMatrix(CsrMatrix(rp, ci, va, shape, dev), zoff * N * N)
+        sol, info = kb.cg(A2, b_host.to(dev, non_blocking=True), tol=1e-8, maxiter=20000)
         x_host.copy_(info.xk.reshape(-1))
         barrier()
         dt = time.perf_counter() - t0
-        h2d, d2h = b.numel() * 8 * world, b.numel() * 8 * world
-        how = ("krylov_b200.cg(DistCsrMatrix resident, b from pinned host memory, tol=1e-8): "
-               "per-rank H2D of b and D2H of x inside the timed region")
+        h2d = float((rp.numel() + ci.numel()) * 4 + va.numel() * 8 + n_loc * 8) * world
+        d2h = float(n_loc * 8) * world
+        how = ("per rank: CSR slab (global columns) + b slice in pinned host memory -> "
+               "DistCsrMatrix(CsrMatrix(host arrays)) -> krylov_b200.cg(tol=1e-8) -> x slice to pinned "
+               "host memory; uploads, halo-plan construction, solve and download inside the timed region")
     else:
         import scipy.sparse
 
