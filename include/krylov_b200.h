@@ -40,13 +40,15 @@ extern "C" {
 
 typedef struct kb_csr_s* kb_csr_t; /* CSR matrix view + schedule */
 typedef struct kb_ws_s* kb_ws_t;   /* reduction workspace + gate  */
+typedef struct kb_comm_s* kb_comm_t; /* peer-memory communicator (one per process/GPU) */
 
 /* --- library ---------------------------------------------------------- */
 int kb_version(void);
 int kb_last_error(char* buf, size_t len);
 int kb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* developer tunables: key 0 stream-kernel configuration (0..5), key 1 stream CTAs/SM
- * (0 = default), key 2 CTAs/SM of the vector and row-wise grids */
+ * (0 = default), key 2 CTAs/SM of the vector and row-wise grids, key 3 CTAs/SM of the
+ * pattern kernels, key 4 windowed-kernel configuration (-1 = gather variant) */
 int kb_tune(int key, int value);
 
 /* --- workspace -------------------------------------------------------- */
@@ -54,6 +56,23 @@ int kb_ws_create(kb_ws_t* ws, int max_k);
 int kb_ws_destroy(kb_ws_t ws);
 /* stop_at: device int (or NULL to disable); launches are skipped when *stop_at <= tag */
 int kb_ws_set_gate(kb_ws_t ws, const int* stop_at, int tag);
+
+/* --- peer-memory communicator (row-partitioned problems) ---
+ * One process per GPU on one NVLink/NVSwitch node.  Each rank creates a mailbox,
+ * exports its 64-byte CUDA-IPC handle, the handles of all ranks (rank order, 64
+ * bytes each) are handed to kb_comm_open.  A workspace with a communicator and
+ * collective = 1 finishes every reduction with a one-shot all-reduce INSIDE the
+ * reducing kernel's last block (values and flags written straight into the peers'
+ * mailboxes over NVLink): one kernel does the local partial, the exchange and the
+ * deterministic rank-ordered sum.  Replaces one NCCL all-reduce per inner product. */
+int kb_comm_create(kb_comm_t* c, int rank, int size, int max_k);
+int kb_comm_get_handle(kb_comm_t c, void* out64);
+int kb_comm_open(kb_comm_t c, const void* handles);
+int kb_comm_destroy(kb_comm_t c);
+int kb_comm_error(kb_comm_t c, int* err); /* 1 if a peer ever failed to arrive (synchronises) */
+int kb_ws_set_comm(kb_ws_t ws, kb_comm_t c, int collective);
+/* stand-alone fused all-reduce of slot[0..k) (one block) */
+int kb_allreduce(kb_ws_t ws, int k, double* slot, void* stream);
 
 /* --- CSR handle ------------------------------------------------------- */
 /* rowptr (n_rows+1, int32), colidx/vals (nnz) are device arrays owned by the
@@ -64,7 +83,10 @@ int kb_csr_create(kb_csr_t* h, int64_t n_rows, int64_t n_cols, int64_t nnz,
                   const int32_t* rowptr, const int32_t* colidx, const double* vals,
                   int padded, void* stream);
 int kb_csr_destroy(kb_csr_t h);
-/* schedule: 0 = auto, 1 = row-wise generic kernel, 2 = TMA-staged stream kernel (k == 1) */
+/* schedule: 0 = auto, 1 = row-wise generic kernel, 2 = TMA-staged stream kernel (k == 1),
+ * 3 = TMA-staged stream kernel on offset-pattern compressed indices (k == 1; needs <= 16
+ * distinct diagonals col-row and ascending columns, detected by kb_csr_create, which then
+ * owns one 16-bit mask per row) */
 int kb_csr_set_schedule(kb_csr_t h, int schedule);
 int kb_csr_get_info(kb_csr_t h, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
                     int* max_row_len, int* schedule);
@@ -102,16 +124,19 @@ int kb_dot(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, doubl
 
 /* --- CG (cg.py:155-234) ------------------------------------------------ */
 /* alpha = rho / nz(pAp [+ pAp2]);  x += alpha p;  r -= alpha Ap;  rr = <r, r>
- * (cg.py:185,196,200,209).  pAp2 may be NULL (halo dot correction otherwise). */
+ * (cg.py:185,196,200,209).  pAp2 may be NULL.  x == NULL defers the x update to the
+ * next kb_cg_update_p (what & 4), which reads p anyway: 24 instead of 48 B/element here. */
 int kb_cg_update_xr(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
                     const double* pAp2, const double* p, const double* Ap, double* x,
                     double* r, double* rr_out, void* stream);
 /* what & 2: record resnorm[step] = sqrt(rho_new) into hist[step*k + c]; if all
  *           columns satisfy resnorm <= crit[c] set *stop_at = step (cg.py:156,214-217)
+ * what & 4: x += (rho_old / nz(pAp)) p  -- the previous iteration's deferred update,
+ *           taken before p is overwritten (cg.py:196)
  * what & 1: omega = rho_new / nz(rho_old);  p = r + omega p  (cg.py:175-178) */
 int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new,
-                   const double* rho_old, const double* crit, double* hist, int* stop_at,
-                   const double* r, double* p, int what, void* stream);
+                   const double* rho_old, const double* pAp, const double* crit, double* hist,
+                   int* stop_at, const double* r, double* p, double* x, int what, void* stream);
 
 /* --- generic vector kernels (fallback path for M/Ml/Mr/custom inner) ---- */
 /* y += sign * coef[c] * x   (product rounded, then sum: NumPy temporaries) */

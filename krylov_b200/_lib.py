@@ -56,6 +56,13 @@ SIGNATURES = {
     "kb_ws_create": [C.POINTER(vp), i32],
     "kb_ws_destroy": [vp],
     "kb_ws_set_gate": [vp, vp, i32],
+    "kb_comm_create": [C.POINTER(vp), i32, i32, i32],
+    "kb_comm_get_handle": [vp, vp],
+    "kb_comm_open": [vp, vp],
+    "kb_comm_destroy": [vp],
+    "kb_comm_error": [vp, C.POINTER(i32)],
+    "kb_ws_set_comm": [vp, vp, i32],
+    "kb_allreduce": [vp, i32, vp, vp],
     "kb_csr_create": [C.POINTER(vp), i64, i64, i64, vp, vp, vp, i32, vp],
     "kb_csr_destroy": [vp],
     "kb_csr_set_schedule": [vp, i32],
@@ -66,7 +73,7 @@ SIGNATURES = {
     "kb_pack_rows": [vp, i32, i64, vp, vp, vp, vp],
     "kb_dot": [vp, i64, i32, vp, vp, vp, vp],
     "kb_cg_update_xr": [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
-    "kb_cg_update_p": [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "kb_cg_update_p": [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "kb_axpy": [vp, i64, i32, f64, vp, vp, vp, vp],
     "kb_xpby": [vp, i64, i32, vp, vp, vp, vp],
     "kb_div_scale": [vp, i64, i32, vp, vp, vp, vp],

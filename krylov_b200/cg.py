@@ -121,6 +121,10 @@ class FusedCG:
         self.crit_d = torch.from_numpy(np.ascontiguousarray(self.crit)).to(self.dev)
         self.p = self.r.clone()
         self.kk = 0
+        # x += alpha p of the last enqueued iteration is deferred into the next p
+        # update (which streams p anyway: 64 instead of 72 B/element for the two
+        # vector kernels of a step); current_x() flushes it
+        self.x_pending = False
 
     def _residual_norm2(self, x, out_vec, slot):
         """out_vec = b - A x; returns host <out_vec, out_vec> (k,)."""
@@ -130,7 +134,15 @@ class FusedCG:
     def explicit_resnorm(self, xk):
         return np.sqrt(self._residual_norm2(xk, self.Ap, self.sl[3]))
 
+    def flush_x(self):
+        if self.x_pending:
+            i = self.kk - 1  # last completed iteration: alpha_i = rho_i / <p_i, A p_i>
+            self.ops.gate(None, 0)
+            self.ops.cg_flush_x(self.sl[i % 2], self.sl[2], self.p, self.yk)
+            self.x_pending = False
+
     def current_x(self):
+        self.flush_x()
         xk = torch.empty_like(self.yk)
         self.ops.add(xk, self.x0, self.yk)
         return xk
@@ -140,7 +152,11 @@ class FusedCG:
         cur, nxt = sl[i % 2], sl[(i + 1) % 2]
         ops.gate(self.stop_at, i)  # iteration i is a no-op once a step <= i converged
         if i > 0:
-            ops.cg_update_p(cur, nxt, self.r, self.p)  # omega = rho_i / rho_{i-1}; p = r + omega p
+            # [x += alpha_{i-1} p;]  omega = rho_i / rho_{i-1};  p = r + omega p
+            if self.x_pending:
+                ops.cg_update_p(cur, nxt, self.r, self.p, x=self.yk, pAp=sl[2])
+            else:
+                ops.cg_update_p(cur, nxt, self.r, self.p)
         if self.spmv_events is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
@@ -149,7 +165,8 @@ class FusedCG:
         if self.spmv_events is not None:
             e1.record()
             self.spmv_events.append((e0, e1))
-        ops.cg_update_xr(cur, sl[2], None, self.p, self.Ap, self.yk, self.r, nxt)  # rho_{i+1}
+        ops.cg_update_xr(cur, sl[2], None, None, self.Ap, None, self.r, nxt)  # r, rho_{i+1}
+        self.x_pending = True
         ops.cg_record(i + 1, nxt, self.crit_d, hist_ptr, self.stop_at)
 
     def run(self, nb):

@@ -14,7 +14,7 @@ import torch
 from ._lib import check, lib
 from .device import Ops, as_device_matrix, cur_stream, ptr, require_cuda
 
-_SCHEDULES = {"auto": 0, "rowwise": 1, "stream": 2}
+_SCHEDULES = {"auto": 0, "rowwise": 1, "stream": 2, "pattern": 3}
 _PAD = 4  # elements readable past nnz (TMA tiles are 4-aligned windows)
 
 
@@ -114,7 +114,7 @@ class CsrMatrix:
                                   C.byref(sc)))
         return {"n_rows": nr.value, "n_cols": nc.value, "nnz": nz.value,
                 "max_row_len": mx.value,
-                "schedule": {1: "rowwise", 2: "stream"}[sc.value]}
+                "schedule": {1: "rowwise", 2: "stream", 3: "pattern"}[sc.value]}
 
     def set_schedule(self, name: str):
         check(lib.kb_csr_set_schedule(self.handle, _SCHEDULES[name]))

@@ -27,8 +27,12 @@ struct kb_csr_s {
   const double* vals;
   int padded;
   int max_row_len;
-  int schedule;  // 1 row-wise, 2 TMA stream
+  int schedule;  // 1 row-wise, 2 TMA stream, 3 offset-pattern compressed TMA stream
   int forced;    // user override (0 = auto)
+  // offset-pattern compression (library-owned): one 16-bit mask per row
+  uint16_t* masks;
+  KbPattern pat;
+  int pattern_ok;
 };
 
 
@@ -37,7 +41,93 @@ static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
 // runtime tunables (kb_tune): stream-kernel configuration and grid sizing
 static int g_stream_cfg = 0;
 static int g_stream_ctas = 0;  // 0 = configuration default
+static int g_pattern_ctas = 0; // kb_tune key 3 (0 = default)
+static int g_window_cfg = 0;   // kb_tune key 4
 int g_vec_ctas = KB_CTAS_PER_SM;
+
+// Finds the set of distinct diagonals (col - row); if there are at most 16 and every
+// row lists its entries in ascending column order, builds the per-row masks.
+static int kb_detect_pattern(kb_csr_s* h, cudaStream_t st) {
+  int* d_tab = nullptr;  // 64 hash slots + overflow + fail
+  KB_CUDA(cudaMalloc(&d_tab, sizeof(int) * 66));
+  int init[66];
+  for (int i = 0; i < 64; ++i) init[i] = KB_PAT_EMPTY;
+  init[64] = init[65] = 0;
+  cudaError_t e = cudaMemcpyAsync(d_tab, init, sizeof(init), cudaMemcpyHostToDevice, st);
+  int grid = (int)((h->n_rows + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  int res[66];
+  if (e == cudaSuccess) {
+    kb_pattern_collect_kernel<<<grid, 256, 0, st>>>(h->n_rows, h->rowptr, h->colidx, d_tab,
+                                                    d_tab + 64);
+    e = cudaMemcpyAsync(res, d_tab, sizeof(res), cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    cudaFree(d_tab);
+    return kb_fail(KB_ECUDA, "kb_detect_pattern: %s", cudaGetErrorString(e));
+  }
+  int offs[64], nd = 0;
+  for (int i = 0; i < 64; ++i)
+    if (res[i] != KB_PAT_EMPTY) offs[nd++] = res[i];
+  if (res[64] != 0 || nd == 0 || nd > 16) {
+    cudaFree(d_tab);
+    return KB_OK;  // not stencil-like: keep the CSR schedules
+  }
+  for (int i = 1; i < nd; ++i)  // insertion sort, ascending
+    for (int j = i; j > 0 && offs[j - 1] > offs[j]; --j) {
+      int t = offs[j];
+      offs[j] = offs[j - 1];
+      offs[j - 1] = t;
+    }
+  h->pat.nd = nd;
+  for (int i = 0; i < 16; ++i) h->pat.off[i] = i < nd ? offs[i] : 0;
+  // group nearby diagonals into contiguous x windows (windowed kernel)
+  h->pat.nw = 0;
+  for (int i = 0; i < 16; ++i) h->pat.grp[i] = h->pat.dwlo[i] = 0;
+  for (int i = 0; i < 8; ++i) h->pat.wlo[i] = h->pat.wspan[i] = 0;
+  if (nd <= 8) {
+    int nw = 0;
+    bool ok = true;
+    for (int i = 0; i < nd; ++i) {
+      if (nw > 0 && offs[i] - h->pat.wlo[nw - 1] <= KB_WIN_SLACK - 10) {
+        h->pat.wspan[nw - 1] = offs[i] - h->pat.wlo[nw - 1];
+      } else {
+        if (nw == 8) {
+          ok = false;
+          break;
+        }
+        h->pat.wlo[nw] = offs[i];
+        h->pat.wspan[nw] = 0;
+        ++nw;
+      }
+      h->pat.grp[i] = nw - 1;
+      h->pat.dwlo[i] = h->pat.wlo[nw - 1];
+    }
+    h->pat.nw = ok ? nw : 0;
+  }
+  e = cudaMalloc(&h->masks, sizeof(uint16_t) * (size_t)h->n_rows);
+  if (e != cudaSuccess) {
+    h->masks = nullptr;
+    cudaFree(d_tab);
+    cudaGetLastError();
+    return KB_OK;  // no memory for the masks: keep the CSR schedules
+  }
+  kb_pattern_build_kernel<<<grid, 256, 0, st>>>(h->n_rows, h->rowptr, h->colidx, h->pat, h->masks,
+                                                d_tab + 65);
+  int fail = 1;
+  e = cudaMemcpyAsync(&fail, d_tab + 65, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_tab);
+  if (e != cudaSuccess) return kb_fail(KB_ECUDA, "kb_detect_pattern: %s", cudaGetErrorString(e));
+  if (fail) {
+    cudaFree(h->masks);
+    h->masks = nullptr;
+    return KB_OK;
+  }
+  h->pattern_ok = 1;
+  return KB_OK;
+}
 
 extern "C" {
 
@@ -55,6 +145,8 @@ int kb_tune(int key, int value) {
     case 0: g_stream_cfg = value; return KB_OK;
     case 1: g_stream_ctas = value; return KB_OK;
     case 2: g_vec_ctas = value > 0 ? value : KB_CTAS_PER_SM; return KB_OK;
+    case 3: g_pattern_ctas = value; return KB_OK;
+    case 4: g_window_cfg = value; return KB_OK;  // -1: gather variant of the pattern kernel
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -87,6 +179,8 @@ int kb_ws_create(kb_ws_t* out, int max_k) {
   ws->num_sms = sms;
   ws->gate = nullptr;
   ws->gate_tag = 0;
+  ws->comm = nullptr;
+  ws->collective = 0;
   cudaError_t e = cudaMalloc(&ws->partials, sizeof(double) * KB_MAX_BLOCKS * (size_t)max_k);
   if (e == cudaSuccess) e = cudaMalloc(&ws->ticket, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(ws->ticket, 0, sizeof(unsigned int));
@@ -113,6 +207,102 @@ int kb_ws_set_gate(kb_ws_t ws, const int* stop_at, int tag) {
   return KB_OK;
 }
 
+// ------------------------------------------------------------ peer comm --
+int kb_comm_create(kb_comm_t* out, int rank, int size, int max_k) {
+  KB_REQUIRE(out != nullptr, "null handle pointer");
+  KB_REQUIRE(size >= 1 && size <= 64 && rank >= 0 && rank < size, "bad rank/size");
+  KB_REQUIRE(max_k >= 1 && max_k <= KB_MAX_K, "max_k out of range [1, 256]");
+  kb_comm_s* c = new (std::nothrow) kb_comm_s();
+  if (!c) return kb_fail(KB_ENOMEM, "out of host memory");
+  memset(c, 0, sizeof(*c));
+  c->max_k = max_k;
+  c->dev.rank = rank;
+  c->dev.size = size;
+  c->dev.stride = ((1 + max_k + 15) / 16) * 16;  // 128-byte multiples
+  // mailbox | counter | error live in one IPC-exported allocation
+  const size_t mbox_doubles = (size_t)2 * size * c->dev.stride;
+  const size_t bytes = (mbox_doubles + 16) * sizeof(double);
+  cudaError_t e = cudaMalloc(&c->mailbox, bytes);
+  if (e == cudaSuccess) e = cudaMemset(c->mailbox, 0, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&c->peers_dev, sizeof(double*) * size);
+  if (e != cudaSuccess) {
+    if (c->mailbox) cudaFree(c->mailbox);
+    delete c;
+    return kb_fail(KB_ECUDA, "kb_comm_create: %s", cudaGetErrorString(e));
+  }
+  c->dev.counter = reinterpret_cast<unsigned long long*>(c->mailbox + mbox_doubles);
+  c->dev.error = reinterpret_cast<int*>(c->mailbox + mbox_doubles + 8);
+  c->dev.peers = c->peers_dev;
+  *out = c;
+  return KB_OK;
+}
+
+int kb_comm_get_handle(kb_comm_t c, void* out64) {
+  KB_REQUIRE(c != nullptr && out64 != nullptr, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  KB_CUDA(cudaIpcGetMemHandle(&h, c->mailbox));
+  memcpy(out64, &h, 64);
+  return KB_OK;
+}
+
+int kb_comm_open(kb_comm_t c, const void* handles) {
+  KB_REQUIRE(c != nullptr && handles != nullptr, "null argument");
+  KB_REQUIRE(!c->opened, "already opened");
+  double* table[64];
+  for (int p = 0; p < c->dev.size; ++p) {
+    if (p == c->dev.rank) {
+      table[p] = c->mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * (size_t)p, 64);
+    void* base = nullptr;
+    KB_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_base[p] = base;
+    table[p] = (double*)base;
+  }
+  KB_CUDA(cudaMemcpy(c->peers_dev, table, sizeof(double*) * c->dev.size, cudaMemcpyHostToDevice));
+  c->opened = 1;
+  return KB_OK;
+}
+
+int kb_comm_destroy(kb_comm_t c) {
+  if (!c) return KB_OK;
+  for (int p = 0; p < c->dev.size; ++p)
+    if (c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
+  if (c->peers_dev) cudaFree(c->peers_dev);
+  if (c->mailbox) cudaFree(c->mailbox);
+  delete c;
+  return KB_OK;
+}
+
+int kb_comm_error(kb_comm_t c, int* err) {
+  KB_REQUIRE(c != nullptr && err != nullptr, "null argument");
+  KB_CUDA(cudaMemcpy(err, c->dev.error, sizeof(int), cudaMemcpyDeviceToHost));
+  return KB_OK;
+}
+
+int kb_ws_set_comm(kb_ws_t ws, kb_comm_t c, int collective) {
+  KB_REQUIRE(ws != nullptr, "null workspace");
+  KB_REQUIRE(c == nullptr || c->opened || c->dev.size == 1, "communicator not opened");
+  KB_REQUIRE(c == nullptr || c->max_k >= ws->max_k, "communicator max_k too small");
+  ws->comm = c;
+  ws->collective = collective ? 1 : 0;
+  return KB_OK;
+}
+
+int kb_allreduce(kb_ws_t ws, int k, double* slot, void* stream) {
+  KB_REQUIRE(ws != nullptr && slot != nullptr, "null argument");
+  KB_REQUIRE(ws->comm != nullptr, "workspace has no communicator");
+  KB_REQUIRE(k >= 1 && k <= ws->max_k, "k exceeds workspace max_k");
+  KbRed rd = kb_red(ws);
+  const int block = ((k > ws->comm->dev.size ? k : ws->comm->dev.size) + 31) / 32 * 32;
+  kb_allreduce_kernel<<<1, block, 0, S(stream)>>>(k, slot, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
 // ------------------------------------------------------------------ CSR --
 static void kb_csr_pick(kb_csr_s* h) {
   // Row-length statistics -> schedule (SURVEY.md 7 "short rows").  The stream
@@ -124,8 +314,10 @@ static void kb_csr_pick(kb_csr_s* h) {
   if (h->padded && h->n_rows >= 1 && h->n_rows < (1ll << 31) - 512 && mean <= 32.0 &&
       h->max_row_len <= 8 * (mean + 8.0))
     sched = 2;
+  if (sched == 2 && h->pattern_ok) sched = 3;
   if (h->forced == 1) sched = 1;
   if (h->forced == 2 && h->padded) sched = 2;
+  if (h->forced == 3 && h->pattern_ok) sched = 3;
   h->schedule = sched;
 }
 
@@ -168,21 +360,36 @@ int kb_csr_create(kb_csr_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz,
       return kb_fail(KB_ECUDA, "kb_csr_create: %s", cudaGetErrorString(e));
     }
   }
+  h->masks = nullptr;
+  h->pattern_ok = 0;
+  h->pat.nd = 0;
+  if (padded && n_rows > 0 && n_rows < (1ll << 31) - 1024 && n_cols < (1ll << 31) &&
+      h->max_row_len >= 1 && h->max_row_len <= 16) {
+    int rc = kb_detect_pattern(h, S(stream));
+    if (rc != KB_OK) {
+      delete h;
+      return rc;
+    }
+  }
   kb_csr_pick(h);
   *out = h;
   return KB_OK;
 }
 
 int kb_csr_destroy(kb_csr_t h) {
+  if (h && h->masks) cudaFree(h->masks);
   delete h;
   return KB_OK;
 }
 
 int kb_csr_set_schedule(kb_csr_t h, int schedule) {
   KB_REQUIRE(h != nullptr, "null matrix");
-  KB_REQUIRE(schedule >= 0 && schedule <= 2, "schedule must be 0, 1 or 2");
+  KB_REQUIRE(schedule >= 0 && schedule <= 3, "schedule must be 0, 1, 2 or 3");
   if (schedule == 2 && !h->padded)
     return kb_fail(KB_EUNSUPPORTED, "stream schedule needs padded, 16-byte aligned CSR arrays");
+  if (schedule == 3 && !h->pattern_ok)
+    return kb_fail(KB_EUNSUPPORTED,
+                   "pattern schedule needs <= 16 distinct diagonals and ascending columns");
   h->forced = schedule;
   kb_csr_pick(h);
   return KB_OK;
@@ -242,6 +449,94 @@ static int kb_launch_stream(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y
   }
 }
 
+template <int MAXD, int MINCTAS, int DOT>
+static int kb_launch_pattern_cfg(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                                 const double* z, const double* coef, const double* w, double* out,
+                                 cudaStream_t st) {
+  constexpr int ROWS = 512, STAGES = 2, CAP = 4096;
+  typedef KbPatternSmem<STAGES, CAP> Smem;
+  static bool configured[64] = {false};
+  auto kern = kb_spmv_pattern_kernel<ROWS, STAGES, CAP, MAXD, MINCTAS, DOT>;
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(Smem)));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const int n_tiles = (int)((A->n_rows + ROWS - 1) / ROWS);
+  int grid = ws->num_sms * (g_pattern_ctas > 0 ? g_pattern_ctas : MINCTAS);
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
+  kern<<<grid, ROWS + 32, sizeof(Smem), st>>>((int)A->n_rows, n_tiles, A->rowptr, A->masks, A->vals,
+                                              A->pat, x, y, mode, z, coef, w, out, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+template <int ROWS, int STAGES, int MINB, int DOT>
+static int kb_launch_window_cfg(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                                const double* z, const double* coef, const double* w, double* out,
+                                cudaStream_t st) {
+  static int max_smem[64] = {0};  // per device: opt-in dynamic shared memory limit once set
+  auto kern = kb_spmv_window_kernel<ROWS, STAGES, MINB, DOT>;
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  // stage buffers sized from the actual pattern
+  int span = 0;
+  for (int g = 0; g < A->pat.nw; ++g) span = A->pat.wspan[g] > span ? A->pat.wspan[g] : span;
+  const int cap = (ROWS * A->pat.nd + 8 + 3) & ~3;
+  const int wlen = (ROWS + span + 6 + 1) & ~1;
+  const size_t smem = ((size_t)STAGES * cap + (size_t)STAGES * A->pat.nw * wlen) * 8 + 16 * STAGES;
+  if (dev < 0 || dev >= 64 || max_smem[dev] == 0) {
+    int lim = 0;
+    KB_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lim - 8 * 1024));
+    if (dev >= 0 && dev < 64) max_smem[dev] = lim - 8 * 1024;
+  }
+  int ctas = 0;
+  KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, ROWS + 32, smem));
+  if (ctas < 1) return kb_fail(KB_EUNSUPPORTED, "windowed SpMV: stage buffers do not fit");
+  if (g_pattern_ctas > 0 && g_pattern_ctas < ctas) ctas = g_pattern_ctas;
+  const int n_tiles = (int)((A->n_rows + ROWS - 1) / ROWS);
+  int grid = ws->num_sms * ctas;
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
+  kern<<<grid, ROWS + 32, smem, st>>>((int)A->n_rows, (int)A->n_cols, n_tiles, cap, wlen, A->rowptr,
+                                      A->masks, A->vals, A->pat, x, y, mode, z, coef, w, out,
+                                      kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+// windowed kernel applicable to this product?
+static inline bool kb_window_ok(const kb_csr_s* A, const double* x) {
+  return A->pat.nw > 0 && (A->n_cols % 2 == 0) && ((uintptr_t)x % 16 == 0);
+}
+
+template <int DOT>
+static int kb_launch_window(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                            const double* z, const double* coef, const double* w, double* out,
+                            cudaStream_t st) {
+  switch (g_window_cfg) {
+    case 1: return kb_launch_window_cfg<256, 3, 3, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 2: return kb_launch_window_cfg<512, 2, 2, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 3: return kb_launch_window_cfg<128, 2, 7, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 4: return kb_launch_window_cfg<128, 3, 6, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 5: return kb_launch_window_cfg<256, 2, 5, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    default: return kb_launch_window_cfg<256, 2, 4, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+  }
+}
+
+template <int DOT>
+static int kb_launch_pattern(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                             const double* z, const double* coef, const double* w, double* out,
+                             cudaStream_t st) {
+  if (A->pat.nd <= 8) return kb_launch_pattern_cfg<8, 2, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+  return kb_launch_pattern_cfg<16, 1, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+}
+
 extern "C" {
 
 int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode, const double* z,
@@ -260,7 +555,17 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
     if (dot) KB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * k, st));
     return KB_OK;
   }
-  if (k == 1 && A->schedule == 2) {
+  if (k == 1 && A->schedule == 3 && g_window_cfg >= 0 && kb_window_ok(A, x)) {
+    if (dot == 0) return kb_launch_window<0>(A, ws, x, y, mode, z, coef, w, out, st);
+    if (dot == 1) return kb_launch_window<1>(A, ws, x, y, mode, z, coef, w, out, st);
+    return kb_launch_window<2>(A, ws, x, y, mode, z, coef, w, out, st);
+  }
+  if (k == 1 && A->schedule == 3) {
+    if (dot == 0) return kb_launch_pattern<0>(A, ws, x, y, mode, z, coef, w, out, st);
+    if (dot == 1) return kb_launch_pattern<1>(A, ws, x, y, mode, z, coef, w, out, st);
+    return kb_launch_pattern<2>(A, ws, x, y, mode, z, coef, w, out, st);
+  }
+  if (k == 1 && A->schedule >= 2) {
     if (dot == 0) return kb_launch_stream<0>(A, ws, x, y, mode, z, coef, w, out, st);
     if (dot == 1) return kb_launch_stream<1>(A, ws, x, y, mode, z, coef, w, out, st);
     return kb_launch_stream<2>(A, ws, x, y, mode, z, coef, w, out, st);
@@ -340,24 +645,31 @@ int kb_cg_update_xr(kb_ws_t ws, int64_t n, int k, const double* rho, const doubl
                     const double* pAp2, const double* p, const double* Ap, double* x, double* r,
                     double* rr_out, void* stream) {
   KB_VEC_PROLOGUE();
-  KB_REQUIRE(rho && pAp && p && Ap && x && r && rr_out, "null argument");
+  KB_REQUIRE(rho && pAp && Ap && r && rr_out, "null argument");
+  KB_REQUIRE((x == nullptr) || (p != nullptr), "x update needs p");
   const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
-  kb_cg_update_xr_kernel<<<grid, block, 0, st>>>(total, k, rho, pAp, pAp2, p, Ap, x, r, rr_out, rd);
+  if (x != nullptr)
+    kb_cg_update_xr_kernel<true><<<grid, block, 0, st>>>(total, k, rho, pAp, pAp2, p, Ap, x, r,
+                                                         rr_out, rd);
+  else
+    kb_cg_update_xr_kernel<false><<<grid, block, 0, st>>>(total, k, rho, pAp, pAp2, p, Ap, x, r,
+                                                          rr_out, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
 
 int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new,
-                   const double* rho_old, const double* crit, double* hist, int* stop_at,
-                   const double* r, double* p, int what, void* stream) {
+                   const double* rho_old, const double* pAp, const double* crit, double* hist,
+                   int* stop_at, const double* r, double* p, double* x, int what, void* stream) {
   KB_VEC_PROLOGUE();
-  KB_REQUIRE(what >= 1 && what <= 3, "what must be 1 (update p), 2 (record) or 3");
-  KB_REQUIRE(rho_new != nullptr, "null rho_new");
-  KB_REQUIRE(!(what & 2) || (crit && hist && stop_at), "record needs crit, hist, stop_at");
-  KB_REQUIRE(!(what & 1) || (r && p && rho_old), "update needs r, p, rho_old");
-  const int grid = (what & 1) ? kb_grid_for(ws, total, block, KB_UNROLL) : 1;
-  kb_cg_update_p_kernel<<<grid, block, 0, st>>>(total, k, step, rho_new, rho_old, crit, hist,
-                                                stop_at, r, p, what, rd);
+  KB_REQUIRE(what >= 1 && what <= 7, "what is a mask of 1 (update p), 2 (record), 4 (update x)");
+  KB_REQUIRE(!(what & 2) || (rho_new && crit && hist && stop_at),
+             "record needs rho_new, crit, hist, stop_at");
+  KB_REQUIRE(!(what & 1) || (r && p && rho_new && rho_old), "p update needs r, p, rho_new, rho_old");
+  KB_REQUIRE(!(what & 4) || (x && p && rho_old && pAp), "x update needs x, p, rho_old, pAp");
+  const int grid = (what & 5) ? kb_grid_for(ws, total, block, KB_UNROLL) : 1;
+  kb_cg_update_p_kernel<<<grid, block, 0, st>>>(total, k, step, rho_new, rho_old, pAp, crit, hist,
+                                                stop_at, r, p, x, what, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

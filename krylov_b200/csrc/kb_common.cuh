@@ -36,6 +36,35 @@ int kb_fail(int code, const char* fmt, ...);
       return kb_fail(KB_ECUDA, "%s: launch failed: %s", __func__, cudaGetErrorString(e_)); \
   } while (0)
 
+// ------------------------------------------------------------ peer comm --
+// One-shot all-reduce over NVLink peer memory, fused into the last block of a
+// reduction kernel ("custom one-shot P2P allreduce fused into the
+// reduction kernel's last-block epilogue").  Every rank owns a mailbox
+//   mbox[parity][src_rank][stride]   (u64 flag, then k doubles)
+// mapped into every peer with CUDA IPC.  A collective with sequence number q
+// writes this rank's k partial sums into slot [q & 1][rank] of EVERY rank's
+// mailbox (plain stores over NVLink), fences, stores the flag q, then waits until
+// all `size` flags of its own mailbox show q and adds the contributions in rank
+// order (deterministic, identical on all ranks).  q is a device-resident counter,
+// so launches skipped by the gate do not consume a number and parities alternate:
+// a rank can only overwrite slot [q & 1] after every peer has finished reading
+// collective q - 2 (it needed their contribution to q - 1).
+struct KbComm {
+  double* const* peers;         // device array [size]: mailbox base of every rank (peer-mapped)
+  unsigned long long* counter;  // this rank's collective sequence counter
+  int* error;                   // set to 1 if a peer did not arrive within the spin budget
+  int rank, size, stride;       // stride in doubles per (parity, src) slot
+};
+
+struct kb_comm_s {
+  KbComm dev;
+  double* mailbox;       // own mailbox (cudaMalloc, IPC-exported)
+  double** peers_dev;    // device copy of the pointer table
+  void* peer_base[64];   // opened IPC mappings (host view)
+  int max_k;
+  int opened;
+};
+
 // ------------------------------------------------------------- workspace --
 struct kb_ws_s {
   double* partials;      // KB_MAX_BLOCKS * max_k doubles
@@ -44,6 +73,8 @@ struct kb_ws_s {
   int num_sms;
   const int* gate;       // device int or nullptr
   int gate_tag;
+  kb_comm_s* comm;       // optional: fused all-reduce of every finished reduction
+  int collective;        // 1: reductions launched now end with the all-reduce
 };
 
 // Passed by value to every kernel.
@@ -52,6 +83,8 @@ struct KbRed {
   unsigned int* ticket;
   const int* gate;
   int gate_tag;
+  int collective;
+  KbComm cm;
 };
 
 static inline KbRed kb_red(const kb_ws_s* ws) {
@@ -60,6 +93,17 @@ static inline KbRed kb_red(const kb_ws_s* ws) {
   r.ticket = ws->ticket;
   r.gate = ws->gate;
   r.gate_tag = ws->gate_tag;
+  r.collective = (ws->comm != nullptr && ws->collective) ? 1 : 0;
+  if (ws->comm != nullptr) {
+    r.cm = ws->comm->dev;
+  } else {
+    r.cm.peers = nullptr;
+    r.cm.counter = nullptr;
+    r.cm.error = nullptr;
+    r.cm.rank = 0;
+    r.cm.size = 1;
+    r.cm.stride = 0;
+  }
   return r;
 }
 
@@ -130,6 +174,44 @@ __device__ __forceinline__ double kb_block_colsum(double acc, int k, double* sm)
   return tot;
 }
 
+// All-reduce of k values held by threads t < k of ONE block (see KbComm).  Must be
+// called by every thread of that block.  Returns the global sum in threads t < k.
+__device__ __forceinline__ double kb_p2p_allreduce(double v, int k, const KbComm& cm) {
+  __shared__ unsigned long long s_seq;
+  const int t = threadIdx.x;
+  if (t == 0) s_seq = ++(*cm.counter);
+  __syncthreads();
+  const unsigned long long q = s_seq;
+  const size_t slot = ((size_t)(q & 1ull) * cm.size + cm.rank) * cm.stride;
+  if (t < k)
+    for (int p = 0; p < cm.size; ++p) cm.peers[p][slot + 1 + t] = v;
+  __threadfence_system();
+  __syncthreads();
+  if (t < cm.size)  // one thread per destination publishes the flag
+    *reinterpret_cast<volatile unsigned long long*>(cm.peers[t] + slot) = q;
+  // wait for every source's flag in the own mailbox
+  const double* mine = cm.peers[cm.rank];
+  if (t < cm.size) {
+    const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(
+        mine + ((size_t)(q & 1ull) * cm.size + t) * cm.stride);
+    const long long t0 = clock64();
+    while (*f != q) {
+      if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer is gone; fail loudly, do not hang
+        *cm.error = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  double tot = 0.0;
+  if (t < k)
+    for (int p = 0; p < cm.size; ++p)
+      tot += *reinterpret_cast<const volatile double*>(
+          mine + ((size_t)(q & 1ull) * cm.size + p) * cm.stride + 1 + t);
+  return tot;
+}
+
 // Finish a grid-wide column-wise reduction in the same launch: every block
 // publishes its partial, the last block to arrive (ticket) adds the partials
 // in block order and writes out[0..k).  `acc` follows the kb_block_colsum
@@ -173,7 +255,13 @@ __device__ __forceinline__ void kb_grid_colsum(double acc, int k, const KbRed& r
       }
     }
     // accumulate: add to what an earlier launch on this stream left in out[]
-    if (t < k) out[t] = accumulate ? out[t] + fin : fin;
+    if (accumulate && t < k) fin += out[t];
+    // row-partitioned problems: sum over ranks through NVLink peer memory, same launch
+    if (rd.collective && rd.cm.size > 1) {
+      fin = kb_p2p_allreduce(fin, k, rd.cm);
+      if (t < k && *rd.cm.error) fin = nan("");
+    }
+    if (t < k) out[t] = fin;
     if (t == 0) *rd.ticket = 0u;  // ready for the next launch on this stream
   }
 }

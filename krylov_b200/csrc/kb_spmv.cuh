@@ -264,6 +264,401 @@ kb_spmv_stream_kernel(int n_rows, int n_tiles, const int32_t* __restrict__ rowpt
   if (DOT != 0) kb_grid_colsum(acc, 1, rd, out, red_sm);
 }
 
+// ------------------------------------------- offset-pattern compressed stream --
+// Stencil-like matrices have only a handful of distinct diagonals: every column
+// index is row + D[d] for d in a set of <= 16 offsets.  kb_csr_create detects
+// this and stores ONE 16-bit mask per row (which diagonals are present) instead
+// of one 32-bit index per nonzero; the values stay in CSR order, so the row sum
+// visits the same products in the same order (bit-identical result) while the
+// matrix stream shrinks from 12 to 8 bytes per nonzero (+2 per row).
+// Per launch: 8 nnz + 2 n + 4 (n+1) + 16 n bytes  (7-point: 78 instead of 104 B/row).
+struct KbPattern {
+  int nd;
+  int off[16];   // ascending diagonal offsets col - row
+  // x windows of the windowed kernel: nearby diagonals share one contiguous window
+  int nw;        // number of windows (0: windowed kernel not applicable)
+  int wlo[8];    // window g of the tile starting at row r0 begins at x[r0 + wlo[g]]
+  int wspan[8];  // ... and holds ROWS + wspan[g] entries
+  int grp[16];   // window of diagonal d
+  int dwlo[16];  // wlo[grp[d]]
+};
+
+#define KB_PAT_EMPTY (-2147483647 - 1)
+
+__global__ void __launch_bounds__(256)
+kb_pattern_collect_kernel(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                          const int32_t* __restrict__ colidx, int* table, int* overflow) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
+       row += (int64_t)gridDim.x * blockDim.x) {
+    const int lo = rowptr[row], hi = rowptr[row + 1];
+    for (int j = lo; j < hi; ++j) {
+      const int off = colidx[j] - (int)row;
+      const unsigned h = ((unsigned)off * 2654435761u) >> 26;  // 64 slots
+      bool done = false;
+      for (int s = 0; s < 64 && !done; ++s) {
+        const int idx = (h + s) & 63;
+        int v = *(volatile int*)&table[idx];
+        if (v == off) {
+          done = true;
+        } else if (v == KB_PAT_EMPTY) {
+          v = atomicCAS(&table[idx], KB_PAT_EMPTY, off);
+          if (v == KB_PAT_EMPTY || v == off) done = true;
+        }
+      }
+      if (!done) *overflow = 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kb_pattern_build_kernel(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                        const int32_t* __restrict__ colidx, KbPattern pat,
+                        uint16_t* __restrict__ masks, int* fail) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
+       row += (int64_t)gridDim.x * blockDim.x) {
+    const int lo = rowptr[row], hi = rowptr[row + 1];
+    unsigned m = 0;
+    int prev = -1;
+    for (int j = lo; j < hi; ++j) {
+      const int off = colidx[j] - (int)row;
+      int d = -1;
+      for (int q = 0; q < pat.nd; ++q)
+        if (pat.off[q] == off) d = q;
+      if (d <= prev) *fail = 1;  // unknown offset, duplicate, or not in ascending column order
+      prev = d;
+      if (d >= 0) m |= 1u << d;
+    }
+    masks[row] = (uint16_t)m;
+  }
+}
+
+template <int STAGES, int CAP>
+struct KbPatternSmem {
+  double vals[STAGES][CAP];
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+};
+
+template <int ROWS, int STAGES, int CAP, int MAXD, int MINCTAS, int DOT>
+__global__ void __launch_bounds__(ROWS + 32, MINCTAS)
+kb_spmv_pattern_kernel(int n_rows, int n_tiles, const int32_t* __restrict__ rowptr,
+                       const uint16_t* __restrict__ masks, const double* __restrict__ vals,
+                       KbPattern pat, const double* __restrict__ x, double* __restrict__ y,
+                       int mode, const double* __restrict__ z, const double* __restrict__ coef,
+                       const double* __restrict__ w, double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  extern __shared__ __align__(128) unsigned char kb_dyn_smem[];
+  KbPatternSmem<STAGES, CAP>& S = *reinterpret_cast<KbPatternSmem<STAGES, CAP>*>(kb_dyn_smem);
+  __shared__ double red_sm[ROWS + 32];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int nconsumer_warps = ROWS / 32;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      kb_mbar_init(&S.full[s], 1);
+      kb_mbar_init(&S.empty[s], nconsumer_warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc = 0.0;
+
+  if (warp == nconsumer_warps) {
+    // producer warp: bounds of 32 tiles per round, lane 0 issues the TMA bulk copies
+    const int lane = tid & 31;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t base = blockIdx.x; base < n_tiles; base += 32ll * gridDim.x) {
+      const int64_t my_tile = base + (int64_t)lane * gridDim.x;
+      int my_s = 0, my_e = 0;
+      if (my_tile < n_tiles) {
+        const int r0 = (int)my_tile * ROWS;
+        const int r1 = min(r0 + ROWS, n_rows);
+        my_s = rowptr[r0];
+        my_e = rowptr[r1];
+      }
+      for (int q = 0; q < 32; ++q) {
+        if (base + (int64_t)q * gridDim.x >= n_tiles) break;
+        const int s = __shfl_sync(0xffffffffu, my_s, q);
+        const int e = __shfl_sync(0xffffffffu, my_e, q);
+        if (lane == 0 && e > s) {
+          const int nch = (((e + 3) & ~3) - (s & ~3) + CAP - 1) / CAP;
+          for (int ci = 0; ci < nch; ++ci) {
+            int a, b;
+            kb_chunk_range(s, e, ci, CAP, a, b);
+            kb_mbar_wait(&S.empty[stage], phase ^ 1u);
+            const uint32_t cnt = (uint32_t)(b - a);
+            kb_mbar_expect_tx(&S.full[stage], cnt * 8u);
+            kb_bulk_g2s(&S.vals[stage][0], vals + a, cnt * 8u, &S.full[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    int stage = 0;
+    uint32_t phase = 0;
+    const double cf = (mode == 1) ? coef[0] : 0.0;
+    int tile = blockIdx.x;
+    int lo_n = 0, s_n = 0, e_n = 0;
+    unsigned m_n = 0;
+    if (tile < n_tiles) {
+      const int r0 = tile * ROWS;
+      const int r1 = min(r0 + ROWS, n_rows);
+      const int row = r0 + tid;
+      s_n = rowptr[r0];
+      e_n = rowptr[r1];
+      if (row < n_rows) {
+        lo_n = rowptr[row];
+        m_n = masks[row];
+      }
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
+      const int r0 = tile * ROWS;
+      const int row = r0 + tid;
+      const int lo = lo_n, s = s_n, e = e_n;
+      const unsigned mask = m_n;
+      {
+        const int nt = tile + gridDim.x;
+        if (nt < n_tiles) {
+          const int q0 = nt * ROWS;
+          const int q1 = min(q0 + ROWS, n_rows);
+          const int qrow = q0 + tid;
+          s_n = rowptr[q0];
+          e_n = rowptr[q1];
+          lo_n = 0;
+          m_n = 0;
+          if (qrow < n_rows) {
+            lo_n = rowptr[qrow];
+            m_n = masks[qrow];
+          }
+        }
+      }
+      double sum = 0.0;
+      if (e > s) {
+        const int nch = (((e + 3) & ~3) - (s & ~3) + CAP - 1) / CAP;
+        for (int ci = 0; ci < nch; ++ci) {
+          int a, b;
+          kb_chunk_range(s, e, ci, CAP, a, b);
+          kb_mbar_wait(&S.full[stage], phase);
+          const double* sv = &S.vals[stage][0];
+          // all gathers are independent of each other: issue them, then the ordered sum
+          double xv[MAXD];
+#pragma unroll
+          for (int d = 0; d < MAXD; ++d) {
+            xv[d] = 0.0;
+            if (d < pat.nd && (mask >> d) & 1u) xv[d] = __ldg(x + (row + pat.off[d]));
+          }
+#pragma unroll
+          for (int d = 0; d < MAXD; ++d) {
+            if (d < pat.nd && (mask >> d) & 1u) {
+              const int j = lo + __popc(mask & ((1u << d) - 1u));  // CSR position of diagonal d
+              if (j >= a && j < b) sum = __dadd_rn(sum, __dmul_rn(sv[j - a], xv[d]));
+            }
+          }
+          __syncwarp();
+          if ((tid & 31) == 0) kb_mbar_arrive(&S.empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      if (row < n_rows) {
+        const double yv = kb_spmv_epilogue(sum, mode, z, cf, (size_t)row);
+        y[row] = yv;
+        if (DOT == 1) acc = fma(w[row], yv, acc);
+        if (DOT == 2) acc = fma(yv, yv, acc);
+      }
+    }
+  }
+  if (DOT != 0) kb_grid_colsum(acc, 1, rd, out, red_sm);
+}
+
+// ------------------------------------------------ windowed pattern kernel -----
+// Same compressed matrix as above, but no per-thread gathers at all: for a tile
+// of ROWS consecutive rows the x entries on diagonal d are the CONTIGUOUS range
+// x[r0 + off[d] .. r0 + off[d] + ROWS), so the producer lane TMA-copies a handful
+// of x windows (nearby diagonals share one) into shared memory together with the
+// tile's values.  Consumers touch global memory only for rowptr/mask (prefetched
+// one tile ahead), the epilogue operands and the y store; everything else is
+// asynchronous bulk traffic, so the kernel is bound by HBM again
+// (8 nnz + 2 n + 4 (n+1) + 16 n bytes per launch).
+// Requires: nd <= 8, window spans <= KB_WIN_SLACK-2, even n_cols, 16-byte aligned x.
+#define KB_WIN_SLACK 40
+
+// first (even) global index held by window `wlo` of the tile starting at r0
+__device__ __forceinline__ int kb_win_start(int r0, int wlo) { return max(r0 + wlo, 0) & ~1; }
+
+// Shared memory (dynamic, sized by the host from the actual pattern so that as many
+// CTAs as possible are resident):  vals[STAGES][cap] | win[STAGES][nw][wlen] | barriers
+// cap = 4-aligned (ROWS * nd + 8), wlen = even (ROWS + max span + 6).
+template <int ROWS, int STAGES, int MINB, int DOT>
+__global__ void __launch_bounds__(ROWS + 32, MINB)
+kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen,
+                      const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ masks,
+                      const double* __restrict__ vals, KbPattern pat,
+                      const double* __restrict__ x, double* __restrict__ y, int mode,
+                      const double* __restrict__ z, const double* __restrict__ coef,
+                      const double* __restrict__ w, double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  extern __shared__ __align__(128) unsigned char kb_dyn_smem[];
+  double* const s_vals = reinterpret_cast<double*>(kb_dyn_smem);
+  double* const s_win = s_vals + (size_t)STAGES * cap;
+  uint64_t* const s_full = reinterpret_cast<uint64_t*>(s_win + (size_t)STAGES * pat.nw * wlen);
+  uint64_t* const s_empty = s_full + STAGES;
+  __shared__ double red_sm[ROWS + 32];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int nconsumer_warps = ROWS / 32;
+  const int nw = pat.nw;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      kb_mbar_init(&s_full[s], 1);
+      kb_mbar_init(&s_empty[s], nconsumer_warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc = 0.0;
+
+  if (warp == nconsumer_warps) {
+    const int lane = tid & 31;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t base = blockIdx.x; base < n_tiles; base += 32ll * gridDim.x) {
+      const int64_t my_tile = base + (int64_t)lane * gridDim.x;
+      int my_s = 0, my_e = 0;
+      if (my_tile < n_tiles) {
+        const int r0 = (int)my_tile * ROWS;
+        const int r1 = min(r0 + ROWS, n_rows);
+        my_s = rowptr[r0];
+        my_e = rowptr[r1];
+      }
+      for (int q = 0; q < 32; ++q) {
+        const int64_t tile = base + (int64_t)q * gridDim.x;
+        if (tile >= n_tiles) break;
+        const int s = __shfl_sync(0xffffffffu, my_s, q);
+        const int e = __shfl_sync(0xffffffffu, my_e, q);
+        if (lane == 0 && e > s) {
+          const int r0 = (int)tile * ROWS;
+          const int a0 = s & ~3, a1 = (e + 3) & ~3;  // <= ROWS*nd + 6 <= cap entries
+          kb_mbar_wait(&s_empty[stage], phase ^ 1u);
+          uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
+          for (int g = 0; g < nw; ++g) {  // pass 1: transaction size
+            const int ge = min(r0 + pat.wlo[g] + ROWS + pat.wspan[g], n_cols);
+            const int gn = max(((ge + 1) & ~1) - kb_win_start(r0, pat.wlo[g]), 0);
+            bytes += (uint32_t)gn * 8u;  // n_cols is even: the rounded end stays in bounds
+          }
+          kb_mbar_expect_tx(&s_full[stage], bytes);
+          kb_bulk_g2s(s_vals + (size_t)stage * cap, vals + a0, (uint32_t)(a1 - a0) * 8u,
+                      &s_full[stage]);
+          for (int g = 0; g < nw; ++g) {  // pass 2: issue
+            const int ge = min(r0 + pat.wlo[g] + ROWS + pat.wspan[g], n_cols);
+            const int ga = kb_win_start(r0, pat.wlo[g]);
+            const int gn = max(((ge + 1) & ~1) - ga, 0);
+            if (gn > 0)
+              kb_bulk_g2s(s_win + ((size_t)stage * nw + g) * wlen, x + ga, (uint32_t)gn * 8u,
+                          &s_full[stage]);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    int stage = 0;
+    uint32_t phase = 0;
+    const double cf = (mode == 1) ? coef[0] : 0.0;
+    int tile = blockIdx.x;
+    int lo_n = 0, s_n = 0, e_n = 0;
+    unsigned m_n = 0;
+    if (tile < n_tiles) {
+      const int r0 = tile * ROWS;
+      const int r1 = min(r0 + ROWS, n_rows);
+      const int row = r0 + tid;
+      s_n = rowptr[r0];
+      e_n = rowptr[r1];
+      if (row < n_rows) {
+        lo_n = rowptr[row];
+        m_n = masks[row];
+      }
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
+      const int r0 = tile * ROWS;
+      const int row = r0 + tid;
+      const int lo = lo_n, s = s_n, e = e_n;
+      const unsigned mask = m_n;
+      {
+        const int nt = tile + gridDim.x;
+        if (nt < n_tiles) {
+          const int q0 = nt * ROWS;
+          const int q1 = min(q0 + ROWS, n_rows);
+          const int qrow = q0 + tid;
+          s_n = rowptr[q0];
+          e_n = rowptr[q1];
+          lo_n = 0;
+          m_n = 0;
+          if (qrow < n_rows) {
+            lo_n = rowptr[qrow];
+            m_n = masks[qrow];
+          }
+        }
+      }
+      // epilogue operands do not depend on the tile data: fetch them early
+      double zv = 0.0, wv = 0.0;
+      if (row < n_rows) {
+        if (mode != 0) zv = z[row];
+        if (DOT == 1) wv = w[row];
+      }
+      double sum = 0.0;
+      if (e > s) {
+        kb_mbar_wait(&s_full[stage], phase);
+        const double* sv = s_vals + (size_t)stage * cap;
+        const double* sw = s_win + (size_t)stage * nw * wlen;
+        int j = lo - (s & ~3);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          if (d < pat.nd && (mask >> d) & 1u) {
+            const int idx = row + pat.off[d] - kb_win_start(r0, pat.dwlo[d]);
+            const double xv = sw[pat.grp[d] * wlen + idx];
+            sum = __dadd_rn(sum, __dmul_rn(sv[j], xv));
+            ++j;
+          }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) kb_mbar_arrive(&s_empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (row < n_rows) {
+        double yv = sum;
+        if (mode == 1) yv = kb_mul_sub(cf, zv, sum);
+        if (mode == 2) yv = __dsub_rn(zv, sum);
+        y[row] = yv;
+        if (DOT == 1) acc = fma(wv, yv, acc);
+        if (DOT == 2) acc = fma(yv, yv, acc);
+      }
+    }
+  }
+  if (DOT != 0) kb_grid_colsum(acc, 1, rd, out, red_sm);
+}
+
 // ------------------------------------------------- boundary rows (halo part) --
 // Row-partitioned matrices: the local product runs on the
 // columns a rank owns while the halo entries travel; this kernel then finishes

@@ -57,8 +57,11 @@ kb_dot_kernel(int64_t total, int k, const double* __restrict__ x, const double* 
 }
 
 // ------------------------------------------------------------ CG: x, r ---
-// alpha = rho / nz(pAp [+ pAp2]);  x += alpha p;  r -= alpha Ap;  rr = <r,r>
-// 48 B/element (reads x p r Ap, writes x r).  cg.py:185,196,200,209
+// alpha = rho / nz(pAp [+ pAp2]);  [x += alpha p;]  r -= alpha Ap;  rr = <r,r>
+// 48 B/element (reads x p r Ap, writes x r); 24 B/element with UPDX == false,
+// when the x update is deferred into the next p update (kb_cg_update_p_kernel,
+// what & 4), which streams p anyway.     cg.py:185,196,200,209
+template <bool UPDX>
 __global__ void __launch_bounds__(KB_BLOCK, 4)
 kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
                        const double* __restrict__ pAp, const double* __restrict__ pAp2,
@@ -78,15 +81,17 @@ kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
 #pragma unroll
     for (int u = 0; u < KB_UNROLL; ++u) {
       const int64_t i = KB_IDX(u);
-      xv[u] = x[i];
-      pv[u] = p[i];
+      if (UPDX) {
+        xv[u] = x[i];
+        pv[u] = p[i];
+      }
       rv[u] = r[i];
       av[u] = Ap[i];
     }
 #pragma unroll
     for (int u = 0; u < KB_UNROLL; ++u) {
       const int64_t i = KB_IDX(u);
-      x[i] = kb_mul_add(alpha, pv[u], xv[u]);
+      if (UPDX) x[i] = kb_mul_add(alpha, pv[u], xv[u]);
       const double rn = kb_mul_sub(alpha, av[u], rv[u]);
       r[i] = rn;
       acc = fma(rn, rn, acc);
@@ -95,7 +100,7 @@ kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
     for (int u = 0; u < KB_UNROLL; ++u) {
       const int64_t i = KB_IDX(u);
       if (i < total) {
-        x[i] = kb_mul_add(alpha, p[i], x[i]);
+        if (UPDX) x[i] = kb_mul_add(alpha, p[i], x[i]);
         const double rn = kb_mul_sub(alpha, Ap[i], r[i]);
         r[i] = rn;
         acc = fma(rn, rn, acc);
@@ -108,13 +113,16 @@ kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
 
 // ------------------------------------------------------------- CG: p -----
 // what & 2 (block 0): hist[step] = sqrt(rho_new); all columns <= crit -> *stop_at = step
-// what & 1 (all):     omega = rho_new / nz(rho_old);  p = r + omega p      24 B/element
-// cg.py:156,175-178,214-217
+// what & 4 (all):     x += (rho_old / nz(pAp)) p       (the deferred update of the
+//                     previous iteration, with the old p)                 cg.py:196
+// what & 1 (all):     omega = rho_new / nz(rho_old);  p = r + omega p     cg.py:175-178
+// 24 B/element (what = 1), 40 B/element (what = 5), 24 B/element (what = 4)
 __global__ void __launch_bounds__(KB_BLOCK)
 kb_cg_update_p_kernel(int64_t total, int k, int step, const double* __restrict__ rho_new,
-                      const double* __restrict__ rho_old, const double* __restrict__ crit,
-                      double* __restrict__ hist, int* stop_at, const double* __restrict__ r,
-                      double* __restrict__ p, int what, KbRed rd) {
+                      const double* __restrict__ rho_old, const double* __restrict__ pAp,
+                      const double* __restrict__ crit, double* __restrict__ hist, int* stop_at,
+                      const double* __restrict__ r, double* __restrict__ p,
+                      double* __restrict__ x, int what, KbRed rd) {
   if (kb_gated(rd)) return;
   const int c = threadIdx.x % k;
   if ((what & 2) && blockIdx.x == 0) {
@@ -127,21 +135,33 @@ kb_cg_update_p_kernel(int64_t total, int k, int step, const double* __restrict__
     const int all_ok = __syncthreads_and(ok);
     if (all_ok && threadIdx.x == 0) *stop_at = step;
   }
-  if (!(what & 1)) return;
-  const double omega = rho_new[c] / kb_nz(rho_old[c]);
+  if (!(what & 5)) return;
+  const bool updp = (what & 1) != 0, updx = (what & 4) != 0;
+  const double omega = updp ? rho_new[c] / kb_nz(rho_old[c]) : 0.0;
+  const double alpha = updx ? rho_old[c] / kb_nz(pAp[c]) : 0.0;
   KB_TILE_LOOP_BEGIN(total)
   if (kb_full) {
-    double rv[KB_UNROLL], pv[KB_UNROLL];
+    double rv[KB_UNROLL], pv[KB_UNROLL], xv[KB_UNROLL];
 #pragma unroll
     for (int u = 0; u < KB_UNROLL; ++u) {
-      rv[u] = r[KB_IDX(u)];
       pv[u] = p[KB_IDX(u)];
+      if (updp) rv[u] = r[KB_IDX(u)];
+      if (updx) xv[u] = x[KB_IDX(u)];
     }
 #pragma unroll
-    for (int u = 0; u < KB_UNROLL; ++u) p[KB_IDX(u)] = kb_mul_add(omega, pv[u], rv[u]);
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      if (updx) x[KB_IDX(u)] = kb_mul_add(alpha, pv[u], xv[u]);
+      if (updp) p[KB_IDX(u)] = kb_mul_add(omega, pv[u], rv[u]);
+    }
   } else {
-    for (int u = 0; u < KB_UNROLL; ++u)
-      if (KB_IDX(u) < total) p[KB_IDX(u)] = kb_mul_add(omega, p[KB_IDX(u)], r[KB_IDX(u)]);
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      const int64_t i = KB_IDX(u);
+      if (i < total) {
+        const double pv = p[i];
+        if (updx) x[i] = kb_mul_add(alpha, pv, x[i]);
+        if (updp) p[i] = kb_mul_add(omega, pv, r[i]);
+      }
+    }
   }
   KB_TILE_LOOP_END
 }
@@ -386,4 +406,17 @@ __global__ void kb_poke_kernel(int op, double* x, int64_t idx, const double* s, 
   if (op == 0) x[idx] *= s[0];
   else if (op == 1) x[idx] = val;
   else if (op == 2) dst[0] = x[idx];
+}
+
+// stand-alone fused all-reduce of a k-slot (a rank without boundary rows still
+// has to take part in the collective that its peers run inside kb_spmv_halo_add)
+__global__ void kb_allreduce_kernel(int k, double* slot, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const int t = threadIdx.x;
+  double v = (t < k) ? slot[t] : 0.0;
+  if (rd.cm.size > 1) {
+    v = kb_p2p_allreduce(v, k, rd.cm);
+    if (t < k && *rd.cm.error) v = nan("");
+  }
+  if (t < k) slot[t] = v;
 }

@@ -77,6 +77,13 @@ class Ops:
         with torch.cuda.device(self.device):
             self.ws = Workspace(k)
         self.launches = 0  # kernels enqueued through this object (bench `gpu_launches`)
+        # peer-memory communicator: reductions are all-reduced inside the reducing kernel
+        self.fused_allreduce = comm is not None and getattr(comm, "p2p_handle", None) is not None
+        if self.fused_allreduce:
+            self.set_collective(True)
+
+    def set_collective(self, on: bool):
+        check(lib.kb_ws_set_comm(self.ws.handle, self.comm.p2p_handle, 1 if on else 0))
 
     # -- allocation helpers (set-up only, never inside an iteration)
     def vec(self, zero=True):
@@ -96,7 +103,7 @@ class Ops:
 
     # -- reductions
     def reduce_over_ranks(self, slot):
-        if self.comm is not None:
+        if self.comm is not None and not self.fused_allreduce:
             self.comm.allreduce(slot)
 
     def dot(self, x, y, out, n=None):
@@ -112,18 +119,27 @@ class Ops:
                                   ptr(p), ptr(Ap), ptr(x), ptr(r), ptr(rr_out), cur_stream()))
         self.reduce_over_ranks(rr_out)
 
-    def cg_update_p(self, rho_new, rho_old, r, p):
-        """p = r + (rho_new / nz(rho_old)) p"""
+    def cg_update_p(self, rho_new, rho_old, r, p, x=None, pAp=None):
+        """[x += (rho_old / nz(pAp)) p;]  p = r + (rho_new / nz(rho_old)) p"""
         self.launches += 1
+        what = 1 | (4 if x is not None else 0)
         check(lib.kb_cg_update_p(self.ws.handle, self.n, self.k, 0, ptr(rho_new), ptr(rho_old),
-                                 None, None, None, ptr(r), ptr(p), 1, cur_stream()))
+                                 ptr(pAp), None, None, None, ptr(r), ptr(p), ptr(x), what,
+                                 cur_stream()))
+
+    def cg_flush_x(self, rho, pAp, p, x):
+        """x += (rho / nz(pAp)) p  (deferred update of the last iteration)"""
+        self.launches += 1
+        check(lib.kb_cg_update_p(self.ws.handle, self.n, self.k, 0, None, ptr(rho), ptr(pAp), None,
+                                 None, None, None, ptr(p), ptr(x), 4, cur_stream()))
 
     def cg_record(self, step, rho_new, crit, hist_ptr, stop_at):
         """hist[step] = sqrt(rho_new); all columns <= crit -> stop_at = step.
         `hist_ptr` is a raw device address (row 0 of the history)."""
         self.launches += 1
-        check(lib.kb_cg_update_p(self.ws.handle, self.n, self.k, int(step), ptr(rho_new), None,
-                                 ptr(crit), hist_ptr, ptr(stop_at), None, None, 2, cur_stream()))
+        check(lib.kb_cg_update_p(self.ws.handle, self.n, self.k, int(step), ptr(rho_new), None, None,
+                                 ptr(crit), hist_ptr, ptr(stop_at), None, None, None, 2,
+                                 cur_stream()))
 
     # -- generic vector kernels
     def axpy(self, y, coef, x, sign=1.0):

@@ -37,15 +37,57 @@ def partition_rows(n, size):
 
 
 class Comm:
-    """Thin wrapper over a torch.distributed process group."""
+    """Process group + (on CUDA, one node) the peer-memory communicator.
 
-    def __init__(self, group=None):
+    ``allreduce_mode``:
+      * ``"p2p"``  -- every reduction kernel finishes with a one-shot all-reduce
+        through NVLink peer memory inside its own last block (``kb_comm_*``,
+        mailboxes mapped with CUDA IPC): no separate collective launch at all.
+      * ``"nccl"`` -- one ``ncclAllReduce`` of k doubles after each reduction.
+    Chosen by ``KRYLOV_B200_ALLREDUCE`` (default ``p2p`` on CUDA)."""
+
+    def __init__(self, group=None, allreduce_mode=None):
+        import os
+
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = group
         self.rank = dist.get_rank(group)
         self.size = dist.get_world_size(group)
         self.allreduces = 0
+        self.p2p_handle = None
+        mode = allreduce_mode or os.environ.get("KRYLOV_B200_ALLREDUCE", "p2p")
+        if mode == "p2p" and self.size > 1 and torch.cuda.is_available() \
+                and dist.get_backend(group) == "nccl":
+            self._open_p2p()
+        self.allreduce_mode = "p2p" if self.p2p_handle is not None else "nccl"
+
+    def _open_p2p(self, max_k=256):
+        import ctypes as C
+
+        from ._lib import check, lib
+
+        h = C.c_void_p()
+        check(lib.kb_comm_create(C.byref(h), self.rank, self.size, max_k))
+        buf = C.create_string_buffer(64)
+        check(lib.kb_comm_get_handle(h, buf))
+        handles = self.allgather_object(bytes(buf.raw))
+        allh = C.create_string_buffer(b"".join(handles), 64 * self.size)
+        check(lib.kb_comm_open(h, allh))
+        self.p2p_handle = h
+        dist.barrier(group=self.group)  # every mailbox is mapped before anyone writes
+
+    def check_p2p(self):
+        """Raise if a peer ever failed to arrive in a fused all-reduce."""
+        if self.p2p_handle is not None:
+            import ctypes as C
+
+            from ._lib import KrylovB200Error, check, lib
+
+            e = C.c_int(0)
+            check(lib.kb_comm_error(self.p2p_handle, C.byref(e)))
+            if e.value:
+                raise KrylovB200Error("peer-memory all-reduce timed out waiting for a rank")
 
     def allreduce(self, t):
         """In-place sum over ranks; stream-ordered for NCCL (no host sync)."""
@@ -204,9 +246,14 @@ class DistCsrMatrix:
         # local rows/columns while the halo is in flight; <y,y> cannot be split
         # into a local and a halo share, so dot 2 is taken after the halo part
         ldot = dot if dot == 1 else 0
+        fused = ops.fused_allreduce  # reductions end with the peer-memory all-reduce
+        if fused:
+            ops.set_collective(False)  # the local part of <w, y> must not be exchanged yet
         ops.launches += 1
         check(lib.kb_spmv(self.A_loc.handle, ops.ws.handle, k, ptr(x), ptr(y), int(mode), ptr(z),
                           ptr(coef), ldot, ptr(w), ptr(out), cur_stream()))
+        if fused:
+            ops.set_collective(True)
         for wk in works:
             wk.wait()  # compute stream waits for NCCL's stream; the host does not block
         if p.n_brows:
@@ -215,6 +262,9 @@ class DistCsrMatrix:
                                        ptr(p.h_rows), ptr(p.h_rowptr), ptr(p.h_col), ptr(p.h_val),
                                        ptr(recv_buf), ptr(y), ldot, ptr(w), ptr(out),
                                        cur_stream()))
+        elif fused and ldot:
+            ops.launches += 1  # no boundary rows here, but the peers' collective needs this rank
+            check(lib.kb_allreduce(ops.ws.handle, k, ptr(out), cur_stream()))
         if dot == 2:
             ops.launches += 1
             check(lib.kb_dot(ops.ws.handle, ops.n, k, ptr(y), ptr(y), ptr(out), cur_stream()))

@@ -33,12 +33,81 @@ def _mats():
 def test_spmv_bit_exact_vs_scipy(name, A, k):
     x = rng.standard_normal((A.shape[1], k)) if k > 1 else rng.standard_normal(A.shape[1])
     ref = A @ x
-    for sched in ("rowwise", "stream", "auto"):
-        Ad = kb.CsrMatrix.from_scipy(A).set_schedule(sched)
+    for sched in ("rowwise", "stream", "pattern", "auto"):
+        Ad = kb.CsrMatrix.from_scipy(A)
+        try:
+            Ad.set_schedule(sched)
+        except kb.KrylovB200Error:
+            assert sched == "pattern"  # not stencil-like: the library refuses, CSR schedules stay
+            continue
         np.testing.assert_array_equal(Ad @ x, ref)
 
 
-@pytest.mark.parametrize("sched", ["rowwise", "stream"])
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 3, 4, 5])
+def test_pattern_kernel_variants_bit_exact(cfg):
+    """Windowed (TMA x windows, several tile configurations) and gather variants
+    of the offset-pattern kernel; odd column counts and misaligned x fall back
+    to the gather variant.  All bit-identical to SciPy."""
+    from krylov_b200._lib import lib
+
+    lib.kb_tune(4, cfg)
+    try:
+        mats = [st.poisson3d(8), st.poisson3d(7), st.poisson2d(64), st.poisson2d(33),
+                st.convection_diffusion3d(12), st.to_scipy(st.stencil7_csr(40, 6, 4)),
+                st.to_scipy(st.stencil7_csr(2, 2, 300)), st.to_scipy(st.stencil5_csr(700, 3))]
+        for A in mats:
+            Ad = kb.CsrMatrix.from_scipy(A)
+            assert Ad.info()["schedule"] == "pattern"
+            n = A.shape[0]
+            x = rng.standard_normal(n)
+            np.testing.assert_array_equal(Ad @ x, A @ x)
+            # x only 8-byte aligned
+            big = torch.from_numpy(np.concatenate([[0.0], x])).cuda()
+            y = Ad.matvec_device(big[1:])
+            np.testing.assert_array_equal(y.cpu().numpy(), A @ x)
+            # fused epilogues through the same kernels
+            ops = Ops(n, 1)
+            z = rng.standard_normal(n)
+            xd, zd = torch.from_numpy(x).cuda().reshape(n, 1), torch.from_numpy(z).cuda().reshape(n, 1)
+            yd = torch.empty_like(xd)
+            out = ops.slots(1)[0]
+            ops.spmv(Ad, xd, yd, mode=2, z=zd, dot=2, out=out)
+            ref = z - A @ x
+            np.testing.assert_array_equal(yd.cpu().numpy().ravel(), ref)
+            np.testing.assert_allclose(out.cpu().numpy()[0], ref @ ref, rtol=1e-13)
+            ops.spmv(Ad, xd, yd, dot=1, w=xd, out=out)
+            np.testing.assert_allclose(out.cpu().numpy()[0], x @ (A @ x), rtol=1e-12)
+    finally:
+        lib.kb_tune(4, 0)
+
+
+def test_pattern_schedule_selection():
+    """Offset-pattern compression is chosen for stencil-like matrices only."""
+    assert kb.CsrMatrix.from_scipy(st.poisson3d(9)).info()["schedule"] == "pattern"
+    assert kb.CsrMatrix.from_scipy(st.poisson2d(40)).info()["schedule"] == "pattern"
+    assert kb.CsrMatrix.from_scipy(st.convection_diffusion3d(8)).info()["schedule"] == "pattern"
+    R = scipy.sparse.random(3000, 3000, density=0.003, random_state=1, format="csr")
+    assert kb.CsrMatrix.from_scipy(R).info()["schedule"] == "stream"
+    # 27 diagonals (> 16): stays on the CSR stream kernel
+    n = 2000
+    B = scipy.sparse.diags([np.ones(n - abs(o)) for o in range(-13, 14)], list(range(-13, 14)), format="csr")
+    assert kb.CsrMatrix.from_scipy(B).info()["schedule"] == "stream"
+    # 12 diagonals: pattern kernel with the wide (16) mask path; unsorted columns -> refused
+    C = scipy.sparse.diags([np.arange(1.0, n - abs(o) + 1) for o in range(-6, 6)], list(range(-6, 6)), format="csr")
+    Cd = kb.CsrMatrix.from_scipy(C)
+    assert Cd.info()["schedule"] == "pattern"
+    x = rng.standard_normal(n)
+    np.testing.assert_array_equal(Cd @ x, C @ x)
+    U = st.poisson2d(12).tocsr()
+    U.indices[0:2] = U.indices[0:2][::-1].copy()
+    U.data[0:2] = U.data[0:2][::-1].copy()
+    Ud = kb.CsrMatrix.from_scipy(U)
+    assert Ud.info()["schedule"] == "stream"
+    x = rng.standard_normal(U.shape[0])
+    np.testing.assert_array_equal(Ud @ x, U @ x)
+
+
+@pytest.mark.parametrize("sched", ["rowwise", "stream", "pattern"])
 @pytest.mark.parametrize("k", [1, 4])
 def test_spmv_fused_modes(sched, k):
     A = st.convection_diffusion3d(9)
@@ -103,6 +172,20 @@ def test_vector_kernels(k):
     p_ref = r_ref + (rho / pAp) * a["p"]
     ops.cg_update_p(rho_d, pAp_d, d["r"], d["p"])
     np.testing.assert_array_equal(d["p"].cpu().numpy(), p_ref)
+    # deferred x update fused into the p update (what = 5) and the flush (what = 4)
+    x2 = torch.from_numpy(a["x"]).cuda()
+    p2 = torch.from_numpy(a["p"]).cuda()
+    r2 = torch.from_numpy(r_ref).cuda()
+    ops.cg_update_p(rho_d, pAp_d, r2, p2, x=x2, pAp=c1_d)  # alpha = rho_old/pAp = pAp_d/c1
+    al2 = pAp / np.where(c1 != 0, c1, 1.0)
+    np.testing.assert_array_equal(x2.cpu().numpy(), a["x"] + al2 * a["p"])
+    np.testing.assert_array_equal(p2.cpu().numpy(), p_ref)
+    x3 = torch.from_numpy(a["x"]).cuda()
+    ops.cg_flush_x(rho_d, pAp_d, torch.from_numpy(a["p"]).cuda(), x3)
+    np.testing.assert_array_equal(x3.cpu().numpy(), x_ref)
+    r3 = torch.from_numpy(a["r"]).cuda()
+    ops.cg_update_xr(rho_d, pAp_d, None, None, d["A"], None, r3, out)  # r-only variant
+    np.testing.assert_array_equal(r3.cpu().numpy(), r_ref)
     # axpy_dot (arnoldi.py:157-162)
     w_ref = a["w"] - c1 * a["A"]
     ops.axpy_dot(c1_d, d["A"], d["w"], dot=1, z=d["x"], out=out)

@@ -15,6 +15,20 @@ dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=dev)
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 comm = Comm()
+if rank == 0:
+    print("allreduce mode:", comm.allreduce_mode, flush=True)
+# direct check of the reduction + all-reduce path (fused in p2p mode)
+from krylov_b200.device import Ops
+for kk_ in (1, 5, 16):
+    o = Ops(1000, kk_, dev, comm=comm)
+    xv = torch.full((1000, kk_), float(rank + 1), dtype=torch.float64, device=dev)
+    yv = torch.arange(1, kk_ + 1, dtype=torch.float64, device=dev).repeat(1000, 1)
+    sl = o.slots(1)[0]
+    for rep in range(5):
+        o.dot(xv, yv, sl)
+    want = 1000.0 * sum(range(1, world + 1)) * torch.arange(1, kk_ + 1, dtype=torch.float64)
+    assert torch.equal(sl.cpu(), want), (rank, kk_, sl.cpu(), want)
+comm.check_p2p()
 zoff = partition_rows(N, world) * N * N
 r0, r1 = int(zoff[rank]), int(zoff[rank + 1])
 g = torch.Generator(device=dev).manual_seed(0)
@@ -63,6 +77,7 @@ for name, coeffs, shift, fn in cases:
         "success": [bool(info_d.success), bool(info_f.success)],
     }
     del Ad, Afull
+comm.check_p2p()
 if rank == 0:
     json.dump(results, open(sys.argv[1], "w"), indent=1)
     print(json.dumps(results, indent=1))

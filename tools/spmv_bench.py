@@ -33,9 +33,15 @@ if "--one" in sys.argv:
     run(sys.argv[i+1], int(sys.argv[i+2]), int(sys.argv[i+3]), int(sys.argv[i+4]))
     sys.exit(0)
 
-for vc in (2, 4, 6, 8):
+for wc, pcs in ((0, (0, 3)), (1, (0, 2)), (2, (0, 1)), (3, (0, 6, 5)), (4, (0, 4)), (5, (0,)), (-1, (0,))):
+    for pc in pcs:
+        lib.kb_tune(4, wc); lib.kb_tune(3, pc)
+        print(f"window cfg {wc} ctas {pc}: ", end="")
+        run("pattern", 0, 0, vec_ctas=8)
+lib.kb_tune(3, 0); lib.kb_tune(4, 0)
+for vc in (4, 8):
     run("rowwise", 0, 0, vec_ctas=vc)
-for cfg, ctas_list in ((0, (1, 2)), (1, (2, 3, 4)), (2, (2, 3)), (3, (4, 6)), (4, (1, 2)), (5, (4, 6, 8))):
+for cfg, ctas_list in ((0, (2,)), (5, (8,))):
     for ctas in ctas_list:
         run("stream", cfg, ctas)
 # copy bandwidth reference (same method as MEASURED_PEAKS.json)

@@ -9,7 +9,7 @@ for N in (256, 512):
     n = A.shape[0]
     b = torch.randn(n, dtype=torch.float64, device="cuda")
     byt = 12 * A.nnz + 4 * (n + 1) + 92 * n
-    for sched, cfg, ctas, vc in (("rowwise",0,0,4),("rowwise",0,0,8),("stream",4,2,8),("stream",5,8,8),("stream",5,10,8),("stream",1,4,8),("stream",5,8,6),("stream",4,2,12)):
+    for sched, cfg, ctas, vc in (("rowwise",0,0,8),("stream",0,0,8),("pattern",0,0,8)):
         A.set_schedule(sched); lib.kb_tune(0,cfg); lib.kb_tune(1,ctas); lib.kb_tune(2,vc)
         kb.cg(A, b, tol=0.0, atol=0.0, maxiter=10)
         torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
