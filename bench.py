@@ -289,7 +289,7 @@ def ours(args):
         dist.all_reduce(lt)
         launches = int(lt[0])
     its = K / (ms_total / 1e3)
-    rho_final = float(st.sl[it % 2][0])
+    rho_final = float(st.sl[it % 2][0])  # rho of the last step (state slot)
     if not np.isfinite(rho_final):
         raise SystemExit("bench: CG produced a non-finite residual")
     info_sched = A.info()
@@ -298,24 +298,34 @@ def ours(args):
 
     # ---- roofline of the dominant kernel (SpMV fused with <p, Ap>)
     peak, peak_src = load_peaks()
-    spmv_bytes = A.spmv_bytes(1)  # per launch, this rank's rows
+    spmv_bytes = A.spmv_bytes(1)  # per launch, this rank's rows (SURVEY.md 8d CSR model)
+    moved_bytes = A.moved_bytes(1)  # what the chosen schedule streams (pattern: 8 B/nnz + 2 B/row)
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    achieved_moved = moved_bytes / (spmv_ms * 1e-3) / 1e9
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(tfile):
         try:
             tj = json.load(open(tfile))
-            if tj.get("grid") == N and world == 1:
+            if tj.get("grid") == N and world == 1 and tj.get("schedule") == info_sched.get("schedule"):
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
     step_bytes = cg_step_bytes(nnz_glob, n_glob)
+    kname = {"pattern": "kb_spmv_window_kernel", "stream": "kb_spmv_stream_kernel",
+             "rowwise": "kb_spmv_rowwise_kernel"}.get(info_sched.get("schedule"), "kb_spmv")
     roofline = {
-        "bound": "hbm", "kernel": "kb_spmv_stream_kernel (A p fused with <p, Ap>)",
+        "bound": "hbm", "kernel": f"{kname} (A p fused with <p, Ap>)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": spmv_bytes, "launch_ms": spmv_ms,
+        "moved_bytes_per_launch": moved_bytes, "achieved_moved": achieved_moved,
+        "frac_moved": achieved_moved / peak,
+        "note": ("achieved/frac use the CSR byte model of SURVEY.md 8d (12 B per nonzero); the "
+                 "offset-pattern schedule streams 8 B per nonzero + a 2-byte mask per row, so frac "
+                 "can exceed 1 while achieved_moved/frac_moved (bytes actually streamed) cannot"),
         "whole_step": {"algorithmic_bytes": step_bytes,
+                       "moved_bytes": (moved_bytes + 64 * A.shape[0]) * world,
                        "achieved_GBs_aggregate": step_bytes * its / 1e9,
                        "frac_of_aggregate_peak": step_bytes * its / 1e9 / (peak * world)},
     }

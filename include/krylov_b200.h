@@ -125,18 +125,21 @@ int kb_dot(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, doubl
 /* --- CG (cg.py:155-234) ------------------------------------------------ */
 /* alpha = rho / nz(pAp [+ pAp2]);  x += alpha p;  r -= alpha Ap;  rr = <r, r>
  * (cg.py:185,196,200,209).  pAp2 may be NULL.  x == NULL defers the x update to the
- * next kb_cg_update_p (what & 4), which reads p anyway: 24 instead of 48 B/element here. */
+ * next kb_cg_update_p (what & 4), which reads p anyway: 24 instead of 48 B/element here.
+ * alpha_out (nullable) receives alpha: a state slot that only this (gated) kernel writes. */
 int kb_cg_update_xr(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
                     const double* pAp2, const double* p, const double* Ap, double* x,
-                    double* r, double* rr_out, void* stream);
-/* what & 2: record resnorm[step] = sqrt(rho_new) into hist[step*k + c]; if all
- *           columns satisfy resnorm <= crit[c] set *stop_at = step (cg.py:156,214-217)
- * what & 4: x += (rho_old / nz(pAp)) p  -- the previous iteration's deferred update,
- *           taken before p is overwritten (cg.py:196)
+                    double* r, double* rr_out, double* alpha_out, void* stream);
+/* what & 2: record resnorm[step] = sqrt(rho_new) into hist[step*k + c], copy rho_new to
+ *           rho_keep (state slot, nullable); if all columns satisfy resnorm <= crit[c]
+ *           set *stop_at = step (cg.py:156,214-217)
+ * what & 4: x += alpha p  -- the previous iteration's deferred update, taken before p
+ *           is overwritten (cg.py:196)
  * what & 1: omega = rho_new / nz(rho_old);  p = r + omega p  (cg.py:175-178) */
 int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new,
-                   const double* rho_old, const double* pAp, const double* crit, double* hist,
-                   int* stop_at, const double* r, double* p, double* x, int what, void* stream);
+                   const double* rho_old, const double* alpha, const double* crit, double* hist,
+                   int* stop_at, double* rho_keep, const double* r, double* p, double* x, int what,
+                   void* stream);
 
 /* --- generic vector kernels (fallback path for M/Ml/Mr/custom inner) ---- */
 /* y += sign * coef[c] * x   (product rounded, then sum: NumPy temporaries) */

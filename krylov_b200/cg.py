@@ -108,8 +108,11 @@ class FusedCG:
         self.r = ops.vec(zero=False)
         self.Ap = ops.vec(zero=False)
         self.yk = ops.vec(zero=True)
-        # rho ping-pong (rho_i in sl[i % 2]), <p,Ap>, scratch
-        self.sl = ops.slots(4)
+        # State slots (written by gated kernels only): rho ping-pong (rho_i in sl[i % 2]),
+        # sl[2] = alpha of the last iteration.  Landing slots of reductions (these may see
+        # un-gated NCCL all-reduces after on-device convergence, so nothing persistent
+        # lives there): sl[3] = <p, Ap>, sl[4] = <r, r>, sl[5] = scratch.
+        self.sl = ops.slots(6)
         self.stop_at = torch.full((1,), INT_MAX, dtype=torch.int32, device=self.dev)
         self.hist = torch.zeros((_BATCH_MAX, k), dtype=torch.float64, device=self.dev)
         self.spmv_events = None  # bench hook: list of (start, end) CUDA events around A @ p
@@ -132,13 +135,12 @@ class FusedCG:
         return slot.cpu().numpy().copy()
 
     def explicit_resnorm(self, xk):
-        return np.sqrt(self._residual_norm2(xk, self.Ap, self.sl[3]))
+        return np.sqrt(self._residual_norm2(xk, self.Ap, self.sl[5]))
 
     def flush_x(self):
         if self.x_pending:
-            i = self.kk - 1  # last completed iteration: alpha_i = rho_i / <p_i, A p_i>
             self.ops.gate(None, 0)
-            self.ops.cg_flush_x(self.sl[i % 2], self.sl[2], self.p, self.yk)
+            self.ops.cg_flush_x(self.sl[2], self.p, self.yk)  # alpha of the last iteration run
             self.x_pending = False
 
     def current_x(self):
@@ -154,20 +156,21 @@ class FusedCG:
         if i > 0:
             # [x += alpha_{i-1} p;]  omega = rho_i / rho_{i-1};  p = r + omega p
             if self.x_pending:
-                ops.cg_update_p(cur, nxt, self.r, self.p, x=self.yk, pAp=sl[2])
+                ops.cg_update_p(cur, nxt, self.r, self.p, x=self.yk, alpha=sl[2])
             else:
                 ops.cg_update_p(cur, nxt, self.r, self.p)
         if self.spmv_events is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        ops.spmv(self.A, self.p, self.Ap, dot=1, w=self.p, out=sl[2])  # Ap = A p, <p, Ap>
+        ops.spmv(self.A, self.p, self.Ap, dot=1, w=self.p, out=sl[3])  # Ap = A p, <p, Ap>
         if self.spmv_events is not None:
             e1.record()
             self.spmv_events.append((e0, e1))
-        ops.cg_update_xr(cur, sl[2], None, None, self.Ap, None, self.r, nxt)  # r, rho_{i+1}
+        # alpha -> sl[2]; r -= alpha Ap; <r, r> -> sl[4]
+        ops.cg_update_xr(cur, sl[3], None, None, self.Ap, None, self.r, sl[4], alpha_out=sl[2])
         self.x_pending = True
-        ops.cg_record(i + 1, nxt, self.crit_d, hist_ptr, self.stop_at)
+        ops.cg_record(i + 1, sl[4], self.crit_d, hist_ptr, self.stop_at, rho_keep=nxt)  # rho_{i+1}
 
     def run(self, nb):
         """Enqueue iterations kk .. kk+nb-1, then one host read.  Returns the
@@ -212,8 +215,7 @@ def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback):
         xk = None
         if log is not None:  # batch == 1 here
             sv = st.sl.cpu().numpy()
-            rho_i, rho_n, pAp = sv[kk % 2], sv[(kk + 1) % 2], sv[2]
-            alpha = rho_i / nz(pAp)
+            rho_i, rho_n, alpha = sv[kk % 2], sv[(kk + 1) % 2], sv[2]
             omega = rho_i / nz(log.rho_prev) if kk > 0 else None
             log.step(kk, st.r, st.r, alpha, omega, rho_n, rho_i)
             log.rho_prev = rho_i

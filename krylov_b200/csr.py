@@ -125,6 +125,14 @@ class CsrMatrix:
         n = self.shape[0]
         return 12 * self.nnz + 4 * (n + 1) + 16 * n * k
 
+    def moved_bytes(self, k=1):
+        """Bytes the chosen schedule actually streams per product: the offset-pattern
+        schedule replaces the 4-byte column index per nonzero by a 2-byte mask per row."""
+        n = self.shape[0]
+        if k == 1 and self.info()["schedule"] == "pattern":
+            return 8 * self.nnz + 2 * n + 4 * (n + 1) + 16 * n
+        return self.spmv_bytes(k)
+
     def to_scipy(self):
         import scipy.sparse
 

@@ -43,6 +43,8 @@ static int g_stream_cfg = 0;
 static int g_stream_ctas = 0;  // 0 = configuration default
 static int g_pattern_ctas = 0; // kb_tune key 3 (0 = default)
 static int g_window_cfg = 0;   // kb_tune key 4
+static int g_rowwise_contig = -1;  // kb_tune key 5: -1 auto, 0 strided, 1 contiguous rows per block
+static int g_rowwise_ctas = 0;     // kb_tune key 6: CTAs/SM of the contiguous row-wise grid
 int g_vec_ctas = KB_CTAS_PER_SM;
 
 // Finds the set of distinct diagonals (col - row); if there are at most 16 and every
@@ -147,6 +149,8 @@ int kb_tune(int key, int value) {
     case 2: g_vec_ctas = value > 0 ? value : KB_CTAS_PER_SM; return KB_OK;
     case 3: g_pattern_ctas = value; return KB_OK;
     case 4: g_window_cfg = value; return KB_OK;  // -1: gather variant of the pattern kernel
+    case 5: g_rowwise_contig = value; return KB_OK;
+    case 6: g_rowwise_ctas = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -571,17 +575,23 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
     return kb_launch_stream<2>(A, ws, x, y, mode, z, coef, w, out, st);
   }
   const int block = kb_block_for(k);
-  const int grid = kb_grid_for(ws, A->n_rows * (int64_t)k, block, 1);
+  int grid = kb_grid_for(ws, A->n_rows * (int64_t)k, block, 1);
+  // optional (kb_tune 5): contiguous row slices per block
+  const int contiguous = g_rowwise_contig > 0 ? 1 : 0;  // measured slower (profiles/r1_c4_tune.txt)
+  if (contiguous) {
+    const int ctas = g_rowwise_ctas > 0 ? g_rowwise_ctas : 4;
+    if (grid > ws->num_sms * ctas) grid = ws->num_sms * ctas;
+  }
   KbRed rd = kb_red(ws);
   if (dot == 0)
     kb_spmv_rowwise_kernel<0><<<grid, block, 0, st>>>(A->n_rows, k, A->rowptr, A->colidx, A->vals,
-                                                      x, y, mode, z, coef, w, out, rd);
+                                                      x, y, mode, z, coef, w, out, contiguous, rd);
   else if (dot == 1)
     kb_spmv_rowwise_kernel<1><<<grid, block, 0, st>>>(A->n_rows, k, A->rowptr, A->colidx, A->vals,
-                                                      x, y, mode, z, coef, w, out, rd);
+                                                      x, y, mode, z, coef, w, out, contiguous, rd);
   else
     kb_spmv_rowwise_kernel<2><<<grid, block, 0, st>>>(A->n_rows, k, A->rowptr, A->colidx, A->vals,
-                                                      x, y, mode, z, coef, w, out, rd);
+                                                      x, y, mode, z, coef, w, out, contiguous, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -643,33 +653,34 @@ int kb_dot(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, doubl
 
 int kb_cg_update_xr(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
                     const double* pAp2, const double* p, const double* Ap, double* x, double* r,
-                    double* rr_out, void* stream) {
+                    double* rr_out, double* alpha_out, void* stream) {
   KB_VEC_PROLOGUE();
   KB_REQUIRE(rho && pAp && Ap && r && rr_out, "null argument");
   KB_REQUIRE((x == nullptr) || (p != nullptr), "x update needs p");
   const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
   if (x != nullptr)
     kb_cg_update_xr_kernel<true><<<grid, block, 0, st>>>(total, k, rho, pAp, pAp2, p, Ap, x, r,
-                                                         rr_out, rd);
+                                                         rr_out, alpha_out, rd);
   else
     kb_cg_update_xr_kernel<false><<<grid, block, 0, st>>>(total, k, rho, pAp, pAp2, p, Ap, x, r,
-                                                          rr_out, rd);
+                                                          rr_out, alpha_out, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
 
 int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new,
-                   const double* rho_old, const double* pAp, const double* crit, double* hist,
-                   int* stop_at, const double* r, double* p, double* x, int what, void* stream) {
+                   const double* rho_old, const double* alpha, const double* crit, double* hist,
+                   int* stop_at, double* rho_keep, const double* r, double* p, double* x, int what,
+                   void* stream) {
   KB_VEC_PROLOGUE();
   KB_REQUIRE(what >= 1 && what <= 7, "what is a mask of 1 (update p), 2 (record), 4 (update x)");
   KB_REQUIRE(!(what & 2) || (rho_new && crit && hist && stop_at),
              "record needs rho_new, crit, hist, stop_at");
   KB_REQUIRE(!(what & 1) || (r && p && rho_new && rho_old), "p update needs r, p, rho_new, rho_old");
-  KB_REQUIRE(!(what & 4) || (x && p && rho_old && pAp), "x update needs x, p, rho_old, pAp");
+  KB_REQUIRE(!(what & 4) || (x && p && alpha), "x update needs x, p, alpha");
   const int grid = (what & 5) ? kb_grid_for(ws, total, block, KB_UNROLL) : 1;
-  kb_cg_update_p_kernel<<<grid, block, 0, st>>>(total, k, step, rho_new, rho_old, pAp, crit, hist,
-                                                stop_at, r, p, x, what, rd);
+  kb_cg_update_p_kernel<<<grid, block, 0, st>>>(total, k, step, rho_new, rho_old, alpha, crit, hist,
+                                                stop_at, rho_keep, r, p, x, what, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

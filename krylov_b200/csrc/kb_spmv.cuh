@@ -35,7 +35,8 @@ kb_spmv_rowwise_kernel(int64_t n_rows, int k, const int32_t* __restrict__ rowptr
                        const int32_t* __restrict__ colidx, const double* __restrict__ vals,
                        const double* __restrict__ x, double* __restrict__ y, int mode,
                        const double* __restrict__ z, const double* __restrict__ coef,
-                       const double* __restrict__ w, double* __restrict__ out, KbRed rd) {
+                       const double* __restrict__ w, double* __restrict__ out, int contiguous,
+                       KbRed rd) {
   if (kb_gated(rd)) return;
   __shared__ double sm[KB_BLOCK];
   const int c = threadIdx.x % k;
@@ -43,11 +44,33 @@ kb_spmv_rowwise_kernel(int64_t n_rows, int k, const int32_t* __restrict__ rowptr
   const int rsub = threadIdx.x / k;
   const double cf = (mode == 1) ? coef[c] : 0.0;
   double acc = 0.0;
-  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + rsub; row < n_rows;
-       row += (int64_t)gridDim.x * rows_per_block) {
+  // contiguous: block b walks its own contiguous slice of rows, so the x rows that
+  // neighbouring matrix rows share (stencils: +-1, +-nx) are still in this SM's L1
+  // when they are needed again; otherwise rows are dealt round-robin to the blocks.
+  int64_t row0 = (int64_t)blockIdx.x * rows_per_block, row_end = n_rows;
+  int64_t step = (int64_t)gridDim.x * rows_per_block;
+  if (contiguous) {
+    const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
+    row0 = (int64_t)blockIdx.x * per;
+    row_end = row0 + per < n_rows ? row0 + per : n_rows;
+    step = rows_per_block;
+  }
+  for (int64_t row = row0 + rsub; row < row_end; row += step) {
     const int lo = rowptr[row], hi = rowptr[row + 1];
     double sum = 0.0;
-    for (int j = lo; j < hi; ++j)
+    int j = lo;
+    // four independent index/value/gather chains in flight, then the ordered sum
+    for (; j + 3 < hi; j += 4) {
+      const int c0 = colidx[j], c1 = colidx[j + 1], c2 = colidx[j + 2], c3 = colidx[j + 3];
+      const double v0 = vals[j], v1 = vals[j + 1], v2 = vals[j + 2], v3 = vals[j + 3];
+      const double x0 = x[(size_t)c0 * k + c], x1 = x[(size_t)c1 * k + c];
+      const double x2 = x[(size_t)c2 * k + c], x3 = x[(size_t)c3 * k + c];
+      sum = __dadd_rn(sum, __dmul_rn(v0, x0));
+      sum = __dadd_rn(sum, __dmul_rn(v1, x1));
+      sum = __dadd_rn(sum, __dmul_rn(v2, x2));
+      sum = __dadd_rn(sum, __dmul_rn(v3, x3));
+    }
+    for (; j < hi; ++j)
       sum = __dadd_rn(sum, __dmul_rn(vals[j], x[(size_t)colidx[j] * k + c]));
     const size_t idx = (size_t)row * k + c;
     const double yv = kb_spmv_epilogue(sum, mode, z, cf, idx);

@@ -67,13 +67,16 @@ kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
                        const double* __restrict__ pAp, const double* __restrict__ pAp2,
                        const double* __restrict__ p, const double* __restrict__ Ap,
                        double* __restrict__ x, double* __restrict__ r, double* __restrict__ out,
-                       KbRed rd) {
+                       double* __restrict__ alpha_out, KbRed rd) {
   if (kb_gated(rd)) return;
   __shared__ double sm[KB_BLOCK];
   const int c = threadIdx.x % k;
   double d = pAp[c];
   if (pAp2 != nullptr) d += pAp2[c];
   const double alpha = rho[c] / kb_nz(d);
+  // persistent copy of alpha (state slot: only gated kernels write it, so it survives
+  // un-gated NCCL all-reduces of the landing slots after on-device convergence)
+  if (alpha_out != nullptr && blockIdx.x == 0 && threadIdx.x < k) alpha_out[c] = alpha;
   double acc = 0.0;
   KB_TILE_LOOP_BEGIN(total)
   if (kb_full) {
@@ -112,23 +115,26 @@ kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
 }
 
 // ------------------------------------------------------------- CG: p -----
-// what & 2 (block 0): hist[step] = sqrt(rho_new); all columns <= crit -> *stop_at = step
-// what & 4 (all):     x += (rho_old / nz(pAp)) p       (the deferred update of the
-//                     previous iteration, with the old p)                 cg.py:196
+// what & 2 (block 0): hist[step] = sqrt(rho_new); rho_keep = rho_new (state copy);
+//                     all columns <= crit -> *stop_at = step
+// what & 4 (all):     x += alpha p     (the deferred update of the previous iteration,
+//                     taken before p is overwritten)                       cg.py:196
 // what & 1 (all):     omega = rho_new / nz(rho_old);  p = r + omega p     cg.py:175-178
 // 24 B/element (what = 1), 40 B/element (what = 5), 24 B/element (what = 4)
 __global__ void __launch_bounds__(KB_BLOCK)
 kb_cg_update_p_kernel(int64_t total, int k, int step, const double* __restrict__ rho_new,
-                      const double* __restrict__ rho_old, const double* __restrict__ pAp,
+                      const double* __restrict__ rho_old, const double* __restrict__ alpha_in,
                       const double* __restrict__ crit, double* __restrict__ hist, int* stop_at,
-                      const double* __restrict__ r, double* __restrict__ p,
-                      double* __restrict__ x, int what, KbRed rd) {
+                      double* __restrict__ rho_keep, const double* __restrict__ r,
+                      double* __restrict__ p, double* __restrict__ x, int what, KbRed rd) {
   if (kb_gated(rd)) return;
   const int c = threadIdx.x % k;
   if ((what & 2) && blockIdx.x == 0) {
     int ok = 1;
     if (threadIdx.x < k) {
-      const double nrm = sqrt(rho_new[c]);
+      const double rn = rho_new[c];
+      if (rho_keep != nullptr) rho_keep[c] = rn;
+      const double nrm = sqrt(rn);
       hist[(size_t)step * k + c] = nrm;
       ok = (nrm <= crit[c]) ? 1 : 0;
     }
@@ -138,7 +144,7 @@ kb_cg_update_p_kernel(int64_t total, int k, int step, const double* __restrict__
   if (!(what & 5)) return;
   const bool updp = (what & 1) != 0, updx = (what & 4) != 0;
   const double omega = updp ? rho_new[c] / kb_nz(rho_old[c]) : 0.0;
-  const double alpha = updx ? rho_old[c] / kb_nz(pAp[c]) : 0.0;
+  const double alpha = updx ? alpha_in[c] : 0.0;
   KB_TILE_LOOP_BEGIN(total)
   if (kb_full) {
     double rv[KB_UNROLL], pv[KB_UNROLL], xv[KB_UNROLL];

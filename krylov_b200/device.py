@@ -113,33 +113,34 @@ class Ops:
         self.reduce_over_ranks(out)
 
     # -- CG
-    def cg_update_xr(self, rho, pAp, pAp2, p, Ap, x, r, rr_out):
+    def cg_update_xr(self, rho, pAp, pAp2, p, Ap, x, r, rr_out, alpha_out=None):
         self.launches += 1
         check(lib.kb_cg_update_xr(self.ws.handle, self.n, self.k, ptr(rho), ptr(pAp), ptr(pAp2),
-                                  ptr(p), ptr(Ap), ptr(x), ptr(r), ptr(rr_out), cur_stream()))
+                                  ptr(p), ptr(Ap), ptr(x), ptr(r), ptr(rr_out), ptr(alpha_out),
+                                  cur_stream()))
         self.reduce_over_ranks(rr_out)
 
-    def cg_update_p(self, rho_new, rho_old, r, p, x=None, pAp=None):
-        """[x += (rho_old / nz(pAp)) p;]  p = r + (rho_new / nz(rho_old)) p"""
+    def cg_update_p(self, rho_new, rho_old, r, p, x=None, alpha=None):
+        """[x += alpha p;]  p = r + (rho_new / nz(rho_old)) p"""
         self.launches += 1
         what = 1 | (4 if x is not None else 0)
         check(lib.kb_cg_update_p(self.ws.handle, self.n, self.k, 0, ptr(rho_new), ptr(rho_old),
-                                 ptr(pAp), None, None, None, ptr(r), ptr(p), ptr(x), what,
+                                 ptr(alpha), None, None, None, None, ptr(r), ptr(p), ptr(x), what,
                                  cur_stream()))
 
-    def cg_flush_x(self, rho, pAp, p, x):
-        """x += (rho / nz(pAp)) p  (deferred update of the last iteration)"""
+    def cg_flush_x(self, alpha, p, x):
+        """x += alpha p  (deferred update of the last iteration)"""
         self.launches += 1
-        check(lib.kb_cg_update_p(self.ws.handle, self.n, self.k, 0, None, ptr(rho), ptr(pAp), None,
-                                 None, None, None, ptr(p), ptr(x), 4, cur_stream()))
+        check(lib.kb_cg_update_p(self.ws.handle, self.n, self.k, 0, None, None, ptr(alpha), None,
+                                 None, None, None, None, ptr(p), ptr(x), 4, cur_stream()))
 
-    def cg_record(self, step, rho_new, crit, hist_ptr, stop_at):
-        """hist[step] = sqrt(rho_new); all columns <= crit -> stop_at = step.
+    def cg_record(self, step, rho_new, crit, hist_ptr, stop_at, rho_keep=None):
+        """hist[step] = sqrt(rho_new); rho_keep = rho_new; all columns <= crit -> stop_at = step.
         `hist_ptr` is a raw device address (row 0 of the history)."""
         self.launches += 1
         check(lib.kb_cg_update_p(self.ws.handle, self.n, self.k, int(step), ptr(rho_new), None, None,
-                                 ptr(crit), hist_ptr, ptr(stop_at), None, None, None, 2,
-                                 cur_stream()))
+                                 ptr(crit), hist_ptr, ptr(stop_at), ptr(rho_keep), None, None, None,
+                                 2, cur_stream()))
 
     # -- generic vector kernels
     def axpy(self, y, coef, x, sign=1.0):

@@ -210,6 +210,9 @@ class DistCsrMatrix:
         n = self.shape[0]
         return 12 * self.nnz + 4 * (n + 1) + 16 * n * k
 
+    def moved_bytes(self, k=1):
+        return self.A_loc.moved_bytes(k) + 12 * (self.nnz - self.A_loc.nnz)
+
     def info(self):
         d = self.A_loc.info()
         d.update(n_halo=self.plan.n_halo, n_send=self.plan.n_send, n_brows=self.plan.n_brows,

@@ -176,16 +176,18 @@ def test_vector_kernels(k):
     x2 = torch.from_numpy(a["x"]).cuda()
     p2 = torch.from_numpy(a["p"]).cuda()
     r2 = torch.from_numpy(r_ref).cuda()
-    ops.cg_update_p(rho_d, pAp_d, r2, p2, x=x2, pAp=c1_d)  # alpha = rho_old/pAp = pAp_d/c1
-    al2 = pAp / np.where(c1 != 0, c1, 1.0)
-    np.testing.assert_array_equal(x2.cpu().numpy(), a["x"] + al2 * a["p"])
+    ops.cg_update_p(rho_d, pAp_d, r2, p2, x=x2, alpha=c1_d)
+    np.testing.assert_array_equal(x2.cpu().numpy(), a["x"] + c1 * a["p"])
     np.testing.assert_array_equal(p2.cpu().numpy(), p_ref)
     x3 = torch.from_numpy(a["x"]).cuda()
-    ops.cg_flush_x(rho_d, pAp_d, torch.from_numpy(a["p"]).cuda(), x3)
+    al_d = torch.from_numpy(alpha).cuda()
+    ops.cg_flush_x(al_d, torch.from_numpy(a["p"]).cuda(), x3)
     np.testing.assert_array_equal(x3.cpu().numpy(), x_ref)
     r3 = torch.from_numpy(a["r"]).cuda()
-    ops.cg_update_xr(rho_d, pAp_d, None, None, d["A"], None, r3, out)  # r-only variant
+    al_out = torch.zeros(k, dtype=torch.float64, device="cuda")
+    ops.cg_update_xr(rho_d, pAp_d, None, None, d["A"], None, r3, out, alpha_out=al_out)  # r-only
     np.testing.assert_array_equal(r3.cpu().numpy(), r_ref)
+    np.testing.assert_array_equal(al_out.cpu().numpy(), alpha)
     # axpy_dot (arnoldi.py:157-162)
     w_ref = a["w"] - c1 * a["A"]
     ops.axpy_dot(c1_d, d["A"], d["w"], dot=1, z=d["x"], out=out)
