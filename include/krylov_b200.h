@@ -141,6 +141,29 @@ int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new
                    int* stop_at, double* rho_keep, const double* r, double* p, double* x, int what,
                    void* stream);
 
+/* Whole-loop entry point (SURVEY.md 8b "kb_cg_solve"): enqueues CG iterations
+ * i0 .. i0+n_iters-1 of the fused path on one GPU -- per iteration kb_cg_update_p
+ * (i > 0), kb_spmv fused with <p, Ap>, kb_cg_update_xr fused with <r, r>, record --
+ * each gated on *stop_at <= i, with no host involvement between iterations.
+ * slots: 6*k doubles = rho ping-pong (rho_i in slot i % 2), alpha, <p,Ap>, <r,r>, scratch.
+ * hist row 0 receives step i0+1.  x_pending: the x update of iteration i0-1 is still
+ * owed (it is folded into the first p update).  After the call the x update of the
+ * last executed iteration is owed (kb_cg_update_p what = 4 flushes it). */
+typedef struct {
+  kb_csr_t A;
+  int64_t n;
+  int k;
+  double* x;
+  double* r;
+  double* p;
+  double* Ap;
+  double* slots;
+  const double* crit;
+  double* hist;
+  int* stop_at;
+} kb_cg_state;
+int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending, void* stream);
+
 /* --- generic vector kernels (fallback path for M/Ml/Mr/custom inner) ---- */
 /* y += sign * coef[c] * x   (product rounded, then sum: NumPy temporaries) */
 int kb_axpy(kb_ws_t ws, int64_t n, int k, double sign, const double* coef, const double* x,

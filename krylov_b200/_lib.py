@@ -38,6 +38,13 @@ class MinresState(C.Structure):
     ]
 
 
+class CgState(C.Structure):
+    _fields_ = [
+        ("A", vp), ("n", i64), ("k", i32), ("x", vp), ("r", vp), ("p", vp), ("Ap", vp),
+        ("slots", vp), ("crit", vp), ("hist", vp), ("stop_at", vp),
+    ]
+
+
 class GmresState(C.Structure):
     _fields_ = [
         ("dots", vp), ("ww", vp), ("num_reorthos", i32), ("maxiter", i32), ("R", vp),
@@ -74,6 +81,7 @@ SIGNATURES = {
     "kb_dot": [vp, i64, i32, vp, vp, vp, vp],
     "kb_cg_update_xr": [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "kb_cg_update_p": [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "kb_cg_run": [vp, C.POINTER(CgState), i32, i32, i32, vp],
     "kb_axpy": [vp, i64, i32, f64, vp, vp, vp, vp],
     "kb_xpby": [vp, i64, i32, vp, vp, vp, vp],
     "kb_div_scale": [vp, i64, i32, vp, vp, vp, vp],

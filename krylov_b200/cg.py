@@ -20,8 +20,11 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+import ctypes as C
+
 from ._alg import Alg, nz
-from .device import Ops
+from ._lib import CgState, check, lib
+from .device import Ops, cur_stream, ptr
 from .operators import Info, Problem
 
 INT_MAX = 2**31 - 1
@@ -124,6 +127,12 @@ class FusedCG:
         self.crit_d = torch.from_numpy(np.ascontiguousarray(self.crit)).to(self.dev)
         self.p = self.r.clone()
         self.kk = 0
+        self._cstate = None
+        if self.comm is None and hasattr(A, "handle"):
+            self._cstate = CgState(A=A.handle, n=n, k=k, x=ptr(self.yk), r=ptr(self.r),
+                                   p=ptr(self.p), Ap=ptr(self.Ap), slots=ptr(self.sl),
+                                   crit=ptr(self.crit_d), hist=ptr(self.hist),
+                                   stop_at=ptr(self.stop_at))
         # x += alpha p of the last enqueued iteration is deferred into the next p
         # update (which streams p anyway: 64 instead of 72 B/element for the two
         # vector kernels of a step); current_x() flushes it
@@ -177,10 +186,17 @@ class FusedCG:
         residual norms of the steps that actually ran (the rest were gated)."""
         kk, k = self.kk, self.k
         self.stop_at.fill_(INT_MAX)
-        hist_ptr = self.hist.data_ptr() - (kk + 1) * k * 8  # history row kk+1 == hist[0]
-        for i in range(kk, kk + nb):
-            self.enqueue(i, hist_ptr)
-        self.ops.gate(None, 0)
+        if self.comm is None and self.spmv_events is None and self._cstate is not None:
+            # single GPU: the whole batch is enqueued by one C call (kb_cg_run)
+            check(lib.kb_cg_run(self.ops.ws.handle, C.byref(self._cstate), kk, nb,
+                                1 if self.x_pending else 0, cur_stream()))
+            self.ops.launches += 4 * nb - (1 if kk == 0 else 0)
+            self.x_pending = True
+        else:
+            hist_ptr = self.hist.data_ptr() - (kk + 1) * k * 8  # history row kk+1 == hist[0]
+            for i in range(kk, kk + nb):
+                self.enqueue(i, hist_ptr)
+            self.ops.gate(None, 0)
         s = int(self.stop_at.item())  # one host read per batch
         done = min(s, kk + nb) - kk
         rows = self.hist[:done].cpu().numpy()

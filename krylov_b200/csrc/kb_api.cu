@@ -685,6 +685,43 @@ int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new
   return KB_OK;
 }
 
+int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending, void* stream) {
+  KB_REQUIRE(ws != nullptr && s != nullptr, "null argument");
+  KB_REQUIRE(s->A && s->x && s->r && s->p && s->Ap && s->slots && s->crit && s->hist && s->stop_at,
+             "null field in kb_cg_state");
+  KB_REQUIRE(i0 >= 0 && n_iters >= 0, "negative iteration range");
+  const int k = s->k;
+  double* sl = s->slots;
+  const int* saved_gate = ws->gate;
+  const int saved_tag = ws->gate_tag;
+  int rc = KB_OK;
+  for (int i = i0; i < i0 + n_iters && rc == KB_OK; ++i) {
+    double* cur = sl + (size_t)(i % 2) * k;        // rho_i
+    double* nxt = sl + (size_t)((i + 1) % 2) * k;  // rho_{i-1}, then rho_{i+1}
+    double* alpha = sl + 2 * (size_t)k;
+    double* pAp = sl + 3 * (size_t)k;
+    double* rr = sl + 4 * (size_t)k;
+    ws->gate = s->stop_at;
+    ws->gate_tag = i;
+    if (i > 0)
+      rc = kb_cg_update_p(ws, s->n, k, 0, cur, nxt, alpha, nullptr, nullptr, nullptr, nullptr, s->r,
+                          s->p, x_pending ? s->x : nullptr, x_pending ? 5 : 1, stream);
+    if (rc == KB_OK)
+      rc = kb_spmv(s->A, ws, k, s->p, s->Ap, 0, nullptr, nullptr, 1, s->p, pAp, stream);
+    if (rc == KB_OK)
+      rc = kb_cg_update_xr(ws, s->n, k, cur, pAp, nullptr, nullptr, s->Ap, nullptr, s->r, rr, alpha,
+                           stream);
+    x_pending = 1;
+    if (rc == KB_OK)  // hist row (i - i0) <- step i+1
+      rc = kb_cg_update_p(ws, s->n, k, i + 1, rr, nullptr, nullptr, s->crit,
+                          s->hist - (size_t)(i0 + 1) * k, s->stop_at, nxt, nullptr, nullptr, nullptr, 2,
+                          stream);
+  }
+  ws->gate = saved_gate;
+  ws->gate_tag = saved_tag;
+  return rc;
+}
+
 int kb_axpy(kb_ws_t ws, int64_t n, int k, double sign, const double* coef, const double* x,
             double* y, void* stream) {
   KB_VEC_PROLOGUE();
