@@ -523,6 +523,10 @@ template <int DOT>
 static int kb_launch_window(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
                             const double* z, const double* coef, const double* w, double* out,
                             cudaStream_t st) {
+  // measured (profiles/r1_window_sweep.txt): 512-row tiles win by ~4 % on the 512^3 matrix,
+  // 256-row tiles (4 CTAs/SM) at 256^3 and below
+  if (g_window_cfg == 0 && A->n_rows > (40ll << 20))
+    return kb_launch_window_cfg<512, 2, 2, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
   switch (g_window_cfg) {
     case 1: return kb_launch_window_cfg<256, 3, 3, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
     case 2: return kb_launch_window_cfg<512, 2, 2, DOT>(A, ws, x, y, mode, z, coef, w, out, st);

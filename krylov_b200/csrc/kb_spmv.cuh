@@ -120,6 +120,27 @@ __device__ __forceinline__ void kb_bulk_g2s(void* dst, const void* src, uint32_t
       : "memory");
 }
 
+// same, with an L2 eviction-priority hint (createpolicy): the matrix stream is read
+// once (evict_first) while x windows are re-read by later tiles (evict_last)
+__device__ __forceinline__ void kb_bulk_g2s_hint(void* dst, const void* src, uint32_t bytes,
+                                                 uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(kb_smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(kb_smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t kb_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t kb_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
 // ---------------------------------------------------- TMA-staged stream k==1 --
 // rows per tile == consumer threads (template parameter ROWS); + one producer warp
 #define KB_ST_MAX_THREADS (512 + 32)
@@ -559,6 +580,8 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen,
     const int lane = tid & 31;
     int stage = 0;
     uint32_t phase = 0;
+    const uint64_t pol_stream = kb_policy_evict_first();  // matrix values: read once
+    const uint64_t pol_keep = kb_policy_evict_last();     // x windows: re-read by later tiles
     for (int64_t base = blockIdx.x; base < n_tiles; base += 32ll * gridDim.x) {
       const int64_t my_tile = base + (int64_t)lane * gridDim.x;
       int my_s = 0, my_e = 0;
@@ -584,15 +607,15 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen,
             bytes += (uint32_t)gn * 8u;  // n_cols is even: the rounded end stays in bounds
           }
           kb_mbar_expect_tx(&s_full[stage], bytes);
-          kb_bulk_g2s(s_vals + (size_t)stage * cap, vals + a0, (uint32_t)(a1 - a0) * 8u,
-                      &s_full[stage]);
+          kb_bulk_g2s_hint(s_vals + (size_t)stage * cap, vals + a0, (uint32_t)(a1 - a0) * 8u,
+                           &s_full[stage], pol_stream);
           for (int g = 0; g < nw; ++g) {  // pass 2: issue
             const int ge = min(r0 + pat.wlo[g] + ROWS + pat.wspan[g], n_cols);
             const int ga = kb_win_start(r0, pat.wlo[g]);
             const int gn = max(((ge + 1) & ~1) - ga, 0);
             if (gn > 0)
-              kb_bulk_g2s(s_win + ((size_t)stage * nw + g) * wlen, x + ga, (uint32_t)gn * 8u,
-                          &s_full[stage]);
+              kb_bulk_g2s_hint(s_win + ((size_t)stage * nw + g) * wlen, x + ga,
+                               (uint32_t)gn * 8u, &s_full[stage], pol_keep);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -673,7 +696,7 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen,
         double yv = sum;
         if (mode == 1) yv = kb_mul_sub(cf, zv, sum);
         if (mode == 2) yv = __dsub_rn(zv, sum);
-        y[row] = yv;
+        __stcs(&y[row], yv);  // streaming store: y is not re-read by this kernel
         if (DOT == 1) acc = fma(wv, yv, acc);
         if (DOT == 2) acc = fma(yv, yv, acc);
       }
