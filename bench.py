@@ -156,13 +156,29 @@ class ClockSampler:
         self.p = None
 
     def start(self):
+        """Starts nvidia-smi and waits (<= 3 s) for its first sample, so that even a
+        timed region of a few tens of milliseconds is covered."""
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+            return
+        t0 = time.time()
+        while time.time() - t0 < 3.0 and self._lines() == 0:
+            time.sleep(0.02)
+
+    def _lines(self):
+        try:
+            return sum(1 for _ in open(self.f.name))
+        except OSError:
+            return 0
+
+    def mark(self):
+        """Call at the start of the timed region: samples before this are dropped."""
+        self.first = self._lines()
 
     def stop(self):
         if self.p is None:
@@ -176,7 +192,12 @@ class ClockSampler:
         self.f.flush()
         self.f.seek(0)
         sm, mx, reasons = [], [], set()
-        for ln in self.f.read().strip().splitlines():
+        all_lines = self.f.read().strip().splitlines()
+        first = getattr(self, "first", 0)
+        # samples taken during the timed region (from mark() on); the one just before
+        # it is kept as well so that a very short region still has a reading under load
+        lines = all_lines[max(first - 1, 0):]
+        for ln in lines:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -262,13 +283,17 @@ def ours(args):
     for _ in range(W):
         st.enqueue(it, hist0 - (it + 1) * 8)
         it += 1
-    barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
+    for _ in range(W):  # keep the GPU under load while the sampler spins up
+        st.enqueue(it, hist0 - (it + 1) * 8)
+        it += 1
+    barrier()
     launches0 = st.ops.launches
     st.spmv_events = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark()
     e0.record()
     for _ in range(K):
         st.enqueue(it, hist0 - (it + 1) * 8)

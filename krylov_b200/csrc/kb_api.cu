@@ -45,6 +45,7 @@ static int g_pattern_ctas = 0; // kb_tune key 3 (0 = default)
 static int g_window_cfg = 0;   // kb_tune key 4
 static int g_rowwise_contig = -1;  // kb_tune key 5: -1 auto, 0 strided, 1 contiguous rows per block
 static int g_rowwise_ctas = 0;     // kb_tune key 6: CTAs/SM of the contiguous row-wise grid
+static int g_spmm_cfg = 0;         // kb_tune key 7: 0 = RPT 2, 1 = RPT 4, -1 = row-wise kernel
 int g_vec_ctas = KB_CTAS_PER_SM;
 
 // Finds the set of distinct diagonals (col - row); if there are at most 16 and every
@@ -151,6 +152,7 @@ int kb_tune(int key, int value) {
     case 4: g_window_cfg = value; return KB_OK;  // -1: gather variant of the pattern kernel
     case 5: g_rowwise_contig = value; return KB_OK;
     case 6: g_rowwise_ctas = value; return KB_OK;
+    case 7: g_spmm_cfg = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -537,6 +539,51 @@ static int kb_launch_window(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y
   }
 }
 
+template <int STAGES, int RPT, int MINB, int DOT>
+static int kb_launch_spmm_window_cfg(kb_csr_s* A, kb_ws_s* ws, int k, const double* x, double* y,
+                                     int mode, const double* z, const double* coef,
+                                     const double* w, double* out, cudaStream_t st) {
+  static int max_smem[64] = {0};
+  auto kern = kb_spmm_window_kernel<STAGES, RPT, MINB, DOT>;
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  int span = 0;
+  for (int g = 0; g < A->pat.nw; ++g) span = A->pat.wspan[g] > span ? A->pat.wspan[g] : span;
+  const int rows_t = RPT * (256 / k);
+  const int cap = (rows_t * A->pat.nd + 8 + 3) & ~3;
+  const int wlen = rows_t + span;  // x rows per window
+  const size_t smem =
+      ((size_t)STAGES * cap + (size_t)STAGES * A->pat.nw * wlen * k) * 8 + 16 * STAGES;
+  if (dev < 0 || dev >= 64 || max_smem[dev] == 0) {
+    int lim = 0;
+    KB_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lim - 8 * 1024));
+    if (dev >= 0 && dev < 64) max_smem[dev] = lim - 8 * 1024;
+  }
+  if (smem > (size_t)max_smem[dev < 64 && dev >= 0 ? dev : 0]) return KB_EUNSUPPORTED;
+  int ctas = 0;
+  KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 288, smem));
+  if (ctas < 1) return KB_EUNSUPPORTED;
+  const int n_tiles = (int)((A->n_rows + rows_t - 1) / rows_t);
+  int grid = ws->num_sms * ctas;
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
+  kern<<<grid, 288, smem, st>>>((int)A->n_rows, (int)A->n_cols, n_tiles, k, cap, wlen, A->rowptr,
+                                A->masks, A->vals, A->pat, x, y, mode, z, coef, w, out, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+template <int DOT>
+static int kb_launch_spmm_window(kb_csr_s* A, kb_ws_s* ws, int k, const double* x, double* y,
+                                 int mode, const double* z, const double* coef, const double* w,
+                                 double* out, cudaStream_t st) {
+  if (g_spmm_cfg == 1)
+    return kb_launch_spmm_window_cfg<2, 4, 2, DOT>(A, ws, k, x, y, mode, z, coef, w, out, st);
+  return kb_launch_spmm_window_cfg<2, 2, 4, DOT>(A, ws, k, x, y, mode, z, coef, w, out, st);
+}
+
 template <int DOT>
 static int kb_launch_pattern(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
                              const double* z, const double* coef, const double* w, double* out,
@@ -577,6 +624,15 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
     if (dot == 0) return kb_launch_stream<0>(A, ws, x, y, mode, z, coef, w, out, st);
     if (dot == 1) return kb_launch_stream<1>(A, ws, x, y, mode, z, coef, w, out, st);
     return kb_launch_stream<2>(A, ws, x, y, mode, z, coef, w, out, st);
+  }
+  // blocked right-hand sides on a stencil-like matrix: windowed SpMM
+  if (k > 1 && 256 % k == 0 && A->pattern_ok && A->pat.nw > 0 && g_spmm_cfg >= 0 &&
+      A->forced != 1 && ((uintptr_t)x % 16 == 0)) {
+    int rc;
+    if (dot == 0) rc = kb_launch_spmm_window<0>(A, ws, k, x, y, mode, z, coef, w, out, st);
+    else if (dot == 1) rc = kb_launch_spmm_window<1>(A, ws, k, x, y, mode, z, coef, w, out, st);
+    else rc = kb_launch_spmm_window<2>(A, ws, k, x, y, mode, z, coef, w, out, st);
+    if (rc != KB_EUNSUPPORTED) return rc;  // else: stage buffers do not fit -> row-wise kernel
   }
   const int block = kb_block_for(k);
   int grid = kb_grid_for(ws, A->n_rows * (int64_t)k, block, 1);

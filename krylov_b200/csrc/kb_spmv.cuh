@@ -705,6 +705,168 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen,
   if (DOT != 0) kb_grid_colsum(acc, 1, rd, out, red_sm);
 }
 
+// ------------------------------------------ windowed pattern kernel, k > 1 ----
+// SpMM for k right-hand sides in lock-step (x, y are (n, k) row-major): the same
+// compressed matrix and TMA x windows; a window is now rows_t + span consecutive
+// x ROWS (k doubles each, contiguous).  256 consumer threads = (256/k) rows x k
+// columns per pass, RPT passes per tile (rows_t = RPT * 256 / k), so the shared
+// memory per stage is independent of k.  Requires 256 % k == 0 and 16-byte
+// aligned x (k even makes every window start 16-byte aligned).
+template <int STAGES, int RPT, int MINB, int DOT>
+__global__ void __launch_bounds__(288, MINB)
+kb_spmm_window_kernel(int n_rows, int n_cols, int n_tiles, int k, int cap, int wlen,
+                      const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ masks,
+                      const double* __restrict__ vals, KbPattern pat,
+                      const double* __restrict__ x, double* __restrict__ y, int mode,
+                      const double* __restrict__ z, const double* __restrict__ coef,
+                      const double* __restrict__ w, double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  extern __shared__ __align__(128) unsigned char kb_dyn_smem[];
+  const int nw = pat.nw;
+  const int rows_pass = 256 / k;
+  const int rows_t = RPT * rows_pass;
+  double* const s_vals = reinterpret_cast<double*>(kb_dyn_smem);
+  double* const s_win = s_vals + (size_t)STAGES * cap;
+  uint64_t* const s_full =
+      reinterpret_cast<uint64_t*>(s_win + (size_t)STAGES * nw * wlen * k);
+  uint64_t* const s_empty = s_full + STAGES;
+  __shared__ double red_sm[288];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      kb_mbar_init(&s_full[s], 1);
+      kb_mbar_init(&s_empty[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc = 0.0;
+
+  if (warp == 8) {
+    const int lane = tid & 31;
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint64_t pol_stream = kb_policy_evict_first();
+    const uint64_t pol_keep = kb_policy_evict_last();
+    for (int64_t base = blockIdx.x; base < n_tiles; base += 32ll * gridDim.x) {
+      const int64_t my_tile = base + (int64_t)lane * gridDim.x;
+      int my_s = 0, my_e = 0;
+      if (my_tile < n_tiles) {
+        const int r0 = (int)my_tile * rows_t;
+        const int r1 = min(r0 + rows_t, n_rows);
+        my_s = rowptr[r0];
+        my_e = rowptr[r1];
+      }
+      for (int q = 0; q < 32; ++q) {
+        const int64_t tile = base + (int64_t)q * gridDim.x;
+        if (tile >= n_tiles) break;
+        const int s = __shfl_sync(0xffffffffu, my_s, q);
+        const int e = __shfl_sync(0xffffffffu, my_e, q);
+        if (lane == 0 && e > s) {
+          const int r0 = (int)tile * rows_t;
+          const int a0 = s & ~3, a1 = (e + 3) & ~3;
+          kb_mbar_wait(&s_empty[stage], phase ^ 1u);
+          uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
+          for (int g = 0; g < nw; ++g) {
+            const int gs = max(r0 + pat.wlo[g], 0);
+            const int ge = min(r0 + pat.wlo[g] + rows_t + pat.wspan[g], n_cols);
+            bytes += (uint32_t)max(ge - gs, 0) * (uint32_t)k * 8u;
+          }
+          kb_mbar_expect_tx(&s_full[stage], bytes);
+          kb_bulk_g2s_hint(s_vals + (size_t)stage * cap, vals + a0, (uint32_t)(a1 - a0) * 8u,
+                           &s_full[stage], pol_stream);
+          for (int g = 0; g < nw; ++g) {
+            const int gs = max(r0 + pat.wlo[g], 0);
+            const int ge = min(r0 + pat.wlo[g] + rows_t + pat.wspan[g], n_cols);
+            if (ge > gs)
+              kb_bulk_g2s_hint(s_win + ((size_t)stage * nw + g) * wlen * k, x + (size_t)gs * k,
+                               (uint32_t)(ge - gs) * (uint32_t)k * 8u, &s_full[stage], pol_keep);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    int stage = 0;
+    uint32_t phase = 0;
+    const int c = tid % k;
+    const int rs = tid / k;
+    const double cf = (mode == 1) ? coef[c] : 0.0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int r0 = tile * rows_t;
+      const int r1 = min(r0 + rows_t, n_rows);
+      const int s = rowptr[r0], e = rowptr[r1];
+      int lo[RPT];
+      unsigned mk[RPT];
+      double zv[RPT], wv[RPT];
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        const int row = r0 + rs + q * rows_pass;
+        lo[q] = 0;
+        mk[q] = 0;
+        zv[q] = 0.0;
+        wv[q] = 0.0;
+        if (row < n_rows) {
+          lo[q] = rowptr[row];
+          mk[q] = masks[row];
+          if (mode != 0) zv[q] = z[(size_t)row * k + c];
+          if (DOT == 1) wv[q] = w[(size_t)row * k + c];
+        }
+      }
+      double sum[RPT];
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) sum[q] = 0.0;
+      if (e > s) {
+        kb_mbar_wait(&s_full[stage], phase);
+        const double* sv = s_vals + (size_t)stage * cap;
+        const double* sw = s_win + (size_t)stage * nw * wlen * k;
+        const int a0 = s & ~3;
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+          const int row = r0 + rs + q * rows_pass;
+          int j = lo[q] - a0;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) {
+            if (d < pat.nd && (mk[q] >> d) & 1u) {
+              const int xr = row + pat.off[d] - max(r0 + pat.dwlo[d], 0);
+              const double xv = sw[((size_t)pat.grp[d] * wlen + xr) * k + c];
+              sum[q] = __dadd_rn(sum[q], __dmul_rn(sv[j], xv));
+              ++j;
+            }
+          }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) kb_mbar_arrive(&s_empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        const int row = r0 + rs + q * rows_pass;
+        if (row < n_rows) {
+          double yv = sum[q];
+          if (mode == 1) yv = kb_mul_sub(cf, zv[q], sum[q]);
+          if (mode == 2) yv = __dsub_rn(zv[q], sum[q]);
+          __stcs(&y[(size_t)row * k + c], yv);
+          if (DOT == 1) acc = fma(wv[q], yv, acc);
+          if (DOT == 2) acc = fma(yv, yv, acc);
+        }
+      }
+    }
+  }
+  if (DOT != 0) kb_grid_colsum(acc, k, rd, out, red_sm);
+}
+
 // ------------------------------------------------- boundary rows (halo part) --
 // Row-partitioned matrices: the local product runs on the
 // columns a rank owns while the halo entries travel; this kernel then finishes
