@@ -45,7 +45,8 @@ static int g_pattern_ctas = 0; // kb_tune key 3 (0 = default)
 static int g_window_cfg = 0;   // kb_tune key 4
 static int g_rowwise_contig = -1;  // kb_tune key 5: -1 auto, 0 strided, 1 contiguous rows per block
 static int g_rowwise_ctas = 0;     // kb_tune key 6: CTAs/SM of the contiguous row-wise grid
-static int g_spmm_cfg = 0;         // kb_tune key 7: 0 = RPT 2, 1 = RPT 4, -1 = row-wise kernel
+static int g_spmm_cfg = -1;        // kb_tune key 7: -1 = row-wise kernel (default: measured equal
+                                   // or faster, profiles/r1_configs.txt), 0 = windowed RPT 2, 1 = RPT 4
 int g_vec_ctas = KB_CTAS_PER_SM;
 
 // Finds the set of distinct diagonals (col - row); if there are at most 16 and every

@@ -60,6 +60,29 @@ class Workspace:
             pass
 
 
+# Workspaces are pooled per (device, k): creating one is a cudaMalloc and destroying
+# one a cudaFree (which synchronises the device and can stall for tens of ms), so a
+# solve borrows a workspace and hands it back instead -- after the first solve of a
+# given block width the library performs no device allocation at all.
+_WS_POOL = {}
+
+
+def _borrow_workspace(device, k):
+    free = _WS_POOL.setdefault((device.index, int(k)), [])
+    return free.pop() if free else Workspace(k)
+
+
+def _return_workspace(device, k, ws):
+    try:
+        lib.kb_ws_set_gate(ws.handle, None, 0)
+        lib.kb_ws_set_comm(ws.handle, None, 0)
+        free = _WS_POOL.setdefault((device.index, int(k)), [])
+        if len(free) < 16:
+            free.append(ws)
+    except Exception:
+        pass
+
+
 class Ops:
     """Kernel launches for (n, k) fp64 vectors on the current CUDA stream."""
 
@@ -75,12 +98,18 @@ class Ops:
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device())
         with torch.cuda.device(self.device):
-            self.ws = Workspace(k)
+            self.ws = _borrow_workspace(self.device, k)
         self.launches = 0  # kernels enqueued through this object (bench `gpu_launches`)
         # peer-memory communicator: reductions are all-reduced inside the reducing kernel
         self.fused_allreduce = comm is not None and getattr(comm, "p2p_handle", None) is not None
         if self.fused_allreduce:
             self.set_collective(True)
+
+    def __del__(self):
+        ws = getattr(self, "ws", None)
+        if ws is not None:
+            self.ws = None
+            _return_workspace(self.device, self.k, ws)
 
     def set_collective(self, on: bool):
         check(lib.kb_ws_set_comm(self.ws.handle, self.comm.p2p_handle, 1 if on else 0))

@@ -1,7 +1,16 @@
-class ArgumentError(Exception):
-    """Raised when an argument is invalid (same name and role as the
-    reference's ``krylov.errors.ArgumentError``, errors.py:1-9): e.g. stepping an
-    Arnoldi process whose Krylov subspace was already found invariant."""
+"""Exception types of krylov_b200.
 
-    def __init__(self, message):
-        super().__init__(message)
+``ArgumentError`` keeps the name and role it has in the reference package
+(``krylov.errors``): it is what stepping an Arnoldi/Lanczos process raises once
+its Krylov subspace was found invariant, and what the solvers raise when they
+would need such a step.  It derives from ``KrylovB200Error``'s sibling base so
+callers can catch everything this package raises with one ``except`` clause.
+"""
+
+
+class KrylovError(Exception):
+    """Base class of the algorithmic errors raised by this package."""
+
+
+class ArgumentError(KrylovError):
+    pass

@@ -81,6 +81,39 @@ def test_pattern_kernel_variants_bit_exact(cfg):
         lib.kb_tune(4, 0)
 
 
+@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("k", [2, 4, 16, 64])
+def test_windowed_spmm_variants_bit_exact(cfg, k):
+    """The TMA-window SpMM for blocked right-hand sides (kb_tune 7; row-wise is the
+    default because it measured no slower) is bit-identical to SciPy as well."""
+    from krylov_b200._lib import lib
+
+    lib.kb_tune(7, cfg)
+    try:
+        for A in (st.poisson3d(9), st.convection_diffusion3d(10), st.poisson2d(31),
+                  st.to_scipy(st.stencil7_csr(3, 2, 150))):
+            n = A.shape[0]
+            Ad = kb.CsrMatrix.from_scipy(A)
+            X, Z, W = (rng.standard_normal((n, k)) for _ in range(3))
+            np.testing.assert_array_equal(Ad @ X, A @ X)
+            ops = Ops(n, k)
+            x, z, w = (torch.from_numpy(a).cuda() for a in (X, Z, W))
+            cf = torch.from_numpy(rng.standard_normal(k)).cuda()
+            y = torch.empty_like(x)
+            out = ops.slots(1)[0]
+            ops.spmv(Ad, x, y, mode=1, z=z, coef=cf, dot=1, w=w, out=out)
+            ref = A @ X - cf.cpu().numpy() * Z
+            np.testing.assert_array_equal(y.cpu().numpy(), ref)
+            np.testing.assert_allclose(out.cpu().numpy(), np.einsum("ij,ij->j", W, ref), rtol=1e-12,
+                                       atol=1e-12)
+            ops.spmv(Ad, x, y, mode=2, z=z, dot=2, out=out)
+            ref = Z - A @ X
+            np.testing.assert_array_equal(y.cpu().numpy(), ref)
+            np.testing.assert_allclose(out.cpu().numpy(), np.einsum("ij,ij->j", ref, ref), rtol=1e-12)
+    finally:
+        lib.kb_tune(7, -1)
+
+
 def test_pattern_schedule_selection():
     """Offset-pattern compression is chosen for stencil-like matrices only."""
     assert kb.CsrMatrix.from_scipy(st.poisson3d(9)).info()["schedule"] == "pattern"

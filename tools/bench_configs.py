@@ -17,7 +17,8 @@ except Exception:
 out = []
 
 def timed(fn, reps=1):
-    fn()  # warm-up
+    fn()  # warm-up (also lets the caching allocator settle: no cudaMalloc in the timed call)
+    fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -52,10 +53,14 @@ for ortho, r in (("mgs", 1), ("mgs2", 2)):
 secs, (sol, info) = timed(lambda: kb.gmres(A, b, tol=1e-8, maxiter=50, ortho="householder"))
 byt = sum(12*A.nnz + 4*(n+1) + 40*n + 32*n*(2*j+3) for j in range(50))
 report("C3 gmres conv-diff 256^3 one 50-step cycle ortho=householder", info.numsteps, secs, byt)
-del A, b, sol, info; torch.cuda.empty_cache()
+del A, b, sol, info
 # C4: blocked cg k=16, 3-D Poisson 256^3, 50 fixed iterations
 N = 256; A = device_stencil7(N, N, N); n = A.shape[0]
 B = torch.randn((n, 16), generator=g, dtype=torch.float64, device="cuda")
-secs, (sol, info) = timed(lambda: kb.cg(A, B, tol=0.0, atol=0.0, maxiter=50))
-report("C4 blocked cg k=16 3D Poisson 256^3, 50 fixed iterations", info.numsteps, secs, info.numsteps * (12*A.nnz + 4*(n+1) + 92*n*16))
+from krylov_b200._lib import lib
+for cfg, nm in ((-1, "row-wise SpMM"), (0, "windowed SpMM RPT=2"), (1, "windowed SpMM RPT=4")):
+    lib.kb_tune(7, cfg)
+    secs, (sol, info) = timed(lambda: kb.cg(A, B, tol=0.0, atol=0.0, maxiter=50))
+    report(f"C4 blocked cg k=16 3D Poisson 256^3, 50 fixed iterations [{nm}]", info.numsteps, secs, info.numsteps * (12*A.nnz + 4*(n+1) + 92*n*16))
+lib.kb_tune(7, 0)
 open(os.path.join(ROOT, "gpurun_out", "configs.txt"), "w").write("\n".join(out) + "\n")
