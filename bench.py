@@ -374,6 +374,7 @@ def ours(args):
             "config": {"workload": workload_name(N), "n": n_glob, "nnz": nnz_glob,
                        "parallelism": f"rows/{world}" if world > 1 else "single GPU",
                        "allreduce": (A.comm.allreduce_mode if world > 1 else None),
+                       "halo": (A.halo_mode if world > 1 else None),
                        "spmv_schedule": info_sched.get("schedule"),
                        "l2": "inputs larger than L2 (24 GB of operands per step)",
                        "tol": "0 (fixed K iterations; the stopping test never fires)"},

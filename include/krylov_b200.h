@@ -41,6 +41,7 @@ extern "C" {
 typedef struct kb_csr_s* kb_csr_t; /* CSR matrix view + schedule */
 typedef struct kb_ws_s* kb_ws_t;   /* reduction workspace + gate  */
 typedef struct kb_comm_s* kb_comm_t; /* peer-memory communicator (one per process/GPU) */
+typedef struct kb_halo_s* kb_halo_t; /* peer-memory halo receive area of one partitioned matrix */
 
 /* --- library ---------------------------------------------------------- */
 int kb_version(void);
@@ -109,11 +110,28 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y,
  * entries xh have arrived: for i < n_brows, row = rows[i]:
  *   h = sum_j hval[j] * xh[hcol[j], c];  y[row, c] += sign * h
  *   dot 1: out[c] += sum_i w[row, c] * sign * h   (accumulates onto the slot the
- *          local kb_spmv wrote, so one all-reduce covers the whole inner product) */
+ *          local kb_spmv wrote, so one all-reduce covers the whole inner product)
+ * halo == NULL: xh is a receive buffer filled by the caller (NCCL send/recv).
+ * halo != NULL: xh is ignored; the entries were pushed into this rank's peer-memory
+ *          data area by the sources srcs[0..n_src) (device array); the kernel waits for
+ *          their flags and acknowledges when it is done (see kb_halo_push). */
 int kb_spmv_halo_add(kb_ws_t ws, int k, int64_t n_brows, double sign, const int32_t* rows,
                      const int32_t* hrowptr, const int32_t* hcol, const double* hval,
                      const double* xh, double* y, int dot, const double* w, double* out,
-                     void* stream);
+                     kb_halo_t halo, const int* srcs, int n_src, void* stream);
+/* Peer-memory halo exchange: one IPC-exported receive area per rank (flags, acks, product
+ * counter, data).  kb_halo_push gathers the boundary rows of x listed in idx straight into
+ * the destinations' data areas over NVLink and raises their flags -- no NCCL kernel in the
+ * iteration.  segs: n_seg x 4 int64 on the device = (destination rank, first entry in idx,
+ * number of entries, first row in the destination's data area).  Must be launched by every
+ * rank for every product (n_seg may be 0) so the device-resident product counters agree. */
+int kb_halo_create(kb_halo_t* h, int rank, int size, int64_t data_bytes);
+int kb_halo_get_handle(kb_halo_t h, void* out64);
+int kb_halo_open(kb_halo_t h, const void* handles);
+int kb_halo_destroy(kb_halo_t h);
+int kb_halo_error(kb_halo_t h, int* err);
+int kb_halo_push(kb_halo_t h, kb_ws_t ws, int k, int n_seg, const int64_t* segs, int64_t n_total,
+                 const int32_t* idx, const double* x, void* stream);
 /* gather x[idx[i], :] -> buf[i, :] (halo send buffer) */
 int kb_pack_rows(kb_ws_t ws, int k, int64_t n_idx, const int32_t* idx, const double* x,
                  double* buf, void* stream);

@@ -76,7 +76,13 @@ SIGNATURES = {
     "kb_csr_get_info": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32),
                         C.POINTER(i32)],
     "kb_spmv": [vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp],
-    "kb_spmv_halo_add": [vp, i32, i64, f64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
+    "kb_spmv_halo_add": [vp, i32, i64, f64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp],
+    "kb_halo_create": [C.POINTER(vp), i32, i32, i64],
+    "kb_halo_get_handle": [vp, vp],
+    "kb_halo_open": [vp, vp],
+    "kb_halo_destroy": [vp],
+    "kb_halo_error": [vp, C.POINTER(i32)],
+    "kb_halo_push": [vp, vp, i32, i32, vp, i64, vp, vp, vp],
     "kb_pack_rows": [vp, i32, i64, vp, vp, vp, vp],
     "kb_dot": [vp, i64, i32, vp, vp, vp, vp],
     "kb_cg_update_xr": [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],

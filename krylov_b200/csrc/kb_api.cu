@@ -660,22 +660,114 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
 int kb_spmv_halo_add(kb_ws_t ws, int k, int64_t n_brows, double sign, const int32_t* rows,
                      const int32_t* hrowptr, const int32_t* hcol, const double* hval,
                      const double* xh, double* y, int dot, const double* w, double* out,
-                     void* stream) {
+                     kb_halo_t halo, const int* srcs, int n_src, void* stream) {
   KB_REQUIRE(ws != nullptr, "null workspace");
   KB_REQUIRE(k >= 1 && k <= ws->max_k, "k exceeds workspace max_k");
   KB_REQUIRE(dot == 0 || dot == 1, "dot must be 0 or 1");
   KB_REQUIRE(dot == 0 || (w != nullptr && out != nullptr), "dot 1 needs w and out");
+  KB_REQUIRE(halo == nullptr || (halo->opened && n_src >= 0 && n_src <= KB_BLOCK / 2),
+             "halo not opened / too many sources");
+  KB_REQUIRE(halo != nullptr || xh != nullptr || n_brows == 0, "need xh or a peer halo");
   cudaStream_t st = S(stream);
   if (n_brows == 0) return KB_OK;  // nothing to add (the dot slot keeps the local part)
   const int block = kb_block_for(k);
   const int grid = kb_grid_for(ws, n_brows * (int64_t)k, block, 1);
   KbRed rd = kb_red(ws);
+  KbHalo hd;
+  hd.peers = halo ? halo->dev.peers : nullptr;
+  hd.rank = halo ? halo->dev.rank : 0;
+  hd.size = halo ? halo->dev.size : 1;
   if (dot == 0)
     kb_spmv_halo_add_kernel<0><<<grid, block, 0, st>>>(n_brows, k, sign, rows, hrowptr, hcol, hval,
-                                                       xh, y, w, out, rd);
+                                                       xh, y, w, out, hd, srcs, n_src, rd);
   else
     kb_spmv_halo_add_kernel<1><<<grid, block, 0, st>>>(n_brows, k, sign, rows, hrowptr, hcol, hval,
-                                                       xh, y, w, out, rd);
+                                                       xh, y, w, out, hd, srcs, n_src, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+// ------------------------------------------------------------ peer halo ---
+int kb_halo_create(kb_halo_t* out, int rank, int size, int64_t data_bytes) {
+  KB_REQUIRE(out != nullptr, "null handle pointer");
+  KB_REQUIRE(size >= 1 && size <= 64 && rank >= 0 && rank < size, "bad rank/size");
+  KB_REQUIRE(data_bytes >= 0, "negative size");
+  kb_halo_s* h = new (std::nothrow) kb_halo_s();
+  if (!h) return kb_fail(KB_ENOMEM, "out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->dev.rank = rank;
+  h->dev.size = size;
+  h->data_bytes = (size_t)data_bytes;
+  const size_t bytes = KB_HALO_DATA + ((size_t)data_bytes + 255) / 256 * 256 + 256;
+  cudaError_t e = cudaMalloc(&h->base, bytes);
+  if (e == cudaSuccess) e = cudaMemset(h->base, 0, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->peers_dev, sizeof(unsigned char*) * size);
+  if (e != cudaSuccess) {
+    if (h->base) cudaFree(h->base);
+    delete h;
+    return kb_fail(KB_ECUDA, "kb_halo_create: %s", cudaGetErrorString(e));
+  }
+  h->dev.peers = h->peers_dev;
+  *out = h;
+  return KB_OK;
+}
+
+int kb_halo_get_handle(kb_halo_t h, void* out64) {
+  KB_REQUIRE(h != nullptr && out64 != nullptr, "null argument");
+  cudaIpcMemHandle_t ih;
+  KB_CUDA(cudaIpcGetMemHandle(&ih, h->base));
+  memcpy(out64, &ih, 64);
+  return KB_OK;
+}
+
+int kb_halo_open(kb_halo_t h, const void* handles) {
+  KB_REQUIRE(h != nullptr && handles != nullptr, "null argument");
+  KB_REQUIRE(!h->opened, "already opened");
+  unsigned char* table[64];
+  for (int p = 0; p < h->dev.size; ++p) {
+    if (p == h->dev.rank) {
+      table[p] = h->base;
+      continue;
+    }
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, (const char*)handles + 64 * (size_t)p, 64);
+    void* base = nullptr;
+    KB_CUDA(cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_base[p] = base;
+    table[p] = (unsigned char*)base;
+  }
+  KB_CUDA(cudaMemcpy(h->peers_dev, table, sizeof(unsigned char*) * h->dev.size,
+                     cudaMemcpyHostToDevice));
+  h->opened = 1;
+  return KB_OK;
+}
+
+int kb_halo_destroy(kb_halo_t h) {
+  if (!h) return KB_OK;
+  for (int p = 0; p < h->dev.size; ++p)
+    if (h->peer_base[p]) cudaIpcCloseMemHandle(h->peer_base[p]);
+  if (h->peers_dev) cudaFree(h->peers_dev);
+  if (h->base) cudaFree(h->base);
+  delete h;
+  return KB_OK;
+}
+
+int kb_halo_error(kb_halo_t h, int* err) {
+  KB_REQUIRE(h != nullptr && err != nullptr, "null argument");
+  KB_CUDA(cudaMemcpy(err, h->base + KB_HALO_ERROR, sizeof(int), cudaMemcpyDeviceToHost));
+  return KB_OK;
+}
+
+int kb_halo_push(kb_halo_t h, kb_ws_t ws, int k, int n_seg, const int64_t* segs, int64_t n_total,
+                 const int32_t* idx, const double* x, void* stream) {
+  KB_REQUIRE(h != nullptr && ws != nullptr, "null handle");
+  KB_REQUIRE(h->opened, "halo not opened");
+  KB_REQUIRE(k >= 1 && n_seg >= 0 && n_seg <= KB_BLOCK / 2 && n_total >= 0, "bad sizes");
+  KB_REQUIRE(n_seg == 0 || (segs && idx && x), "null argument");
+  int grid = kb_grid_for(ws, n_total * (int64_t)k, KB_BLOCK, 1);
+  if (grid > 64) grid = 64;  // a few MB at most: keep it small so it starts at once
+  kb_halo_push_kernel<<<grid, KB_BLOCK, 0, S(stream)>>>(k, n_seg, segs, n_total, idx, x, h->dev,
+                                                        kb_red(ws));
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

@@ -65,6 +65,55 @@ struct kb_comm_s {
   int opened;
 };
 
+// ------------------------------------------------------------ peer halo ---
+// Halo exchange of row-partitioned products through NVLink peer memory, no NCCL
+// kernel involved (a NCCL send/recv kernel cannot get an SM while the persistent
+// SpMV fills the GPU, so the exchange used to serialise behind it).
+// Every rank owns one IPC-exported allocation:
+//   u64 flags[64] | u64 acks[64] | u64 counter | u64 done | int error | ... | data @ KB_HALO_DATA
+// Product number q (device-resident counter, gating-safe):
+//   push kernel   : waits until every destination acknowledged q-1, gathers the boundary
+//                   rows of x straight into the destinations' data areas, fences, sets
+//                   flags[my rank] = q there.
+//   boundary kernel: waits for flags[src] >= q of its sources, reads its own data area,
+//                   and when all its blocks are done sets acks[my rank] = q at the sources.
+#define KB_HALO_DATA 2048
+struct KbHalo {
+  unsigned char* const* peers;  // device array [size]: allocation base of every rank
+  int rank, size;
+};
+
+struct kb_halo_s {
+  KbHalo dev;
+  unsigned char* base;          // own allocation
+  unsigned char** peers_dev;
+  void* peer_base[64];
+  size_t data_bytes;
+  int opened;
+};
+
+__device__ __forceinline__ volatile unsigned long long* kb_halo_u64(unsigned char* base,
+                                                                    size_t byte_off) {
+  return reinterpret_cast<volatile unsigned long long*>(base + byte_off);
+}
+#define KB_HALO_FLAGS 0
+#define KB_HALO_ACKS 512
+#define KB_HALO_COUNTER 1024
+#define KB_HALO_DONE 1032
+#define KB_HALO_ERROR 1040
+
+// spin until *p >= want (3 s budget, then raise the error flag and go on)
+__device__ __forceinline__ void kb_halo_wait(volatile unsigned long long* p,
+                                             unsigned long long want, unsigned char* own) {
+  const long long t0 = clock64();
+  while (*p < want) {
+    if (clock64() - t0 > 6000000000ll) {
+      *reinterpret_cast<volatile int*>(own + KB_HALO_ERROR) = 1;
+      break;
+    }
+  }
+}
+
 // ------------------------------------------------------------- workspace --
 struct kb_ws_s {
   double* partials;      // KB_MAX_BLOCKS * max_k doubles

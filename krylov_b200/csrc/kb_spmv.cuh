@@ -877,11 +877,25 @@ template <int DOT>
 __global__ void __launch_bounds__(KB_BLOCK)
 kb_spmv_halo_add_kernel(int64_t n_brows, int k, double sign, const int32_t* __restrict__ rows,
                         const int32_t* __restrict__ hrowptr, const int32_t* __restrict__ hcol,
-                        const double* __restrict__ hval, const double* __restrict__ xh,
+                        const double* __restrict__ hval, const double* xh,
                         double* __restrict__ y, const double* __restrict__ w,
-                        double* __restrict__ out, KbRed rd) {
+                        double* __restrict__ out, KbHalo hd, const int* __restrict__ srcs,
+                        int n_src, KbRed rd) {
   if (kb_gated(rd)) return;
   __shared__ double sm[KB_BLOCK];
+  unsigned char* own = nullptr;
+  unsigned long long q = 0;
+  if (hd.peers != nullptr) {
+    // peer-memory halo: the entries were pushed into this rank's data area; wait for the
+    // flag of every source of product q (the push of this product already counted it)
+    own = hd.peers[hd.rank];
+    q = *kb_halo_u64(own, KB_HALO_COUNTER);
+    if ((int)threadIdx.x < n_src)
+      kb_halo_wait(kb_halo_u64(own, KB_HALO_FLAGS + 8 * (size_t)srcs[threadIdx.x]), q, own);
+    __syncthreads();
+    __threadfence_system();
+    xh = reinterpret_cast<const double*>(own + KB_HALO_DATA);
+  }
   const int c = threadIdx.x % k;
   const int rows_per_block = blockDim.x / k;
   const int rsub = threadIdx.x / k;
@@ -891,11 +905,26 @@ kb_spmv_halo_add_kernel(int64_t n_brows, int k, double sign, const int32_t* __re
     const int lo = hrowptr[i], hi = hrowptr[i + 1];
     double h = 0.0;
     for (int j = lo; j < hi; ++j)
-      h = __dadd_rn(h, __dmul_rn(hval[j], xh[(size_t)hcol[j] * k + c]));
+      h = __dadd_rn(h, __dmul_rn(hval[j], __ldcv(xh + (size_t)hcol[j] * k + c)));
     h *= sign;
     const size_t idx = (size_t)rows[i] * k + c;
     y[idx] = __dadd_rn(y[idx], h);
     if (DOT == 1) acc = fma(w[idx], h, acc);
+  }
+  if (hd.peers != nullptr) {
+    // all blocks done reading -> acknowledge product q to the sources (flow control)
+    __shared__ int s_done;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long* done =
+          reinterpret_cast<unsigned long long*>(own + KB_HALO_DONE);
+      const unsigned long long prev = atomicAdd(done, 1ull);
+      s_done = (prev == (unsigned long long)gridDim.x - 1ull) ? 1 : 0;
+      if (s_done) *done = 0ull;
+    }
+    __syncthreads();
+    if (s_done && (int)threadIdx.x < n_src)
+      *kb_halo_u64(hd.peers[srcs[threadIdx.x]], KB_HALO_ACKS + 8 * (size_t)hd.rank) = q;
   }
   if (DOT != 0) kb_grid_colsum(acc, k, rd, out, sm, /*accumulate=*/true);
 }

@@ -426,3 +426,47 @@ __global__ void kb_allreduce_kernel(int k, double* slot, KbRed rd) {
   }
   if (t < k) slot[t] = v;
 }
+
+// ---------------------------------------------------------- halo push -------
+// segs: n_seg x 4 int64 (device): destination rank, first entry in idx, entries, first row
+// in the destination's data area.  One launch per product on every rank (also with
+// n_seg == 0, so that the product counters stay equal on all ranks).
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_halo_push_kernel(int k, int n_seg, const int64_t* __restrict__ segs, int64_t n_total,
+                    const int32_t* __restrict__ idx, const double* __restrict__ x, KbHalo hd,
+                    KbRed rd) {
+  if (kb_gated(rd)) return;
+  unsigned char* own = hd.peers[hd.rank];
+  const unsigned long long q = *kb_halo_u64(own, KB_HALO_COUNTER) + 1ull;
+  // flow control: destinations must have consumed product q-1 before their buffer is reused
+  if ((int)threadIdx.x < n_seg)
+    kb_halo_wait(kb_halo_u64(own, KB_HALO_ACKS + 8 * (size_t)segs[4 * threadIdx.x]), q - 1ull, own);
+  __syncthreads();
+  const int64_t total = n_total * k;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t i = e / k;
+    const int c = (int)(e - i * k);
+    int s = 0;
+    while (s + 1 < n_seg && i >= segs[4 * (s + 1) + 1]) ++s;
+    double* dst = reinterpret_cast<double*>(hd.peers[segs[4 * s]] + KB_HALO_DATA);
+    dst[(size_t)(segs[4 * s + 3] + (i - segs[4 * s + 1])) * k + c] = x[(size_t)idx[i] * k + c];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(rd.ticket, 1u);
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < n_seg)
+      *kb_halo_u64(hd.peers[segs[4 * threadIdx.x]], KB_HALO_FLAGS + 8 * (size_t)hd.rank) = q;
+    if (threadIdx.x == 0) {
+      *kb_halo_u64(own, KB_HALO_COUNTER) = q;
+      *rd.ticket = 0u;
+    }
+  }
+}

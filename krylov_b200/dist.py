@@ -157,6 +157,19 @@ class HaloPlan:
         self.n_send = int(cat.size)
         self.peers = [p for p in range(comm.size)
                       if p != rank and (self.send_counts[p] or self.recv_counts[p])]
+        # ---- peer-memory push tables: where my rows land in each destination's data area
+        all_recv = comm.allgather_object(self.recv_counts.tolist())  # all_recv[p][q]: p gets from q
+        segs = []
+        so = np.concatenate([[0], np.cumsum(self.send_counts)])
+        for p in range(comm.size):
+            if self.send_counts[p]:
+                dst_row = int(np.sum(all_recv[p][:rank]))  # p's buffer is grouped by source rank
+                segs.append([p, int(so[p]), int(self.send_counts[p]), dst_row])
+        self.n_seg = len(segs)
+        self.segs = torch.tensor(segs if segs else [[0, 0, 0, 0]], dtype=torch.int64, device=dev)
+        srcs = [p for p in range(comm.size) if self.recv_counts[p]]
+        self.n_src = len(srcs)
+        self.srcs = torch.tensor(srcs if srcs else [0], dtype=torch.int32, device=dev)
 
     def exchange(self, send_buf, recv_buf):
         """Post the grouped P2P transfers of one product; returns the works.
@@ -204,7 +217,11 @@ class DistCsrMatrix:
         plan.loc_rowptr = plan.loc_colidx = plan.loc_vals = None
         self._bufs = {}
         self._ops = {}
+        self._halos = {}
         self.halo_bytes_per_product = 8 * (plan.n_send + plan.n_halo)
+        # peer-memory halo exchange goes with the peer-memory all-reduce (same requirement:
+        # one NVLink node, CUDA IPC); otherwise grouped NCCL send/recv
+        self.halo_mode = "p2p" if self.comm.p2p_handle is not None else "nccl"
 
     def spmv_bytes(self, k=1):
         n = self.shape[0]
@@ -223,6 +240,40 @@ class DistCsrMatrix:
         self.A_loc.set_schedule(name)
         return self
 
+    def _halo_for(self, k):
+        """Receive area for k right-hand sides (collective on first use: IPC handles of
+        all ranks are exchanged and mapped)."""
+        import ctypes as C
+
+        from ._lib import check, lib
+
+        h = self._halos.get(k)
+        if h is None:
+            h = C.c_void_p()
+            with torch.cuda.device(self.device):
+                check(lib.kb_halo_create(C.byref(h), self.comm.rank, self.comm.size,
+                                         max(self.plan.n_halo, 1) * k * 8))
+                buf = C.create_string_buffer(64)
+                check(lib.kb_halo_get_handle(h, buf))
+                handles = self.comm.allgather_object(bytes(buf.raw))
+                allh = C.create_string_buffer(b"".join(handles), 64 * self.comm.size)
+                check(lib.kb_halo_open(h, allh))
+            dist.barrier(group=self.comm.group)
+            self._halos[k] = h
+        return h
+
+    def check_p2p(self):
+        import ctypes as C
+
+        from ._lib import KrylovB200Error, check, lib
+
+        self.comm.check_p2p()
+        for h in self._halos.values():
+            e = C.c_int(0)
+            check(lib.kb_halo_error(h, C.byref(e)))
+            if e.value:
+                raise KrylovB200Error("peer-memory halo exchange timed out waiting for a rank")
+
     def _buffers(self, k):
         b = self._bufs.get(k)
         if b is None:
@@ -238,18 +289,25 @@ class DistCsrMatrix:
 
         p = self.plan
         k = ops.k
-        send_buf, recv_buf = self._buffers(k)
+        ldot = dot if dot == 1 else 0  # <y, y> cannot be split into local + halo shares
+        fused = ops.fused_allreduce   # reductions end with the peer-memory all-reduce
+        halo = self._halo_for(k) if self.halo_mode == "p2p" else None
         works = []
-        if p.n_send or p.n_halo:
-            if p.n_send:
-                ops.launches += 1
-                check(lib.kb_pack_rows(ops.ws.handle, k, p.n_send, ptr(p.send_idx), ptr(x),
-                                       ptr(send_buf), cur_stream()))
-            works = p.exchange(send_buf[: p.n_send], recv_buf[: p.n_halo])
-        # local rows/columns while the halo is in flight; <y,y> cannot be split
-        # into a local and a halo share, so dot 2 is taken after the halo part
-        ldot = dot if dot == 1 else 0
-        fused = ops.fused_allreduce  # reductions end with the peer-memory all-reduce
+        if halo is not None:
+            # boundary rows of x go straight into the neighbours' receive areas (NVLink
+            # stores + flag), before the local product is launched: no NCCL kernel at all
+            ops.launches += 1
+            check(lib.kb_halo_push(halo, ops.ws.handle, k, p.n_seg, ptr(p.segs), p.n_send,
+                                   ptr(p.send_idx), ptr(x), cur_stream()))
+            recv_buf = None
+        else:
+            send_buf, recv_buf = self._buffers(k)
+            if p.n_send or p.n_halo:
+                if p.n_send:
+                    ops.launches += 1
+                    check(lib.kb_pack_rows(ops.ws.handle, k, p.n_send, ptr(p.send_idx), ptr(x),
+                                           ptr(send_buf), cur_stream()))
+                works = p.exchange(send_buf[: p.n_send], recv_buf[: p.n_halo])
         if fused:
             ops.set_collective(False)  # the local part of <w, y> must not be exchanged yet
         ops.launches += 1
@@ -264,6 +322,7 @@ class DistCsrMatrix:
             check(lib.kb_spmv_halo_add(ops.ws.handle, k, p.n_brows, -1.0 if mode == 2 else 1.0,
                                        ptr(p.h_rows), ptr(p.h_rowptr), ptr(p.h_col), ptr(p.h_val),
                                        ptr(recv_buf), ptr(y), ldot, ptr(w), ptr(out),
+                                       halo, ptr(p.srcs), p.n_src if halo is not None else 0,
                                        cur_stream()))
         elif fused and ldot:
             ops.launches += 1  # no boundary rows here, but the peers' collective needs this rank

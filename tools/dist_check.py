@@ -76,6 +76,7 @@ for name, coeffs, shift, fn in cases:
         "spmv_rel": float(torch.linalg.norm(yd - yf) / torch.linalg.norm(yf)),
         "success": [bool(info_d.success), bool(info_f.success)],
     }
+    Ad.check_p2p()
     del Ad, Afull
 comm.check_p2p()
 if rank == 0:
