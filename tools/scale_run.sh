@@ -25,3 +25,16 @@ except Exception as e:
     print("N=", N, "failed:", e)
 PY
 done
+# N=8: peer-memory (push + fused all-reduce) vs NCCL (send/recv + ncclAllReduce) for the same kernels
+for mode in nccl p2p; do
+  KRYLOV_B200_ALLREDUCE=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29560 bench.py --gpus 8 --steps 300 --warmup 10 --no-e2e > gpurun_out/n8_$mode.json 2> gpurun_out/n8_$mode.err
+  python - "$mode" <<'PY'
+import json, sys
+m = sys.argv[1]
+try:
+    d = json.loads(open(f"gpurun_out/n8_{m}.json").read().strip().splitlines()[-1])
+    print(f"N=8 {m}: {d['value']:.1f} it/s, ms/step {d['ms_per_step']:.4f}, spmv phase ms {d['roofline']['launch_ms']:.4f}, halo {d['config']['halo']}, allreduce {d['config']['allreduce']}")
+except Exception as e:
+    print("N=8", m, "failed:", e)
+PY
+done
