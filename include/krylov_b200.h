@@ -148,6 +148,13 @@ int kb_dot(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, doubl
 int kb_cg_update_xr(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
                     const double* pAp2, const double* p, const double* Ap, double* x,
                     double* r, double* rr_out, double* alpha_out, void* stream);
+/* kb_cg_update_xr + the record step (what & 2 below) in the reduction's finishing block:
+ * valid where that block holds the final <r, r> (single GPU, or a workspace whose
+ * reductions are all-reduced through peer memory) -- one launch less per iteration. */
+int kb_cg_update_xr_record(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
+                           const double* p, const double* Ap, double* x, double* r, double* rr_out,
+                           double* alpha_out, int step, const double* crit, double* hist,
+                           int* stop_at, double* rho_keep, void* stream);
 /* what & 2: record resnorm[step] = sqrt(rho_new) into hist[step*k + c], copy rho_new to
  *           rho_keep (state slot, nullable); if all columns satisfy resnorm <= crit[c]
  *           set *stop_at = step (cg.py:156,214-217)
@@ -161,7 +168,7 @@ int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new
 
 /* Whole-loop entry point (SURVEY.md 8b "kb_cg_solve"): enqueues CG iterations
  * i0 .. i0+n_iters-1 of the fused path on one GPU -- per iteration kb_cg_update_p
- * (i > 0), kb_spmv fused with <p, Ap>, kb_cg_update_xr fused with <r, r>, record --
+ * (i > 0), kb_spmv fused with <p, Ap>, kb_cg_update_xr_record (r update, <r, r>, record) --
  * each gated on *stop_at <= i, with no host involvement between iterations.
  * slots: 6*k doubles = rho ping-pong (rho_i in slot i % 2), alpha, <p,Ap>, <r,r>, scratch.
  * hist row 0 receives step i0+1.  x_pending: the x update of iteration i0-1 is still

@@ -86,6 +86,7 @@ SIGNATURES = {
     "kb_pack_rows": [vp, i32, i64, vp, vp, vp, vp],
     "kb_dot": [vp, i64, i32, vp, vp, vp, vp],
     "kb_cg_update_xr": [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "kb_cg_update_xr_record": [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "kb_cg_update_p": [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "kb_cg_run": [vp, C.POINTER(CgState), i32, i32, i32, vp],
     "kb_axpy": [vp, i64, i32, f64, vp, vp, vp, vp],

@@ -176,10 +176,14 @@ class FusedCG:
         if self.spmv_events is not None:
             e1.record()
             self.spmv_events.append((e0, e1))
-        # alpha -> sl[2]; r -= alpha Ap; <r, r> -> sl[4]
-        ops.cg_update_xr(cur, sl[3], None, None, self.Ap, None, self.r, sl[4], alpha_out=sl[2])
+        # alpha -> sl[2]; r -= alpha Ap; <r, r> -> sl[4]; record step i+1, rho_{i+1} -> nxt
+        if self.comm is None or ops.fused_allreduce:
+            ops.cg_update_r_record(cur, sl[3], self.Ap, self.r, sl[4], sl[2], i + 1, self.crit_d,
+                                   hist_ptr, self.stop_at, nxt)
+        else:  # NCCL all-reduce lands after the kernel: record in a launch of its own
+            ops.cg_update_xr(cur, sl[3], None, None, self.Ap, None, self.r, sl[4], alpha_out=sl[2])
+            ops.cg_record(i + 1, sl[4], self.crit_d, hist_ptr, self.stop_at, rho_keep=nxt)
         self.x_pending = True
-        ops.cg_record(i + 1, sl[4], self.crit_d, hist_ptr, self.stop_at, rho_keep=nxt)  # rho_{i+1}
 
     def run(self, nb):
         """Enqueue iterations kk .. kk+nb-1, then one host read.  Returns the
@@ -190,7 +194,7 @@ class FusedCG:
             # single GPU: the whole batch is enqueued by one C call (kb_cg_run)
             check(lib.kb_cg_run(self.ops.ws.handle, C.byref(self._cstate), kk, nb,
                                 1 if self.x_pending else 0, cur_stream()))
-            self.ops.launches += 4 * nb - (1 if kk == 0 else 0)
+            self.ops.launches += 3 * nb - (1 if kk == 0 else 0)
             self.x_pending = True
         else:
             hist_ptr = self.hist.data_ptr() - (kk + 1) * k * 8  # history row kk+1 == hist[0]

@@ -671,7 +671,10 @@ int kb_spmv_halo_add(kb_ws_t ws, int k, int64_t n_brows, double sign, const int3
   cudaStream_t st = S(stream);
   if (n_brows == 0) return KB_OK;  // nothing to add (the dot slot keeps the local part)
   const int block = kb_block_for(k);
-  const int grid = kb_grid_for(ws, n_brows * (int64_t)k, block, 1);
+  int grid = kb_grid_for(ws, n_brows * (int64_t)k, block, 1);
+  // a small kernel (a few MB): keep the number of blocks, and with it the serialized
+  // arrivals on the reduction ticket, low
+  if (grid > 2 * ws->num_sms) grid = 2 * ws->num_sms;
   KbRed rd = kb_red(ws);
   KbHalo hd;
   hd.peers = halo ? halo->dev.peers : nullptr;
@@ -764,8 +767,9 @@ int kb_halo_push(kb_halo_t h, kb_ws_t ws, int k, int n_seg, const int64_t* segs,
   KB_REQUIRE(h->opened, "halo not opened");
   KB_REQUIRE(k >= 1 && n_seg >= 0 && n_seg <= KB_BLOCK / 2 && n_total >= 0, "bad sizes");
   KB_REQUIRE(n_seg == 0 || (segs && idx && x), "null argument");
-  int grid = kb_grid_for(ws, n_total * (int64_t)k, KB_BLOCK, 1);
-  if (grid > 64) grid = 64;  // a few MB at most: keep it small so it starts at once
+  // two elements per thread: the gather -> remote store chains are latency bound
+  int grid = kb_grid_for(ws, n_total * (int64_t)k, KB_BLOCK, 2);
+  if (grid > 2 * ws->num_sms) grid = 2 * ws->num_sms;
   kb_halo_push_kernel<<<grid, KB_BLOCK, 0, S(stream)>>>(k, n_seg, segs, n_total, idx, x, h->dev,
                                                         kb_red(ws));
   KB_LAUNCH_CHECK();
@@ -804,21 +808,40 @@ int kb_dot(kb_ws_t ws, int64_t n, int k, const double* x, const double* y, doubl
   return KB_OK;
 }
 
-int kb_cg_update_xr(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
-                    const double* pAp2, const double* p, const double* Ap, double* x, double* r,
-                    double* rr_out, double* alpha_out, void* stream) {
+static int kb_cg_update_xr_impl(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
+                                const double* pAp2, const double* p, const double* Ap, double* x,
+                                double* r, double* rr_out, double* alpha_out, KbCgRecord rec,
+                                void* stream) {
   KB_VEC_PROLOGUE();
   KB_REQUIRE(rho && pAp && Ap && r && rr_out, "null argument");
   KB_REQUIRE((x == nullptr) || (p != nullptr), "x update needs p");
+  KB_REQUIRE(rec.step < 0 || (rec.crit && rec.hist && rec.stop_at), "record needs crit, hist, stop_at");
   const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
   if (x != nullptr)
     kb_cg_update_xr_kernel<true><<<grid, block, 0, st>>>(total, k, rho, pAp, pAp2, p, Ap, x, r,
-                                                         rr_out, alpha_out, rd);
+                                                         rr_out, alpha_out, rec, rd);
   else
     kb_cg_update_xr_kernel<false><<<grid, block, 0, st>>>(total, k, rho, pAp, pAp2, p, Ap, x, r,
-                                                          rr_out, alpha_out, rd);
+                                                          rr_out, alpha_out, rec, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
+}
+
+int kb_cg_update_xr(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
+                    const double* pAp2, const double* p, const double* Ap, double* x, double* r,
+                    double* rr_out, double* alpha_out, void* stream) {
+  KbCgRecord rec = {-1, nullptr, nullptr, nullptr, nullptr};
+  return kb_cg_update_xr_impl(ws, n, k, rho, pAp, pAp2, p, Ap, x, r, rr_out, alpha_out, rec, stream);
+}
+
+int kb_cg_update_xr_record(kb_ws_t ws, int64_t n, int k, const double* rho, const double* pAp,
+                           const double* p, const double* Ap, double* x, double* r, double* rr_out,
+                           double* alpha_out, int step, const double* crit, double* hist,
+                           int* stop_at, double* rho_keep, void* stream) {
+  KB_REQUIRE(step >= 0, "negative step");
+  KbCgRecord rec = {step, crit, hist, stop_at, rho_keep};
+  return kb_cg_update_xr_impl(ws, n, k, rho, pAp, nullptr, p, Ap, x, r, rr_out, alpha_out, rec,
+                              stream);
 }
 
 int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new,
@@ -861,14 +884,11 @@ int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pendi
                           s->p, x_pending ? s->x : nullptr, x_pending ? 5 : 1, stream);
     if (rc == KB_OK)
       rc = kb_spmv(s->A, ws, k, s->p, s->Ap, 0, nullptr, nullptr, 1, s->p, pAp, stream);
-    if (rc == KB_OK)
-      rc = kb_cg_update_xr(ws, s->n, k, cur, pAp, nullptr, nullptr, s->Ap, nullptr, s->r, rr, alpha,
-                           stream);
+    if (rc == KB_OK)  // r update + <r,r> + record: hist row (i - i0) <- step i+1, rho_{i+1} -> nxt
+      rc = kb_cg_update_xr_record(ws, s->n, k, cur, pAp, nullptr, s->Ap, nullptr, s->r, rr, alpha,
+                                  i + 1, s->crit, s->hist - (size_t)(i0 + 1) * k, s->stop_at, nxt,
+                                  stream);
     x_pending = 1;
-    if (rc == KB_OK)  // hist row (i - i0) <- step i+1
-      rc = kb_cg_update_p(ws, s->n, k, i + 1, rr, nullptr, nullptr, s->crit,
-                          s->hist - (size_t)(i0 + 1) * k, s->stop_at, nxt, nullptr, nullptr, nullptr, 2,
-                          stream);
   }
   ws->gate = saved_gate;
   ws->gate_tag = saved_tag;

@@ -75,8 +75,9 @@ struct kb_comm_s {
 //   push kernel   : waits until every destination acknowledged q-1, gathers the boundary
 //                   rows of x straight into the destinations' data areas, fences, sets
 //                   flags[my rank] = q there.
-//   boundary kernel: waits for flags[src] >= q of its sources, reads its own data area,
-//                   and when all its blocks are done sets acks[my rank] = q at the sources.
+//   boundary kernel: waits for flags[src] >= q of its sources (q from its own consumed-
+//                   products counter: the push may run on a side stream), reads its own data
+//                   area, and when all its blocks are done sets acks[my rank] = q at the sources.
 #define KB_HALO_DATA 2048
 struct KbHalo {
   unsigned char* const* peers;  // device array [size]: allocation base of every rank
@@ -101,6 +102,9 @@ __device__ __forceinline__ volatile unsigned long long* kb_halo_u64(unsigned cha
 #define KB_HALO_COUNTER 1024
 #define KB_HALO_DONE 1032
 #define KB_HALO_ERROR 1040
+#define KB_HALO_RECV_COUNTER 1056  // u64: products whose halo this rank has consumed
+#define KB_HALO_PUSH_TICKET 1048  // u32 arrival counter of the push kernel (it may run on a side
+                                  // stream next to a reduction that uses the workspace ticket)
 
 // spin until *p >= want (3 s budget, then raise the error flag and go on)
 __device__ __forceinline__ void kb_halo_wait(volatile unsigned long long* p,
@@ -265,7 +269,9 @@ __device__ __forceinline__ double kb_p2p_allreduce(double v, int k, const KbComm
 // publishes its partial, the last block to arrive (ticket) adds the partials
 // in block order and writes out[0..k).  `acc` follows the kb_block_colsum
 // precondition.  All threads of all blocks must call this.
-__device__ __forceinline__ void kb_grid_colsum(double acc, int k, const KbRed& rd, double* out,
+// Returns true (block-uniform) in the block that finished the reduction, i.e. after every
+// block of the grid has arrived.
+__device__ __forceinline__ bool kb_grid_colsum(double acc, int k, const KbRed& rd, double* out,
                                                double* sm, bool accumulate = false) {
   __shared__ int s_last;
   const int t = threadIdx.x;
@@ -313,4 +319,5 @@ __device__ __forceinline__ void kb_grid_colsum(double acc, int k, const KbRed& r
     if (t < k) out[t] = fin;
     if (t == 0) *rd.ticket = 0u;  // ready for the next launch on this stream
   }
+  return s_last != 0;
 }

@@ -889,7 +889,7 @@ kb_spmv_halo_add_kernel(int64_t n_brows, int k, double sign, const int32_t* __re
     // peer-memory halo: the entries were pushed into this rank's data area; wait for the
     // flag of every source of product q (the push of this product already counted it)
     own = hd.peers[hd.rank];
-    q = *kb_halo_u64(own, KB_HALO_COUNTER);
+    q = *kb_halo_u64(own, KB_HALO_RECV_COUNTER) + 1ull;  // bumped by the last block below
     if ((int)threadIdx.x < n_src)
       kb_halo_wait(kb_halo_u64(own, KB_HALO_FLAGS + 8 * (size_t)srcs[threadIdx.x]), q, own);
     __syncthreads();
@@ -911,22 +911,31 @@ kb_spmv_halo_add_kernel(int64_t n_brows, int k, double sign, const int32_t* __re
     y[idx] = __dadd_rn(y[idx], h);
     if (DOT == 1) acc = fma(w[idx], h, acc);
   }
-  if (hd.peers != nullptr) {
-    // all blocks done reading -> acknowledge product q to the sources (flow control)
+  // all blocks done reading -> acknowledge product q to the sources (flow control).  With a
+  // fused dot the reduction's own arrival ticket already identifies the last block.
+  if (DOT != 0) {
+    const bool last = kb_grid_colsum(acc, k, rd, out, sm, /*accumulate=*/true);
+    if (hd.peers != nullptr && last) {
+      if ((int)threadIdx.x < n_src)
+        *kb_halo_u64(hd.peers[srcs[threadIdx.x]], KB_HALO_ACKS + 8 * (size_t)hd.rank) = q;
+      if (threadIdx.x == 0) *kb_halo_u64(own, KB_HALO_RECV_COUNTER) = q;
+    }
+  } else if (hd.peers != nullptr) {
     __shared__ int s_done;
     __syncthreads();
     if (threadIdx.x == 0) {
-      unsigned long long* done =
-          reinterpret_cast<unsigned long long*>(own + KB_HALO_DONE);
+      unsigned long long* done = reinterpret_cast<unsigned long long*>(own + KB_HALO_DONE);
       const unsigned long long prev = atomicAdd(done, 1ull);
       s_done = (prev == (unsigned long long)gridDim.x - 1ull) ? 1 : 0;
       if (s_done) *done = 0ull;
     }
     __syncthreads();
-    if (s_done && (int)threadIdx.x < n_src)
-      *kb_halo_u64(hd.peers[srcs[threadIdx.x]], KB_HALO_ACKS + 8 * (size_t)hd.rank) = q;
+    if (s_done) {
+      if ((int)threadIdx.x < n_src)
+        *kb_halo_u64(hd.peers[srcs[threadIdx.x]], KB_HALO_ACKS + 8 * (size_t)hd.rank) = q;
+      if (threadIdx.x == 0) *kb_halo_u64(own, KB_HALO_RECV_COUNTER) = q;
+    }
   }
-  if (DOT != 0) kb_grid_colsum(acc, k, rd, out, sm, /*accumulate=*/true);
 }
 
 // ----------------------------------------------------------- row statistics --

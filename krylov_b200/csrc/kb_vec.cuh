@@ -61,13 +61,23 @@ kb_dot_kernel(int64_t total, int k, const double* __restrict__ x, const double* 
 // 48 B/element (reads x p r Ap, writes x r); 24 B/element with UPDX == false,
 // when the x update is deferred into the next p update (kb_cg_update_p_kernel,
 // what & 4), which streams p anyway.     cg.py:185,196,200,209
+// Optional fused record (single GPU / peer-memory all-reduce, where the last block holds
+// the final <r,r>): what kb_cg_update_p does with `what & 2`, without a launch of its own.
+struct KbCgRecord {
+  int step;               // < 0: no record
+  const double* crit;
+  double* hist;
+  int* stop_at;
+  double* rho_keep;
+};
+
 template <bool UPDX>
 __global__ void __launch_bounds__(KB_BLOCK, 4)
 kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
                        const double* __restrict__ pAp, const double* __restrict__ pAp2,
                        const double* __restrict__ p, const double* __restrict__ Ap,
                        double* __restrict__ x, double* __restrict__ r, double* __restrict__ out,
-                       double* __restrict__ alpha_out, KbRed rd) {
+                       double* __restrict__ alpha_out, KbCgRecord rec, KbRed rd) {
   if (kb_gated(rd)) return;
   __shared__ double sm[KB_BLOCK];
   const int c = threadIdx.x % k;
@@ -111,7 +121,20 @@ kb_cg_update_xr_kernel(int64_t total, int k, const double* __restrict__ rho,
     }
   }
   KB_TILE_LOOP_END
-  kb_grid_colsum(acc, k, rd, out, sm);
+  const bool last = kb_grid_colsum(acc, k, rd, out, sm);
+  if (last && rec.step >= 0) {  // cg.py:156,214-217 in the reduction's finishing block
+    int ok = 1;
+    __syncthreads();  // out[] written by threads t < k of this block
+    if (threadIdx.x < k) {
+      const double rn = out[threadIdx.x];
+      if (rec.rho_keep != nullptr) rec.rho_keep[threadIdx.x] = rn;
+      const double nrm = sqrt(rn);
+      rec.hist[(size_t)rec.step * k + threadIdx.x] = nrm;
+      ok = (nrm <= rec.crit[threadIdx.x]) ? 1 : 0;
+    }
+    const int all_ok = __syncthreads_and(ok);
+    if (all_ok && threadIdx.x == 0) *rec.stop_at = rec.step;
+  }
 }
 
 // ------------------------------------------------------------- CG: p -----
@@ -455,8 +478,9 @@ kb_halo_push_kernel(int k, int n_seg, const int64_t* __restrict__ segs, int64_t 
   __threadfence_system();
   __syncthreads();
   __shared__ int s_last;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(own + KB_HALO_PUSH_TICKET);
   if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(rd.ticket, 1u);
+    const unsigned int prev = atomicAdd(ticket, 1u);
     s_last = (prev == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
@@ -466,7 +490,7 @@ kb_halo_push_kernel(int k, int n_seg, const int64_t* __restrict__ segs, int64_t 
       *kb_halo_u64(hd.peers[segs[4 * threadIdx.x]], KB_HALO_FLAGS + 8 * (size_t)hd.rank) = q;
     if (threadIdx.x == 0) {
       *kb_halo_u64(own, KB_HALO_COUNTER) = q;
-      *rd.ticket = 0u;
+      *ticket = 0u;
     }
   }
 }

@@ -149,6 +149,17 @@ class Ops:
                                   cur_stream()))
         self.reduce_over_ranks(rr_out)
 
+    def cg_update_r_record(self, rho, pAp, Ap, r, rr_out, alpha_out, step, crit, hist_ptr, stop_at,
+                           rho_keep):
+        """r -= alpha Ap; <r,r> (+ fused all-reduce); record/convergence in the same launch.
+        Only where the reducing kernel holds the final sum (no NCCL all-reduce after it)."""
+        assert self.comm is None or self.fused_allreduce
+        self.launches += 1
+        check(lib.kb_cg_update_xr_record(self.ws.handle, self.n, self.k, ptr(rho), ptr(pAp), None,
+                                         ptr(Ap), None, ptr(r), ptr(rr_out), ptr(alpha_out),
+                                         int(step), ptr(crit), hist_ptr, ptr(stop_at), ptr(rho_keep),
+                                         cur_stream()))
+
     def cg_update_p(self, rho_new, rho_old, r, p, x=None, alpha=None):
         """[x += alpha p;]  p = r + (rho_new / nz(rho_old)) p"""
         self.launches += 1

@@ -222,6 +222,15 @@ class DistCsrMatrix:
         # peer-memory halo exchange goes with the peer-memory all-reduce (same requirement:
         # one NVLink node, CUDA IPC); otherwise grouped NCCL send/recv
         self.halo_mode = "p2p" if self.comm.p2p_handle is not None else "nccl"
+        # the push kernel runs on a high-priority side stream next to the local product
+        # (only the neighbours' boundary kernels wait for it, through device flags)
+        self._side = None
+        self._ev_ready = self._ev_pushed = None
+        if self.halo_mode == "p2p":
+            with torch.cuda.device(self.device):
+                self._side = torch.cuda.Stream(device=self.device, priority=-1)
+                self._ev_ready = torch.cuda.Event()
+                self._ev_pushed = torch.cuda.Event()
 
     def spmv_bytes(self, k=1):
         n = self.shape[0]
@@ -297,8 +306,12 @@ class DistCsrMatrix:
             # boundary rows of x go straight into the neighbours' receive areas (NVLink
             # stores + flag), before the local product is launched: no NCCL kernel at all
             ops.launches += 1
+            main = torch.cuda.current_stream()
+            self._ev_ready.record(main)          # x is complete on the compute stream
+            self._side.wait_event(self._ev_ready)
             check(lib.kb_halo_push(halo, ops.ws.handle, k, p.n_seg, ptr(p.segs), p.n_send,
-                                   ptr(p.send_idx), ptr(x), cur_stream()))
+                                   ptr(p.send_idx), ptr(x), self._side.cuda_stream))
+            self._ev_pushed.record(self._side)
             recv_buf = None
         else:
             send_buf, recv_buf = self._buffers(k)
@@ -327,6 +340,9 @@ class DistCsrMatrix:
         elif fused and ldot:
             ops.launches += 1  # no boundary rows here, but the peers' collective needs this rank
             check(lib.kb_allreduce(ops.ws.handle, k, ptr(out), cur_stream()))
+        if halo is not None:
+            # nobody may overwrite x before the push has read it (it finished long ago)
+            torch.cuda.current_stream().wait_event(self._ev_pushed)
         if dot == 2:
             ops.launches += 1
             check(lib.kb_dot(ops.ws.handle, ops.n, k, ptr(y), ptr(y), ptr(out), cur_stream()))
