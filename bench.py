@@ -451,8 +451,6 @@ def run_e2e(args, A, b, world, rank, dev, barrier):
                                          copy=False)
         A_host.has_canonical_format = True
         b_np = b_host.numpy()
-        del A
-        torch.cuda.empty_cache()
         barrier()
         t0 = time.perf_counter()
         sol, info = kb.cg(A_host, b_np, tol=1e-8, maxiter=20000)  # numpy in -> numpy out

@@ -18,10 +18,14 @@ _SCHEDULES = {"auto": 0, "rowwise": 1, "stream": 2, "pattern": 3}
 _PAD = 4  # elements readable past nnz (TMA tiles are 4-aligned windows)
 
 
-def _padded(t: torch.Tensor) -> torch.Tensor:
+def _padded_upload(src, dtype, device) -> torch.Tensor:
+    """Device copy of a 1-D array with >= 4 readable zero elements past the end, made
+    with ONE allocation and one copy (host data goes straight into the padded buffer)."""
+    t = torch.as_tensor(src)
     n = t.numel()
-    out = torch.zeros(((n + 3) // 4) * 4 + _PAD, dtype=t.dtype, device=t.device)
-    out[:n] = t
+    out = torch.empty(((n + 3) // 4) * 4 + _PAD, dtype=dtype, device=device)
+    out[n:].zero_()
+    out[:n].copy_(t.reshape(-1), non_blocking=True)  # converts dtype / crosses PCIe as needed
     return out
 
 
@@ -38,16 +42,15 @@ class CsrMatrix:
         self.device = dev
         self.shape = (int(shape[0]), int(shape[1]))
         rowptr = torch.as_tensor(rowptr).to(device=dev, dtype=torch.int32).contiguous()
-        colidx = torch.as_tensor(colidx).to(device=dev, dtype=torch.int32).contiguous()
-        vals = torch.as_tensor(vals).to(device=dev, dtype=torch.float64).contiguous()
         if rowptr.numel() != self.shape[0] + 1:
             raise ValueError("rowptr must have n_rows + 1 entries")
-        self.nnz = int(vals.numel())
-        if colidx.numel() != self.nnz:
+        self.nnz = int(torch.as_tensor(vals).numel())
+        if int(torch.as_tensor(colidx).numel()) != self.nnz:
             raise ValueError("colidx and vals differ in length")
         self.rowptr = rowptr
-        self.colidx = _padded(colidx)
-        self.vals = _padded(vals)
+        with torch.cuda.device(dev):
+            self.colidx = _padded_upload(colidx, torch.int32, dev)
+            self.vals = _padded_upload(vals, torch.float64, dev)
         self._finish()
 
     @classmethod
