@@ -62,20 +62,37 @@ class Comm:
             self._open_p2p()
         self.allreduce_mode = "p2p" if self.p2p_handle is not None else "nccl"
 
-    def _open_p2p(self, max_k=256):
-        import ctypes as C
+    def _all_ok(self, ok: bool) -> bool:
+        """Collective AND: peer-memory paths are only used if every rank could set them up."""
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(int(t.item()))
 
-        from ._lib import check, lib
+    def _open_p2p(self, max_k=256):
+        """Maps every rank's mailbox with CUDA IPC.  If any rank cannot (no IPC in this
+        container, GPUs on different nodes, ...) all ranks fall back to NCCL together."""
+        import ctypes as C
+        import warnings
+
+        from ._lib import lib
 
         h = C.c_void_p()
-        check(lib.kb_comm_create(C.byref(h), self.rank, self.size, max_k))
         buf = C.create_string_buffer(64)
-        check(lib.kb_comm_get_handle(h, buf))
-        handles = self.allgather_object(bytes(buf.raw))
-        allh = C.create_string_buffer(b"".join(handles), 64 * self.size)
-        check(lib.kb_comm_open(h, allh))
-        self.p2p_handle = h
-        dist.barrier(group=self.group)  # every mailbox is mapped before anyone writes
+        ok = lib.kb_comm_create(C.byref(h), self.rank, self.size, max_k) == 0
+        ok = ok and lib.kb_comm_get_handle(h, buf) == 0
+        handles = self.allgather_object(bytes(buf.raw) if ok else b"")
+        ok = ok and all(len(x) == 64 for x in handles)
+        if ok:
+            allh = C.create_string_buffer(b"".join(handles), 64 * self.size)
+            ok = lib.kb_comm_open(h, allh) == 0
+        if self._all_ok(ok):
+            self.p2p_handle = h  # every mailbox is mapped before anyone writes
+        else:
+            if h:
+                lib.kb_comm_destroy(h)
+            if self.rank == 0:
+                warnings.warn("krylov_b200: CUDA IPC peer mapping unavailable; using NCCL "
+                              "all-reduce and send/recv")
 
     def check_p2p(self):
         """Raise if a peer ever failed to arrive in a fused all-reduce."""
@@ -260,14 +277,20 @@ class DistCsrMatrix:
         if h is None:
             h = C.c_void_p()
             with torch.cuda.device(self.device):
-                check(lib.kb_halo_create(C.byref(h), self.comm.rank, self.comm.size,
-                                         max(self.plan.n_halo, 1) * k * 8))
                 buf = C.create_string_buffer(64)
-                check(lib.kb_halo_get_handle(h, buf))
-                handles = self.comm.allgather_object(bytes(buf.raw))
-                allh = C.create_string_buffer(b"".join(handles), 64 * self.comm.size)
-                check(lib.kb_halo_open(h, allh))
-            dist.barrier(group=self.comm.group)
+                ok = lib.kb_halo_create(C.byref(h), self.comm.rank, self.comm.size,
+                                        max(self.plan.n_halo, 1) * k * 8) == 0
+                ok = ok and lib.kb_halo_get_handle(h, buf) == 0
+                handles = self.comm.allgather_object(bytes(buf.raw) if ok else b"")
+                ok = ok and all(len(x) == 64 for x in handles)
+                if ok:
+                    allh = C.create_string_buffer(b"".join(handles), 64 * self.comm.size)
+                    ok = lib.kb_halo_open(h, allh) == 0
+            if not self.comm._all_ok(ok):  # collective decision: everybody or nobody
+                if h:
+                    lib.kb_halo_destroy(h)
+                self.halo_mode = "nccl"
+                return None
             self._halos[k] = h
         return h
 
@@ -300,7 +323,7 @@ class DistCsrMatrix:
         k = ops.k
         ldot = dot if dot == 1 else 0  # <y, y> cannot be split into local + halo shares
         fused = ops.fused_allreduce   # reductions end with the peer-memory all-reduce
-        halo = self._halo_for(k) if self.halo_mode == "p2p" else None
+        halo = self._halo_for(k) if self.halo_mode == "p2p" else None  # None: NCCL send/recv
         works = []
         if halo is not None:
             # boundary rows of x go straight into the neighbours' receive areas (NVLink
