@@ -45,6 +45,10 @@ static int g_pattern_ctas = 0; // kb_tune key 3 (0 = default)
 static int g_window_cfg = 0;   // kb_tune key 4
 static int g_rowwise_contig = -1;  // kb_tune key 5: -1 auto, 0 strided, 1 contiguous rows per block
 static int g_rowwise_ctas = 0;     // kb_tune key 6: CTAs/SM of the contiguous row-wise grid
+static int g_tile_block = 0;       // kb_tune key 8: 0 natural tile order (default: the blocked
+                                   // order cut DRAM traffic 11.80 -> 11.57 GB at 512^3 but ran
+                                   // 2.2 instead of 1.73 ms, profiles/r1_tile_order.txt),
+                                   // -1 auto-blocked for large planes, n > 0: blocks of <= n tiles
 static int g_spmm_cfg = -1;        // kb_tune key 7: -1 = row-wise kernel (default: measured equal
                                    // or faster, profiles/r1_configs.txt), 0 = windowed RPT 2, 1 = RPT 4
 int g_vec_ctas = KB_CTAS_PER_SM;
@@ -154,6 +158,7 @@ int kb_tune(int key, int value) {
     case 5: g_rowwise_contig = value; return KB_OK;
     case 6: g_rowwise_ctas = value; return KB_OK;
     case 7: g_spmm_cfg = value; return KB_OK;
+    case 8: g_tile_block = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -510,7 +515,26 @@ static int kb_launch_window_cfg(kb_csr_s* A, kb_ws_s* ws, const double* x, doubl
   int grid = ws->num_sms * ctas;
   if (grid > n_tiles) grid = n_tiles;
   if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
-  kern<<<grid, ROWS + 32, smem, st>>>((int)A->n_rows, (int)A->n_cols, n_tiles, cap, wlen, A->rowptr,
+  // cache-blocked visiting order (see KbTileOrder): only when a plane of matrix stream is
+  // too large for its x windows to survive in L2 until the next plane needs them
+  KbTileOrder ord = {0, 0, 0};
+  const int64_t plane = A->pat.off[A->pat.nd - 1];  // largest offset
+  const int64_t row_bytes = 8 * A->pat.nd + 14;
+  if (g_tile_block != 0 && plane > 0 && plane % ROWS == 0 && A->n_rows % plane == 0 &&
+      (g_tile_block > 0 || plane * row_bytes > (12ll << 20))) {
+    const int tpp = (int)(plane / ROWS);
+    int tpb = 0;
+    for (int d = 1; d <= tpp; ++d)
+      if (tpp % d == 0 && (g_tile_block > 0 ? d <= g_tile_block
+                                            : (int64_t)d * ROWS * row_bytes <= (5ll << 19)))
+        tpb = d;
+    if (tpb > 0 && tpb < tpp) {
+      ord.tpp = tpp;
+      ord.tpb = tpb;
+      ord.nplanes = n_tiles / tpp;
+    }
+  }
+  kern<<<grid, ROWS + 32, smem, st>>>((int)A->n_rows, (int)A->n_cols, n_tiles, cap, wlen, ord, A->rowptr,
                                       A->masks, A->vals, A->pat, x, y, mode, z, coef, w, out,
                                       kb_red(ws));
   KB_LAUNCH_CHECK();

@@ -81,6 +81,36 @@ def test_pattern_kernel_variants_bit_exact(cfg):
         lib.kb_tune(4, 0)
 
 
+@pytest.mark.parametrize("cfg", [0, 2, 3])
+@pytest.mark.parametrize("block", [1, 2, 3])
+def test_cache_blocked_tile_order_bit_exact(cfg, block):
+    """The optional cache-blocked visiting order of the windowed kernel (kb_tune 8; off by
+    default because it measured slower) is a permutation of the tiles: same bits."""
+    from krylov_b200._lib import lib
+
+    lib.kb_tune(4, cfg)
+    lib.kb_tune(8, block)
+    try:
+        for (nx, ny, nz) in ((32, 32, 5), (64, 16, 3), (32, 16, 7)):
+            A = st.to_scipy(st.stencil7_csr(nx, ny, nz, coeffs=st.convdiff_coeffs()))
+            Ad = kb.CsrMatrix.from_scipy(A)
+            assert Ad.info()["schedule"] == "pattern"
+            n = A.shape[0]
+            x, z = rng.standard_normal(n), rng.standard_normal(n)
+            np.testing.assert_array_equal(Ad @ x, A @ x)
+            ops = Ops(n, 1)
+            xd, zd = (torch.from_numpy(a).cuda().reshape(n, 1) for a in (x, z))
+            yd = torch.empty_like(xd)
+            out = ops.slots(1)[0]
+            ops.spmv(Ad, xd, yd, mode=2, z=zd, dot=2, out=out)
+            ref = z - A @ x
+            np.testing.assert_array_equal(yd.cpu().numpy().ravel(), ref)
+            np.testing.assert_allclose(out.cpu().numpy()[0], ref @ ref, rtol=1e-13)
+    finally:
+        lib.kb_tune(4, 0)
+        lib.kb_tune(8, 0)
+
+
 @pytest.mark.parametrize("cfg", [0, 1])
 @pytest.mark.parametrize("k", [2, 4, 16, 64])
 def test_windowed_spmm_variants_bit_exact(cfg, k):

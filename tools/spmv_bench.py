@@ -39,6 +39,11 @@ for wc, pcs in ((0, (0, 3)), (1, (0, 2)), (2, (0, 1)), (3, (0, 6, 5)), (4, (0, 4
         print(f"window cfg {wc} ctas {pc}: ", end="")
         run("pattern", 0, 0, vec_ctas=8)
 lib.kb_tune(3, 0); lib.kb_tune(4, 0)
+for tb in (0, -1, 16, 32, 64, 128, 256):
+    lib.kb_tune(8, tb)
+    print(f"tile block {tb}: ", end="")
+    run("pattern", 0, 0, vec_ctas=8)
+lib.kb_tune(8, 0)
 for vc in (4, 8):
     run("rowwise", 0, 0, vec_ctas=vc)
 for cfg, ctas_list in ((0, (2,)), (5, (8,))):
