@@ -6,14 +6,14 @@ with an explicit residual that overwrites ``resnorms[-1]``, cg.py:156-164),
 same zero-division guards, same ``callback(xk, Ml_rk)``.
 
 Two paths:
-  * fused (M = Ml = None, default inner product, A a matrix): three kernels per
-    iteration -- ``p`` update, SpMV fused with ``<p, Ap>``, x/r update fused with
-    ``<r, r>`` -- plus a one-block record/convergence kernel; all scalars stay in
-    HBM, iterations are enqueued in batches and gated on a device flag, so the
-    host reads back once per batch, not per iteration.
-  * general (preconditioners, custom ``inner``, duck-typed operators): the
-    reference loop statement by statement, every vector statement one kernel,
-    scalars on the host.
+  * fused (default inner product; A -- and M / Ml if given -- are matrices): three
+    kernels per iteration -- x/p update, SpMV fused with ``<p, Ap>``, r update fused
+    with ``<r, r>`` and the record/convergence step -- all scalars stay in HBM,
+    iterations are enqueued in batches and gated on a device flag, so the host reads
+    back once per batch, not per iteration.  A matrix preconditioner adds one sparse
+    product ``z = M r`` fused with ``rho = <r, z>`` (e.g. Jacobi: 30 B/row).
+  * general (custom ``inner``, duck-typed operators): the reference loop statement
+    by statement, every vector statement one kernel, scalars on the host.
 """
 from __future__ import annotations
 
@@ -38,8 +38,13 @@ def cg(A, b, M=None, Ml=None, inner=None, x0=None, tol=1e-5, atol=1.0e-15, maxit
     prob = Problem(A, b, x0)
     maxiter = prob.n if maxiter is None else int(maxiter)
     with torch.cuda.device(prob.device):
-        if M is None and Ml is None and inner is None and prob.A_csr is not None:
-            return _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback)
+        if inner is None and prob.A_csr is not None:
+            # device-resident path: A and the preconditioners (if any) are matrices
+            Mop, Mlop = prob.operator(M), prob.operator(Ml)
+            if all(op is None or op.csr is not None for op in (Mop, Mlop)):
+                return _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback,
+                                 None if Mop is None else Mop.csr,
+                                 None if Mlop is None else Mlop.csr)
         return _cg_general(prob, M, Ml, inner, tol, atol, maxiter, return_arnoldi, callback)
 
 
@@ -94,23 +99,31 @@ class _LanczosLog:
 
 # ---------------------------------------------------------------------------
 class FusedCG:
-    """Device-resident state of the fused CG iteration (M = Ml = I, default
-    inner product).  ``enqueue(i)`` launches iteration i (no host sync);
-    ``run(nb)`` enqueues a gated batch and reads back once.
+    """Device-resident state of the fused (P)CG iteration with the default inner
+    product.  ``enqueue(i)`` launches iteration i (no host sync); ``run(nb)``
+    enqueues a gated batch and reads back once.
 
     ``A`` is a CsrMatrix or a row-partitioned DistCsrMatrix; in the latter case
-    every reduction slot is summed over ranks by ``A.comm`` right after the
-    kernel that produced it (one small all-reduce per inner product)."""
+    every reduction is summed over ranks (inside the reducing kernel through peer
+    memory, or by one small NCCL all-reduce).  ``M`` / ``Ml`` are optional
+    preconditioner *matrices* (CsrMatrix, e.g. Jacobi): ``z = M r`` is a sparse
+    product fused with ``rho = <r, z>`` and ``Ml`` is chained behind ``A`` -- all
+    scalars stay on the device exactly as without preconditioner
+    (cg.py:86-95, 109, 180, 207-212)."""
 
-    def __init__(self, A, b, x0, tol, atol):
+    def __init__(self, A, b, x0, tol, atol, M=None, Ml=None):
         n, k = b.shape
         self.A, self.b, self.x0 = A, b, x0
+        self.M, self.Ml = M, Ml
         self.n, self.k, self.dev = n, k, b.device
         self.comm = getattr(A, "comm", None)
         self.ops = ops = Ops(n, k, self.dev, comm=self.comm)
         self.r = ops.vec(zero=False)
         self.Ap = ops.vec(zero=False)
         self.yk = ops.vec(zero=True)
+        self.z = ops.vec(zero=False) if M is not None else self.r   # M_Ml_rk (== Ml_rk if M = I)
+        self.t = ops.vec(zero=False) if Ml is not None else None      # A p before Ml is applied
+        self.zs = ops.vec(zero=False) if M is not None else None      # scratch z of explicit checks
         # State slots (written by gated kernels only): rho ping-pong (rho_i in sl[i % 2]),
         # sl[2] = alpha of the last iteration.  Landing slots of reductions (these may see
         # un-gated NCCL all-reduces after on-device convergence, so nothing persistent
@@ -121,14 +134,14 @@ class FusedCG:
         self.spmv_events = None  # bench hook: list of (start, end) CUDA events around A @ p
         # initial residual r0 = b - A x0 fused with <r0, r0>  (cg.py:116)
         ops.gate(None, 0)
-        self.rho0 = self._residual_norm2(x0, self.r, self.sl[0])
+        self.rho0 = self._residual_norm2(x0, self.r, self.z, self.sl[0])
         self.nrm0 = np.sqrt(self.rho0)
         self.crit = np.maximum(tol * self.nrm0, atol)  # cg.py:154
         self.crit_d = torch.from_numpy(np.ascontiguousarray(self.crit)).to(self.dev)
-        self.p = self.r.clone()
+        self.p = self.z.clone()
         self.kk = 0
         self._cstate = None
-        if self.comm is None and hasattr(A, "handle"):
+        if self.comm is None and hasattr(A, "handle") and M is None and Ml is None:
             self._cstate = CgState(A=A.handle, n=n, k=k, x=ptr(self.yk), r=ptr(self.r),
                                    p=ptr(self.p), Ap=ptr(self.Ap), slots=ptr(self.sl),
                                    crit=ptr(self.crit_d), hist=ptr(self.hist),
@@ -138,13 +151,22 @@ class FusedCG:
         # vector kernels of a step); current_x() flushes it
         self.x_pending = False
 
-    def _residual_norm2(self, x, out_vec, slot):
-        """out_vec = b - A x; returns host <out_vec, out_vec> (k,)."""
-        self.ops.spmv(self.A, x, out_vec, mode=2, z=self.b, dot=2, out=slot)
+    def _residual_norm2(self, x, out_r, out_z, slot):
+        """out_r = Ml (b - A x); out_z = M out_r; returns host <out_r, out_z> (k,)
+        (cg.py:72-95).  Without preconditioners one fused kernel."""
+        ops = self.ops
+        if self.Ml is None:
+            ops.spmv(self.A, x, out_r, mode=2, z=self.b, dot=0 if self.M is not None else 2,
+                     out=slot)
+        else:
+            ops.spmv(self.A, x, self.t, mode=2, z=self.b)
+            ops.spmv(self.Ml, self.t, out_r, dot=0 if self.M is not None else 2, out=slot)
+        if self.M is not None:
+            ops.spmv(self.M, out_r, out_z, dot=1, w=out_r, out=slot)
         return slot.cpu().numpy().copy()
 
     def explicit_resnorm(self, xk):
-        return np.sqrt(self._residual_norm2(xk, self.Ap, self.sl[5]))
+        return np.sqrt(self._residual_norm2(xk, self.Ap, self.zs, self.sl[5]))
 
     def flush_x(self):
         if self.x_pending:
@@ -163,21 +185,30 @@ class FusedCG:
         cur, nxt = sl[i % 2], sl[(i + 1) % 2]
         ops.gate(self.stop_at, i)  # iteration i is a no-op once a step <= i converged
         if i > 0:
-            # [x += alpha_{i-1} p;]  omega = rho_i / rho_{i-1};  p = r + omega p
+            # [x += alpha_{i-1} p;]  omega = rho_i / rho_{i-1};  p = z + omega p   (z = M r)
             if self.x_pending:
-                ops.cg_update_p(cur, nxt, self.r, self.p, x=self.yk, alpha=sl[2])
+                ops.cg_update_p(cur, nxt, self.z, self.p, x=self.yk, alpha=sl[2])
             else:
-                ops.cg_update_p(cur, nxt, self.r, self.p)
+                ops.cg_update_p(cur, nxt, self.z, self.p)
         if self.spmv_events is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        ops.spmv(self.A, self.p, self.Ap, dot=1, w=self.p, out=sl[3])  # Ap = A p, <p, Ap>
+        if self.Ml is None:
+            ops.spmv(self.A, self.p, self.Ap, dot=1, w=self.p, out=sl[3])  # Ap = A p, <p, Ap>
+        else:  # Product(Ml, A) @ p   (cg.py:109,180)
+            ops.spmv(self.A, self.p, self.t)
+            ops.spmv(self.Ml, self.t, self.Ap, dot=1, w=self.p, out=sl[3])
         if self.spmv_events is not None:
             e1.record()
             self.spmv_events.append((e0, e1))
         # alpha -> sl[2]; r -= alpha Ap; <r, r> -> sl[4]; record step i+1, rho_{i+1} -> nxt
-        if self.comm is None or ops.fused_allreduce:
+        if self.M is not None:
+            # r -= alpha Ap;  z = M r fused with rho_{i+1} = <r, z>  (cg.py:200-212);  record
+            ops.cg_update_xr(cur, sl[3], None, None, self.Ap, None, self.r, sl[5], alpha_out=sl[2])
+            ops.spmv(self.M, self.r, self.z, dot=1, w=self.r, out=sl[4])
+            ops.cg_record(i + 1, sl[4], self.crit_d, hist_ptr, self.stop_at, rho_keep=nxt)
+        elif self.comm is None or ops.fused_allreduce:
             ops.cg_update_r_record(cur, sl[3], self.Ap, self.r, sl[4], sl[2], i + 1, self.crit_d,
                                    hist_ptr, self.stop_at, nxt)
         else:  # NCCL all-reduce lands after the kernel: record in a launch of its own
@@ -208,13 +239,13 @@ class FusedCG:
         return [rows[j].copy() for j in range(done)]
 
 
-def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback):
-    st = FusedCG(prob.A_csr, prob.b, prob.x0, tol, atol)
+def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback, M=None, Ml=None):
+    st = FusedCG(prob.A_csr, prob.b, prob.x0, tol, atol, M=M, Ml=Ml)
     ops, crit = st.ops, st.crit
     if callback is not None:
         callback(prob.to_user(prob.x0), prob.to_user(st.r))
     resn = [st.nrm0]
-    log = _LanczosLog(prob, ops, maxiter, st.r, st.r, st.nrm0) if return_arnoldi else None
+    log = _LanczosLog(prob, ops, maxiter, st.z, st.r, st.nrm0) if return_arnoldi else None
 
     step_by_step = callback is not None or return_arnoldi
     batch = 1 if step_by_step else _BATCH_MIN
@@ -237,7 +268,7 @@ def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback):
             sv = st.sl.cpu().numpy()
             rho_i, rho_n, alpha = sv[kk % 2], sv[(kk + 1) % 2], sv[2]
             omega = rho_i / nz(log.rho_prev) if kk > 0 else None
-            log.step(kk, st.r, st.r, alpha, omega, rho_n, rho_i)
+            log.step(kk, st.z, st.r, alpha, omega, rho_n, rho_i)
             log.rho_prev = rho_i
         if callback is not None:
             xk = st.current_x()

@@ -101,3 +101,34 @@ def test_callback_can_override_resnorm():
     _, io = orc.minres(A, b, tol=1e-6, callback=cb)
     assert info.numsteps == io.numsteps and bool(info.success) == bool(io.success)
     np.testing.assert_allclose(np.asarray(info.resnorms), np.asarray(io.resnorms), rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_fused_preconditioned_cg_vs_oracle(k):
+    """Matrix preconditioners stay on the device-resident path (z = M r fused with
+    rho = <r, z>; Ml chained behind A): Jacobi M, sparse Ml, both, vs the oracle."""
+    n = 12
+    A = st.poisson3d(n).tolil()
+    d = 1.0 + rng.random(n ** 3) * 50.0           # badly scaled diagonal: Jacobi matters
+    for i in range(n ** 3):
+        A[i, i] = A[i, i] + d[i]
+    A = A.tocsr()
+    M = scipy.sparse.diags(1.0 / A.diagonal()).tocsr()
+    shape = (A.shape[0],) if k == 1 else (A.shape[0], k)
+    b = A @ rng.standard_normal(shape)
+    plain_steps = orc.cg(A, b, tol=1e-10)[1].numsteps
+    # commuting, symmetric Ml so that Ml A stays self-adjoint (reference test_ml uses diagonals)
+    Dl = scipy.sparse.identity(A.shape[0], format="csr") * 0.5
+    for kw in (dict(M=M), dict(Ml=Dl), dict(M=M, Ml=Dl)):
+        sol, info = kb.cg(A, b, tol=1e-10, **kw)
+        so, io = orc.cg(A, b, tol=1e-10, **kw)
+        assert info.success and info.numsteps == io.numsteps
+        ro, rg = np.asarray(io.resnorms, float), np.asarray(info.resnorms, float)
+        live = ro / ro[0] >= 1e-6
+        assert np.all(np.abs(rg - ro)[live] <= 1e-8 * ro[live])
+        assert np.linalg.norm(sol - so) <= 1e-10 * np.linalg.norm(so)
+    assert kb.cg(A, b, tol=1e-10, M=M)[1].numsteps < plain_steps  # the preconditioner did its job
+    # the device-resident path was taken: no duck-typed operator involved
+    from krylov_b200.operators import Problem
+    prob = Problem(A, b)
+    assert prob.operator(M).csr is not None and prob.operator(Dl).csr is not None
