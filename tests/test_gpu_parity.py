@@ -318,6 +318,63 @@ def test_arnoldi_builders_match_reference():
         next(arn)
 
 
+def test_coefficients_first_50_steps():
+    """BASELINE.json: 'Hessenberg/Lanczos coefficients compared on the first 50 steps'.
+    Arnoldi-MGS (x1, x2), Householder and Lanczos on 3-D stencil matrices, 50 steps, against
+    the live oracle within 10x its own summation-order noise; CG's Lanczos tridiagonal
+    (return_arnoldi) against the oracle's."""
+    m = 50
+    A = cases.st.convection_diffusion3d(12)
+    As = cases.st.shifted_laplace3d(12)
+    v = np.random.default_rng(7).standard_normal(A.shape[0])
+
+    def drive(arn, lanczos=False):
+        if lanczos:
+            T = []
+            for _ in range(m):
+                _v, h, _p = next(arn)
+                T.append(np.array(h))
+            return [np.array(T).T]
+        H = np.zeros((m + 1, m))
+        for k in range(m):
+            _, h = next(arn)
+            H[: k + 2, k] = h
+        return [H]
+
+    for nre in (1, 2):
+        env = _self_noise_envelope(
+            lambda inner: orc.ArnoldiMGS(A, v.copy(), num_reorthos=nre, inner=inner), drive, m)
+        ref = drive(orc.ArnoldiMGS(A, v.copy(), num_reorthos=nre, inner=lambda x, y: np.dot(x, y)))
+        got = drive(kb.ArnoldiMGS(A, v.copy(), num_reorthos=nre))
+        _assert_within(got[0], ref[0], env[0], f"mgs{nre} H, 50 steps")
+    # Householder has no inner-product hook: its noise amplification is probed by perturbing
+    # the start vector at the level of one rounding error
+    ref = drive(orc.ArnoldiHouseholder(A, v.copy()))
+    prng = np.random.default_rng(8)
+    henv = np.zeros(m)
+    for _ in range(3):
+        v2 = v * (1.0 + np.finfo(float).eps * prng.standard_normal(v.shape))
+        alt = drive(orc.ArnoldiHouseholder(A, v2))
+        henv = np.maximum(henv, np.abs(alt[0] - ref[0]).max(axis=0))
+    got = drive(kb.ArnoldiHouseholder(A, v.copy(), max_steps=m))
+    _assert_within(got[0], ref[0], 10.0 * henv + 1e-13, "householder H, 50 steps")
+    env = _self_noise_envelope(
+        lambda inner: orc.ArnoldiLanczos(As, v.copy(), inner=inner),
+        lambda arn: drive(arn, lanczos=True), m)
+    ref = drive(orc.ArnoldiLanczos(As, v.copy(), inner=lambda x, y: np.dot(x, y)), lanczos=True)
+    got = drive(kb.ArnoldiLanczos(As, v.copy()), lanczos=True)
+    _assert_within(got[0], ref[0], env[0], "lanczos h, 50 steps")
+    # CG's tridiagonal on the SPD Poisson matrix
+    Ap = cases.st.poisson3d(12)
+    b = Ap @ v
+    _, info = kb.cg(Ap, b, tol=0.0, atol=0.0, maxiter=m, return_arnoldi=True)
+    _, io = orc.cg(Ap, b, tol=0.0, atol=0.0, maxiter=m, return_arnoldi=True)
+    H, Ho = info.arnoldi[1], io.arnoldi[1]
+    assert H.shape == Ho.shape == (m + 1, m)
+    np.testing.assert_allclose(H, Ho, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(H[:, :25], Ho[:, :25], rtol=1e-10, atol=1e-12)
+
+
 def test_givens_bit_exact():
     fg = SML["givens_fg"]
     Gm, r = kb.givens(np.ascontiguousarray(fg.T))
