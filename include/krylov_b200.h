@@ -226,10 +226,12 @@ typedef struct {
 } kb_minres_state;
 int kb_minres_scalar(kb_ws_t ws, int k, int iter, const kb_minres_state* st, void* stream);
 /* z = (v - R0 W0 - R1 W1)/nz(R2); W0 <- z (becomes W1 by buffer rotation);
- * yk += y0 z; vnext = Av / nz(h2)   (minres.py:219-221, arnoldi.py:274-277) */
+ * yk += y0 z; vnext = Av / nz(h2)   (minres.py:219-221, arnoldi.py:274-277).
+ * With a preconditioner M pass MAv = M Av and pnext: vnext = MAv / nz(h2),
+ * pnext = Av / nz(h2) (the two bases V = M P); otherwise both NULL. */
 int kb_minres_update(kb_ws_t ws, int64_t n, int k, const double* coefs, const double* v,
                      double* W0, const double* W1, const double* Av, double* yk,
-                     double* vnext, void* stream);
+                     double* vnext, const double* MAv, double* pnext, void* stream);
 
 /* --- Arnoldi-MGS / GMRES (arnoldi.py:167-200, gmres.py:179-234) -------- */
 typedef struct {

@@ -96,7 +96,7 @@ SIGNATURES = {
     "kb_axpy_dot": [vp, i64, i32, vp, vp, vp, vp, i32, vp, vp, vp],
     "kb_house_hlast": [vp, vp, i64, vp, vp, vp, vp, vp],
     "kb_minres_scalar": [vp, i32, i32, C.POINTER(MinresState), vp],
-    "kb_minres_update": [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp],
+    "kb_minres_update": [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "kb_gmres_scalar": [vp, i32, i32, C.POINTER(GmresState), vp],
     "kb_gmres_solve_y": [vp, i32, i32, i32, vp, vp, vp, vp],
     "kb_basis_combine": [vp, i64, i32, i32, vp, vp, i64, vp, vp, vp],

@@ -988,12 +988,18 @@ int kb_minres_scalar(kb_ws_t ws, int k, int iter, const kb_minres_state* stt, vo
 
 int kb_minres_update(kb_ws_t ws, int64_t n, int k, const double* coefs, const double* v,
                      double* W0, const double* W1, const double* Av, double* yk, double* vnext,
-                     void* stream) {
+                     const double* MAv, double* pnext, void* stream) {
   KB_VEC_PROLOGUE();
   KB_REQUIRE(coefs && v && W0 && W1 && Av && yk && vnext, "null argument");
+  KB_REQUIRE((MAv == nullptr) == (pnext == nullptr), "MAv and pnext go together");
   if (total == 0) return KB_OK;
   const int grid = kb_grid_for(ws, total, block, KB_MR_UNROLL);
-  kb_minres_update_kernel<<<grid, block, 0, st>>>(total, k, coefs, v, W0, W1, Av, yk, vnext, rd);
+  if (MAv)
+    kb_minres_update_kernel<true><<<grid, block, 0, st>>>(total, k, coefs, v, W0, W1, Av, yk, vnext,
+                                                          MAv, pnext, rd);
+  else
+    kb_minres_update_kernel<false><<<grid, block, 0, st>>>(total, k, coefs, v, W0, W1, Av, yk,
+                                                           vnext, nullptr, nullptr, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

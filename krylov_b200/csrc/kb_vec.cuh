@@ -334,13 +334,17 @@ kb_axpy_dot_kernel(int64_t total, int k, const double* __restrict__ coef,
 // coefs = [R0 | R1 | R2 | y0 | h2] (k each)
 // z = (v - R0 W0 - R1 W1) / nz(R2);  W0 <- z;  yk += y0 z;  vnext = Av / nz(h2)
 // 64 B/element (reads v W0 W1 Av yk, writes W0 yk vnext).
+// With a preconditioner M (MAv != NULL): vnext = MAv / nz(h2), pnext = Av / nz(h2)
+// (the V = M P pair of bases, arnoldi.py:274-277): 80 B/element.
 // minres.py:219-221 ("take the longest"), arnoldi.py:274-277
 #define KB_MR_UNROLL 2
+template <bool PRE>
 __global__ void __launch_bounds__(KB_BLOCK, 4)
 kb_minres_update_kernel(int64_t total, int k, const double* __restrict__ coefs,
                         const double* __restrict__ v, double* __restrict__ W0,
                         const double* __restrict__ W1, const double* __restrict__ Av,
-                        double* __restrict__ yk, double* __restrict__ vnext, KbRed rd) {
+                        double* __restrict__ yk, double* __restrict__ vnext,
+                        const double* __restrict__ MAv, double* __restrict__ pnext, KbRed rd) {
   if (kb_gated(rd)) return;
   const int c = threadIdx.x % k;
   const double R0 = coefs[c];
@@ -348,9 +352,11 @@ kb_minres_update_kernel(int64_t total, int k, const double* __restrict__ coefs,
   const double R2 = kb_nz(coefs[2 * k + c]);
   const double y0 = coefs[3 * k + c];
   const double h2 = kb_nz(coefs[4 * k + c]);
+  constexpr bool pre = PRE;
   KB_TILE_LOOP_BEGIN_U(total, KB_MR_UNROLL)
   if (kb_full) {
-    double vv[KB_MR_UNROLL], w0[KB_MR_UNROLL], w1[KB_MR_UNROLL], av[KB_MR_UNROLL], yv[KB_MR_UNROLL];
+    double vv[KB_MR_UNROLL], w0[KB_MR_UNROLL], w1[KB_MR_UNROLL], av[KB_MR_UNROLL],
+        yv[KB_MR_UNROLL], mv[KB_MR_UNROLL];
 #pragma unroll
     for (int q = 0; q < KB_MR_UNROLL; ++q) {
       const int64_t i = KB_IDX(q);
@@ -359,6 +365,7 @@ kb_minres_update_kernel(int64_t total, int k, const double* __restrict__ coefs,
       w1[q] = W1[i];
       av[q] = Av[i];
       yv[q] = yk[i];
+      mv[q] = pre ? MAv[i] : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < KB_MR_UNROLL; ++q) {
@@ -366,16 +373,27 @@ kb_minres_update_kernel(int64_t total, int k, const double* __restrict__ coefs,
       const double zz = kb_mul_sub(R1, w1[q], kb_mul_sub(R0, w0[q], vv[q])) / R2;
       W0[i] = zz;
       yk[i] = kb_mul_add(y0, zz, yv[q]);
-      vnext[i] = av[q] / h2;
+      if (pre) {
+        vnext[i] = mv[q] / h2;
+        pnext[i] = av[q] / h2;
+      } else {
+        vnext[i] = av[q] / h2;
+      }
     }
   } else {
     for (int q = 0; q < KB_MR_UNROLL; ++q) {
       const int64_t i = KB_IDX(q);
       if (i < total) {
         const double zz = kb_mul_sub(R1, W1[i], kb_mul_sub(R0, W0[i], v[i])) / R2;
+        const double a = Av[i];
         W0[i] = zz;
         yk[i] = kb_mul_add(y0, zz, yk[i]);
-        vnext[i] = Av[i] / h2;
+        if (pre) {
+          vnext[i] = MAv[i] / h2;
+          pnext[i] = a / h2;
+        } else {
+          vnext[i] = a / h2;
+        }
       }
     }
   }

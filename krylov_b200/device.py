@@ -213,10 +213,11 @@ class Ops:
         self.launches += 1
         check(lib.kb_minres_scalar(self.ws.handle, self.k, int(it), C.byref(state), cur_stream()))
 
-    def minres_update(self, coefs, v, W0, W1, Av, yk, vnext):
+    def minres_update(self, coefs, v, W0, W1, Av, yk, vnext, MAv=None, pnext=None):
         self.launches += 1
         check(lib.kb_minres_update(self.ws.handle, self.n, self.k, ptr(coefs), ptr(v), ptr(W0),
-                                   ptr(W1), ptr(Av), ptr(yk), ptr(vnext), cur_stream()))
+                                   ptr(W1), ptr(Av), ptr(yk), ptr(vnext), ptr(MAv), ptr(pnext),
+                                   cur_stream()))
 
     # -- GMRES
     def gmres_scalar(self, it, state: GmresState):

@@ -3,12 +3,14 @@
 QR of the tridiagonal with two stored Givens rotations, two-vector ``W``
 recurrence.
 
-Fused path (M = Ml = Mr = None, default inner product, A a matrix), per step:
+Fused path (default inner product; A and any of M / Ml / Mr given as matrices), per step:
   1. ``Av = A v - beta_{k-1} v_old`` fused with ``alpha = <v, Av>``   (SpMV kernel)
   2. ``Av -= alpha v`` fused with ``beta_k^2 = <Av, Av>``             (24 B/elem)
   3. one-block scalar kernel: Givens QR update on the device (dlartg semantics),
      residual norm, convergence flag                                  (no host)
   4. ``z = (v - R0 W0 - R1 W1)/R2; yk += y0 z; v_next = Av/beta_k``   (64 B/elem)
+With preconditioners step 1 runs the chain ``Ml A Mr`` (fusion on its last product), step 2's
+norm becomes ``<Av, M Av>`` out of M's product, step 4 also writes ``p_next`` (80 B/elem).
 The general path mirrors the reference loop with host scalars.
 """
 from __future__ import annotations
@@ -36,8 +38,12 @@ def minres(A, b, M=None, Ml=None, Mr=None, inner=None, x0=None, tol=1e-5, atol=1
     prob = Problem(A, b, x0)
     maxiter = prob.n if maxiter is None else int(maxiter)
     with torch.cuda.device(prob.device):
-        if M is None and Ml is None and Mr is None and inner is None and prob.A_csr is not None:
-            return _minres_fused(prob, tol, atol, maxiter, callback)
+        if inner is None and prob.A_csr is not None:
+            # device-resident path: A and the preconditioners (if any) are matrices
+            pre = [prob.operator(op) for op in (M, Ml, Mr)]
+            if all(op is None or op.csr is not None for op in pre):
+                return _minres_fused(prob, tol, atol, maxiter, callback,
+                                     *[None if op is None else op.csr for op in pre])
         return _minres_general(prob, M, Ml, Mr, inner, tol, atol, maxiter, callback)
 
 
@@ -62,13 +68,21 @@ def _callback_resnorm(prob, callback, xk, rn):
     return np.broadcast_to(np.asarray(arr[()], dtype=np.float64).reshape(-1), (prob.k,)).copy()
 
 
-def _minres_fused(prob, tol, atol, maxiter, callback):
+def _minres_fused(prob, tol, atol, maxiter, callback, M=None, Ml=None, Mr=None):
+    """Device-resident MINRES; ``M``/``Ml``/``Mr`` are CSR matrices or None.  With them the
+    Lanczos operator is the chain ``Ml A Mr`` (minres.py:136-141; the last product of the
+    chain carries the fused ``- beta v_old`` and ``<v, .>``), ``M`` keeps the two bases
+    ``V = M P`` (arnoldi.py:250-277) and ``beta^2 = <Av, M Av>`` comes out of M's own product."""
     A, b, x0 = prob.A_csr, prob.b, prob.x0
     n, k, dev = prob.n, prob.k, prob.device
     ops = Ops(n, k, dev, comm=prob.comm)
+    chain = [op for op in (Mr, A, Ml) if op is not None]
     Vb = [ops.vec(zero=True), ops.vec(zero=True)]  # v_i in Vb[i % 2], v_{i-1} in the other
+    Pb = Vb if M is None else [ops.vec(zero=True), ops.vec(zero=True)]  # p_i likewise
     Wb = [ops.vec(zero=True), ops.vec(zero=True)]  # W0 in Wb[i % 2], W1 in the other
     Av = ops.vec(zero=False)
+    MAv = None if M is None else ops.vec(zero=False)
+    tmp = [ops.vec(zero=False) for _ in range(min(len(chain) - 1, 2))]
     yk = ops.vec(zero=True)
     sl = ops.slots(5)  # alpha, ww, h2prev, y0, scratch
     g0, g1 = ops.slots(2), ops.slots(2)
@@ -77,12 +91,33 @@ def _minres_fused(prob, tol, atol, maxiter, callback):
     flags = torch.zeros((1,), dtype=torch.int32, device=dev)
     hist = torch.zeros((_BATCH_MAX, k), dtype=torch.float64, device=dev)
 
-    # r0 = b - A x0, ||r0||  (minres.py:121-127); v_0 = r0 / nz(||r0||) (arnoldi.py:229-231)
+    def get_x():  # minres.py:95-98
+        xk = torch.empty_like(yk)
+        if Mr is None:
+            ops.add(xk, x0, yk)
+        else:
+            ops.spmv(Mr, yk, Av)
+            ops.add(xk, x0, Av)
+        return xk
+
+    def explicit_norm(z, keep=False):  # minres.py:106-112 / 121-127
+        """sqrt(<r, M r>), r = Ml (b - A z).  keep: leave r in Av and M r in MAv."""
+        if Ml is None:
+            ops.spmv(A, z, Av, mode=2, z=b, dot=(2 if M is None else 0), out=sl[4])
+        else:
+            ops.spmv(A, z, tmp[0], mode=2, z=b)
+            ops.spmv(Ml, tmp[0], Av, dot=(2 if M is None else 0), out=sl[4])
+        if M is not None:
+            ops.spmv(M, Av, MAv, dot=1, w=Av, out=sl[4])
+        return np.sqrt(sl[4].cpu().numpy().copy())
+
+    # Ml r0, M Ml r0, ||.||  (minres.py:121-127); p_0, v_0 = ./nz(norm) (arnoldi.py:229-231)
     ops.gate(None, 0)
-    ops.spmv(A, x0, Av, mode=2, z=b, dot=2, out=sl[4])
-    nrm0 = np.sqrt(sl[4].cpu().numpy().copy())
+    nrm0 = explicit_norm(x0, keep=True)
     sl[3].copy_(torch.from_numpy(nrm0))  # y = [||r0||, 0]   (minres.py:149)
-    ops.div_scale(Vb[0], Av, sl[3])
+    ops.div_scale(Pb[0], Av, sl[3])
+    if M is not None:
+        ops.div_scale(Vb[0], MAv, sl[3])
     if callback is not None:
         nrm0 = _callback_resnorm(prob, callback, x0, nrm0)
     resn = [nrm0]
@@ -100,10 +135,8 @@ def _minres_fused(prob, tol, atol, maxiter, callback):
     while True:
         if np.all(resn[-1] <= crit):  # minres.py:169-175
             if xk is None:
-                xk = torch.empty_like(yk)
-                ops.add(xk, x0, yk)
-            ops.spmv(A, xk, Av, mode=2, z=b, dot=2, out=sl[4])
-            resn[-1] = np.sqrt(sl[4].cpu().numpy().copy())
+                xk = get_x()
+            resn[-1] = explicit_norm(xk)
             if np.all(resn[-1] <= crit):
                 success = True
                 break
@@ -116,14 +149,26 @@ def _minres_fused(prob, tol, atol, maxiter, callback):
         st.hist = hist.data_ptr() - (kk + 1) * k * 8
         for i in range(kk, kk + nb):
             v, vold = Vb[i % 2], Vb[(i + 1) % 2]
+            p, pold = Pb[i % 2], Pb[(i + 1) % 2]
             ops.gate(stop_at, i)
+            src = v
+            for j, op in enumerate(chain[:-1]):  # Mr, A in front of the fused last product
+                ops.spmv(op, src, tmp[j])
+                src = tmp[j]
             if i == 0:
-                ops.spmv(A, v, Av, dot=1, w=v, out=sl[0])
-            else:  # Av = A v - beta_{i-1} v_old   (arnoldi.py:244-249)
-                ops.spmv(A, v, Av, mode=1, z=vold, coef=sl[2], dot=1, w=v, out=sl[0])
-            ops.axpy_dot(sl[0], v, Av, dot=2, out=sl[1])  # arnoldi.py:264-267
-            ops.minres_scalar(i, st)  # minres.py:190-228
-            ops.minres_update(coefs, v, Wb[i % 2], Wb[(i + 1) % 2], Av, yk, vold)
+                ops.spmv(chain[-1], src, Av, dot=1, w=v, out=sl[0])
+            else:  # Av = (Ml A Mr) v - beta_{i-1} p_old   (arnoldi.py:244-249)
+                ops.spmv(chain[-1], src, Av, mode=1, z=pold, coef=sl[2], dot=1, w=v, out=sl[0])
+            if M is None:
+                ops.axpy_dot(sl[0], p, Av, dot=2, out=sl[1])  # arnoldi.py:264-267
+                ops.minres_scalar(i, st)  # minres.py:190-228
+                ops.minres_update(coefs, v, Wb[i % 2], Wb[(i + 1) % 2], Av, yk, vold)
+            else:
+                ops.axpy_dot(sl[0], p, Av, dot=0, out=sl[1])  # Av -= alpha p
+                ops.spmv(M, Av, MAv, dot=1, w=Av, out=sl[1])  # beta^2 = <Av, M Av>
+                ops.minres_scalar(i, st)
+                ops.minres_update(coefs, v, Wb[i % 2], Wb[(i + 1) % 2], Av, yk, vold,
+                                  MAv=MAv, pnext=pold)
         ops.gate(None, 0)
         s = int(stop_at.item())
         done = min(s, kk + nb) - kk
@@ -133,15 +178,13 @@ def _minres_fused(prob, tol, atol, maxiter, callback):
         kk += done
         xk = None
         if callback is not None:
-            xk = torch.empty_like(yk)
-            ops.add(xk, x0, yk)
+            xk = get_x()
             resn[-1] = _callback_resnorm(prob, callback, xk, resn[-1])
         else:
             batch = min(2 * batch, _BATCH_MAX)
 
     if xk is None:
-        xk = torch.empty_like(yk)
-        ops.add(xk, x0, yk)
+        xk = get_x()
     prob.launches = ops.launches
     return _finish(prob, success, xk, kk, resn)
 

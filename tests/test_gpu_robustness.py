@@ -132,3 +132,41 @@ def test_fused_preconditioned_cg_vs_oracle(k):
     from krylov_b200.operators import Problem
     prob = Problem(A, b)
     assert prob.operator(M).csr is not None and prob.operator(Dl).csr is not None
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_fused_preconditioned_minres_vs_oracle(k):
+    """MINRES with matrix M / Ml / Mr stays device-resident (chain Ml A Mr with the fusion
+    on its last product, V = M P bases, beta^2 = <Av, M Av> out of M's product)."""
+    n = 10
+    A = st.shifted_laplace3d(n).tolil()            # symmetric indefinite
+    d = rng.random(n ** 3) * 20.0
+    for i in range(n ** 3):
+        A[i, i] = A[i, i] + d[i]
+    A = A.tocsr()
+    N = A.shape[0]
+    M = scipy.sparse.diags(1.0 / (1.0 + np.abs(A.diagonal()))).tocsr()   # SPD
+    Dl = scipy.sparse.identity(N, format="csr") * 0.5
+    Dr = scipy.sparse.identity(N, format="csr") * 2.0
+    shape = (N,) if k == 1 else (N, k)
+    b = A @ rng.standard_normal(shape)
+    import sys
+    kmin = sys.modules["krylov_b200.minres"]
+    calls = []
+    orig = kmin._minres_fused
+    kmin._minres_fused = lambda *a, **kw: (calls.append(1), orig(*a, **kw))[1]
+    try:
+        for kw in (dict(M=M), dict(Ml=Dl), dict(Mr=Dr), dict(Ml=Dl, Mr=Dr),
+                   dict(M=M, Ml=Dl, Mr=Dr)):
+            sol, info = kb.minres(A, b, tol=1e-9, maxiter=3000, **kw)
+            so, io = orc.minres(A, b, tol=1e-9, maxiter=3000, **kw)
+            assert info.success and io.success, kw
+            assert abs(info.numsteps - io.numsteps) <= max(2, io.numsteps // 50), kw
+            m = min(info.numsteps, io.numsteps)
+            ro, rg = np.asarray(io.resnorms, float)[:m], np.asarray(info.resnorms, float)[:m]
+            live = ro / ro[0] >= 1e-5
+            assert np.all(np.abs(rg - ro)[live] <= 1e-7 * ro[live]), kw
+            assert np.linalg.norm(sol - so) <= 1e-7 * np.linalg.norm(so), kw
+    finally:
+        kmin._minres_fused = orig
+    assert len(calls) == 5     # every variant took the device-resident path
