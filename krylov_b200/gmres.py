@@ -74,7 +74,11 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
         householder = True
     # everything device-resident <=> default inner product (no host callable in the loop)
     fused_dots = inner is None
-    csr_only = prob.A_csr is not None and Ml is None and Mr is None
+    csr_chain = None  # Ml A Mr as device matrices: the last product carries the first MGS dot
+    if prob.A_csr is not None and all(op is None or op.csr is not None for op in (Ml, Mr)):
+        csr_chain = [op for op in (None if Mr is None else Mr.csr, prob.A_csr,
+                                   None if Ml is None else Ml.csr) if op is not None]
+    M_csr = None if M is None else M.csr
 
     def residual_triple(z):  # gmres.py:105-114
         Ml_r = alg.apply(Ml, alg.residual(A, b, z))
@@ -148,8 +152,12 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
             return
         w = Wbuf
         # w = Ml A Mr V[i]  (+ first MGS dot <V[0], w> fused into the product)
-        if csr_only and fused_dots:
-            ops.spmv(prob.A_csr, Vbuf[i], w, dot=1, w=Vbuf[0], out=dots[0])
+        if csr_chain is not None and fused_dots:
+            src = Vbuf[i]
+            for j, op in enumerate(csr_chain[:-1]):
+                ops.spmv(op, src, Tbuf[j])
+                src = Tbuf[j]
+            ops.spmv(csr_chain[-1], src, w, dot=1, w=Vbuf[0], out=dots[0])
         else:
             w.copy_(alg.apply_chain(chain, Vbuf[i]))
             _dot(Vbuf[0], w, dots[0])
@@ -172,7 +180,10 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
                         ops.axpy_dot(dots[idx], Pbuf[j], w, dot=0)
                         _dot(nxt, w, dots[idx + 1])
                 idx += 1
-        if not last_fused:  # h[k+1]^2 = <w, M w>   (arnoldi.py:184-185)
+        if not last_fused and M_csr is not None and fused_dots:
+            Mw = MWbuf  # h[k+1]^2 = <w, M w> out of M's own product   (arnoldi.py:184-185)
+            ops.spmv(M_csr, w, Mw, dot=1, w=w, out=ww)
+        elif not last_fused:
             Mw = alg.apply(M, w)
             _dot(w, Mw, ww)
         else:
@@ -189,6 +200,8 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
             out.copy_(torch.from_numpy(alg.inner(xv, yv)))
 
     Wbuf = None if householder else ops.vec(zero=False)
+    Tbuf = [ops.vec(zero=False) for _ in range(0 if csr_chain is None else len(csr_chain) - 1)]
+    MWbuf = ops.vec(zero=False) if M_csr is not None and not householder else None
     step_by_step = callback is not None or not fused_dots
     batch = 1 if step_by_step else _BATCH_MIN
     kk = 0

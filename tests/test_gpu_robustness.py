@@ -170,3 +170,27 @@ def test_fused_preconditioned_minres_vs_oracle(k):
     finally:
         kmin._minres_fused = orig
     assert len(calls) == 5     # every variant took the device-resident path
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_preconditioned_gmres_sparse_vs_oracle(k):
+    """GMRES with sparse M / Ml / Mr: the chain Ml A Mr runs as device products with the first
+    Gram-Schmidt dot fused into the last one; <w, M w> comes out of M's product."""
+    A = st.convection_diffusion3d(8)
+    N = A.shape[0]
+    M = scipy.sparse.diags(1.0 / (1.0 + rng.random(N))).tocsr()          # SPD
+    Jl = scipy.sparse.diags(1.0 / A.diagonal()).tocsr()
+    Jr = scipy.sparse.diags(0.5 + rng.random(N)).tocsr()
+    shape = (N,) if k == 1 else (N, k)
+    b = A @ rng.standard_normal(shape)
+    for kw in (dict(M=M), dict(Ml=Jl), dict(Mr=Jr), dict(Ml=Jl, Mr=Jr),
+               dict(M=M, Ml=Jl, Mr=Jr), dict(Ml=Jl, Mr=Jr, ortho="mgs2")):
+        sol, info = kb.gmres(A, b, tol=1e-9, maxiter=200, **kw)
+        so, io = orc.gmres(A, b, tol=1e-9, maxiter=200, **kw)
+        assert info.success and io.success, kw
+        assert abs(info.numsteps - io.numsteps) <= 1, kw
+        m = min(info.numsteps, io.numsteps)
+        ro, rg = np.asarray(io.resnorms, float)[:m], np.asarray(info.resnorms, float)[:m]
+        live = ro / ro[0] >= 1e-5
+        assert np.all(np.abs(rg - ro)[live] <= 1e-7 * ro[live]), kw
+        assert np.linalg.norm(sol - so) <= 1e-7 * np.linalg.norm(so), kw
