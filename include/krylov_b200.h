@@ -259,6 +259,16 @@ int kb_basis_combine(kb_ws_t ws, int64_t n, int k, int m, const double* yy, cons
                      int64_t vstride, const double* x0, double* out, void* stream);
 
 /* --- Householder (householder.py:26-62, arnoldi.py:65-104), k == 1 ------ */
+/* Classical Gram-Schmidt building blocks (ortho="cgs"/"cgs<N>": an additive extension, the
+ * reference's Arnoldi is MGS only, arnoldi.py:157-162).  Tall-skinny V^T w in one pass over w:
+ * out[j, c] = <V[j][:, c], w[:, c]>, j < cnt; V[j] = V + j * vstride.  (cnt + 1) * 8 B/element. */
+int kb_multi_dot(kb_ws_t ws, int64_t n, int k, int cnt, const double* V, int64_t vstride,
+                 const double* w, double* out, void* stream);
+/* w -= sum_{j < m} h[j, :] * P[j]; dot = 2 also returns out = <w, w> of the result.
+ * (m + 2) * 8 B/element. */
+int kb_multi_axpy(kb_ws_t ws, int64_t n, int k, int m, const double* h, const double* P,
+                  int64_t pstride, double* w, int dot, double* out, void* stream);
+
 /* Builds the reflector for the tail x[off:]: v (length n, zeros before off),
  * params[0..3] = alpha, beta, xnorm, sigma2-taken-from-slot.  Two launches. */
 int kb_house_make(kb_ws_t ws, int64_t n, int64_t off, const double* x, double* v,

@@ -100,6 +100,8 @@ SIGNATURES = {
     "kb_gmres_scalar": [vp, i32, i32, C.POINTER(GmresState), vp],
     "kb_gmres_solve_y": [vp, i32, i32, i32, vp, vp, vp, vp],
     "kb_basis_combine": [vp, i64, i32, i32, vp, vp, i64, vp, vp, vp],
+    "kb_multi_dot": [vp, i64, i32, i32, vp, i64, vp, vp, vp],
+    "kb_multi_axpy": [vp, i64, i32, i32, vp, vp, i64, vp, i32, vp, vp],
     "kb_house_make": [vp, i64, i64, vp, vp, vp, vp, vp],
     "kb_poke": [vp, i32, vp, i64, vp, f64, vp, vp],
     "kb_lartg": [i32, vp, vp, vp, vp],

@@ -43,6 +43,7 @@ static int g_stream_cfg = 0;
 static int g_stream_ctas = 0;  // 0 = configuration default
 static int g_pattern_ctas = 0; // kb_tune key 3 (0 = default)
 static int g_window_cfg = 0;   // kb_tune key 4
+static int g_cgs_jc = 8;  // kb_tune key 9: basis vectors per multi-dot launch (8 or 16)
 static int g_rowwise_contig = -1;  // kb_tune key 5: -1 auto, 0 strided, 1 contiguous rows per block
 static int g_rowwise_ctas = 0;     // kb_tune key 6: CTAs/SM of the contiguous row-wise grid
 static int g_tile_block = 0;       // kb_tune key 8: 0 natural tile order (default: the blocked
@@ -159,6 +160,7 @@ int kb_tune(int key, int value) {
     case 6: g_rowwise_ctas = value; return KB_OK;
     case 7: g_spmm_cfg = value; return KB_OK;
     case 8: g_tile_block = value; return KB_OK;
+    case 9: g_cgs_jc = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -1031,6 +1033,49 @@ int kb_basis_combine(kb_ws_t ws, int64_t n, int k, int m, const double* yy, cons
   if (total == 0) return KB_OK;
   const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
   kb_basis_combine_kernel<<<grid, block, 0, st>>>(total, k, m, yy, Vbuf, vstride, x0, out, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_multi_dot(kb_ws_t ws, int64_t n, int k, int cnt, const double* V, int64_t vstride,
+                 const double* w, double* out, void* stream) {
+  KB_VEC_PROLOGUE();
+  KB_REQUIRE(cnt >= 0 && (cnt == 0 || (V && w && out)), "null argument");
+  // cnt * k sums per launch are bounded by the partials buffer / mailbox width and the block
+  int cap = ws->max_k < block ? ws->max_k : block;
+  int per = cap / k;
+  if (per < 1) per = 1;
+  const int jcmax = g_cgs_jc == 16 ? 16 : 8;
+  if (per > jcmax) per = jcmax;
+  const int grid = kb_grid_for(ws, total, block, KB_MD_UNROLL);
+  for (int j0 = 0; j0 < cnt; j0 += per) {
+    const int c = cnt - j0 < per ? cnt - j0 : per;
+    const double* Vj = V + (size_t)j0 * vstride;
+    double* oj = out + (size_t)j0 * k;
+    if (c > 8)
+      kb_multi_dot_kernel<16><<<grid, block, 0, st>>>(total, k, c, Vj, vstride, w, oj, rd);
+    else if (c > 4)
+      kb_multi_dot_kernel<8><<<grid, block, 0, st>>>(total, k, c, Vj, vstride, w, oj, rd);
+    else if (c > 2)
+      kb_multi_dot_kernel<4><<<grid, block, 0, st>>>(total, k, c, Vj, vstride, w, oj, rd);
+    else
+      kb_multi_dot_kernel<2><<<grid, block, 0, st>>>(total, k, c, Vj, vstride, w, oj, rd);
+    KB_LAUNCH_CHECK();
+  }
+  return KB_OK;
+}
+
+int kb_multi_axpy(kb_ws_t ws, int64_t n, int k, int m, const double* h, const double* P,
+                  int64_t pstride, double* w, int dot, double* out, void* stream) {
+  KB_VEC_PROLOGUE();
+  KB_REQUIRE(m >= 0 && w && (m == 0 || (h && P)), "null argument");
+  KB_REQUIRE(dot == 0 || dot == 2, "dot must be 0 or 2");
+  KB_REQUIRE(dot == 0 || out, "dot needs out");
+  const int grid = kb_grid_for(ws, total, block, KB_MD_UNROLL);
+  if (dot == 2)
+    kb_multi_axpy_kernel<2><<<grid, block, 0, st>>>(total, k, m, h, P, pstride, w, out, rd);
+  else
+    kb_multi_axpy_kernel<0><<<grid, block, 0, st>>>(total, k, m, h, P, pstride, w, out, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

@@ -321,3 +321,50 @@ __device__ __forceinline__ bool kb_grid_colsum(double acc, int k, const KbRed& r
   }
   return s_last != 0;
 }
+
+// The same single-launch reduction for JC column-wise sums at once (tall-skinny V^T w):
+// acc[jj] feeds out[jj * k + c], jj < cnt.  Needs cnt * k <= blockDim.x and <= the workspace /
+// communicator max_k (checked by the host).  Fixed summation shape -> bitwise reproducible.
+template <int JC>
+__device__ __forceinline__ void kb_grid_multisum(const double (&acc)[JC], int cnt, int k,
+                                                 const KbRed& rd, double* out, double* sm) {
+  __shared__ int s_last_m;
+  const int t = threadIdx.x;
+  const int kk = cnt * k;
+#pragma unroll
+  for (int jj = 0; jj < JC; ++jj) {
+    if (jj < cnt) {  // block-uniform
+      const double tot = kb_block_colsum(acc[jj], k, sm);
+      if (t < k) rd.partials[(size_t)blockIdx.x * kk + jj * k + t] = tot;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    unsigned int prev = atomicAdd(rd.ticket, 1u);
+    s_last_m = (prev == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last_m) {
+    __threadfence();
+    const int Q = blockDim.x / kk;
+    double a2 = 0.0;
+    if (t < Q * kk) {
+      const int c = t % kk;
+      for (unsigned int b = t / kk; b < gridDim.x; b += Q)
+        a2 += __ldcg(&rd.partials[(size_t)b * kk + c]);
+    }
+    __syncthreads();
+    sm[t] = a2;
+    __syncthreads();
+    double fin = 0.0;
+    if (t < kk)
+      for (int i = 0; i < Q; ++i) fin += sm[i * kk + t];
+    if (rd.collective && rd.cm.size > 1) {
+      fin = kb_p2p_allreduce(fin, kk, rd.cm);
+      if (t < kk && *rd.cm.error) fin = nan("");
+    }
+    if (t < kk) out[t] = fin;
+    if (t == 0) *rd.ticket = 0u;
+  }
+}

@@ -432,6 +432,98 @@ kb_basis_combine_kernel(int64_t total, int k, int m, const double* __restrict__ 
   KB_TILE_LOOP_END
 }
 
+// ------------------------------------- classical Gram-Schmidt (extension) -
+// Tall-skinny V^T w: out[jj, c] = <V[j0 + jj][:, c], w[:, c]>, jj < cnt <= JC, in ONE pass
+// over w: (cnt + 1) * 8 B/element instead of the 16-32 of cnt separate dots.  Not in the
+// reference (its Arnoldi is MGS only, arnoldi.py:157-162): ortho="cgs"/"cgs<N>" is additive.
+#define KB_MD_UNROLL 2
+template <int JC>
+__global__ void __launch_bounds__(KB_BLOCK, (JC > 8 ? 2 : 4))
+kb_multi_dot_kernel(int64_t total, int k, int cnt, const double* __restrict__ V, int64_t vstride,
+                    const double* __restrict__ w, double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  __shared__ double sm[KB_BLOCK];
+  double acc[JC];
+#pragma unroll
+  for (int jj = 0; jj < JC; ++jj) acc[jj] = 0.0;
+  KB_TILE_LOOP_BEGIN_U(total, KB_MD_UNROLL)
+  if (kb_full) {
+    double wv[KB_MD_UNROLL];
+#pragma unroll
+    for (int q = 0; q < KB_MD_UNROLL; ++q) wv[q] = w[KB_IDX(q)];
+#pragma unroll
+    for (int jj = 0; jj < JC; ++jj) {
+      if (jj < cnt) {
+        const double* __restrict__ vj = V + (size_t)jj * vstride;
+#pragma unroll
+        for (int q = 0; q < KB_MD_UNROLL; ++q) acc[jj] = fma(vj[KB_IDX(q)], wv[q], acc[jj]);
+      }
+    }
+  } else {
+    for (int q = 0; q < KB_MD_UNROLL; ++q) {
+      const int64_t i = KB_IDX(q);
+      if (i < total) {
+        const double wi = w[i];
+#pragma unroll
+        for (int jj = 0; jj < JC; ++jj)
+          if (jj < cnt) acc[jj] = fma(V[(size_t)jj * vstride + i], wi, acc[jj]);
+      }
+    }
+  }
+  KB_TILE_LOOP_END
+  kb_grid_multisum<JC>(acc, cnt, k, rd, out, sm);
+}
+
+// w -= sum_{j < m} h[j, c] * P[j]   (+ out = <w, w> with DOT 2): one pass, (m + 2) * 8 B/element.
+template <int DOT>
+__global__ void __launch_bounds__(KB_BLOCK, 4)
+kb_multi_axpy_kernel(int64_t total, int k, int m, const double* __restrict__ h,
+                     const double* __restrict__ P, int64_t pstride, double* __restrict__ w,
+                     double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  __shared__ double sm[KB_BLOCK];
+  const int c = threadIdx.x % k;
+  double acc = 0.0;
+  KB_TILE_LOOP_BEGIN_U(total, KB_MD_UNROLL)
+  double wv[KB_MD_UNROLL];
+  bool ok[KB_MD_UNROLL];
+#pragma unroll
+  for (int q = 0; q < KB_MD_UNROLL; ++q) {
+    ok[q] = kb_full || KB_IDX(q) < total;
+    wv[q] = ok[q] ? w[KB_IDX(q)] : 0.0;
+  }
+  int j = 0;
+  for (; j + 7 < m; j += 8) {
+    double pv[8][KB_MD_UNROLL];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+      for (int q = 0; q < KB_MD_UNROLL; ++q)
+        pv[jj][q] = ok[q] ? P[(size_t)(j + jj) * pstride + KB_IDX(q)] : 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const double hj = __ldg(&h[(size_t)(j + jj) * k + c]);
+#pragma unroll
+      for (int q = 0; q < KB_MD_UNROLL; ++q) wv[q] = kb_mul_sub(hj, pv[jj][q], wv[q]);
+    }
+  }
+  for (; j < m; ++j) {
+    const double hj = __ldg(&h[(size_t)j * k + c]);
+#pragma unroll
+    for (int q = 0; q < KB_MD_UNROLL; ++q)
+      if (ok[q]) wv[q] = kb_mul_sub(hj, P[(size_t)j * pstride + KB_IDX(q)], wv[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < KB_MD_UNROLL; ++q) {
+    if (ok[q]) {
+      w[KB_IDX(q)] = wv[q];
+      if (DOT == 2) acc = fma(wv[q], wv[q], acc);
+    }
+  }
+  KB_TILE_LOOP_END
+  if (DOT != 0) kb_grid_colsum(acc, k, rd, out, sm);
+}
+
 // gather rows: buf[i, :] = x[idx[i], :]   (halo send buffer)
 __global__ void __launch_bounds__(KB_BLOCK)
 kb_pack_rows_kernel(int64_t n_idx, int k, const int32_t* __restrict__ idx,

@@ -69,7 +69,8 @@ _WS_POOL = {}
 
 def _borrow_workspace(device, k):
     free = _WS_POOL.setdefault((device.index, int(k)), [])
-    return free.pop() if free else Workspace(k)
+    # room for the multi-sum reductions of classical Gram-Schmidt (up to 16 sums per launch)
+    return free.pop() if free else Workspace(max(int(k), min(256, 16 * int(k))))
 
 
 def _return_workspace(device, k, ws):
@@ -228,6 +229,22 @@ class Ops:
         self.launches += 1
         check(lib.kb_gmres_solve_y(self.ws.handle, self.k, int(m), int(maxiter), ptr(R), ptr(y),
                                    ptr(yy), cur_stream()))
+
+    def multi_dot(self, cnt, V, w, out):
+        """out[j] = <V[j], w>, j < cnt: V a (>= cnt, n, k) buffer, out (>= cnt, k) rows."""
+        self.launches += -(-int(cnt) // 8)
+        check(lib.kb_multi_dot(self.ws.handle, self.n, self.k, int(cnt), ptr(V), self.n * self.k,
+                               ptr(w), ptr(out), cur_stream()))
+        if cnt:
+            self.reduce_over_ranks(out[:cnt])
+
+    def multi_axpy(self, m, h, P, w, dot=0, out=None):
+        """w -= sum_j h[j] P[j], j < m; dot=2 also out = <w, w>."""
+        self.launches += 1
+        check(lib.kb_multi_axpy(self.ws.handle, self.n, self.k, int(m), ptr(h), ptr(P),
+                                self.n * self.k, ptr(w), int(dot), ptr(out), cur_stream()))
+        if dot:
+            self.reduce_over_ranks(out)
 
     def basis_combine(self, m, yy, Vbuf, x0, out):
         self.launches += 1

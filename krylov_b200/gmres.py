@@ -1,6 +1,7 @@
 """Preconditioned GMRES on the device -- drop-in for ``krylov.gmres``
 (gmres.py:41-251): full (non-restarted) GMRES with ``ortho`` in
-``"mgs"``, ``"mgs<N>"`` (N sweeps of modified Gram-Schmidt), ``"householder"``;
+``"mgs"``, ``"mgs<N>"`` (N sweeps of modified Gram-Schmidt), ``"householder"``
+(plus the additive ``"cgs"`` / ``"cgs<N>"``: classical Gram-Schmidt as tall-skinny products);
 Hessenberg QR by Givens rotations; the solution is only formed when needed.
 ``restart=`` is an additive extension: GMRES(m) as an outer loop
 of ``gmres(maxiter=m, x0=xk)`` cycles.
@@ -63,9 +64,19 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
     M, Ml, Mr = prob.operator(M), prob.operator(Ml), prob.operator(Mr)
     chain = [Mr, A, Ml]  # Product(Ml, A, Mr)   (gmres.py:136)
 
+    cgs = False
     if ortho.startswith("mgs"):  # gmres.py:147-157
         nre = 1 if len(ortho) == 3 else int(ortho[3:])
         householder = False
+    elif ortho.startswith("cgs"):
+        # additive extension: classical Gram-Schmidt, "cgs<N>" = N passes
+        # ("cgs2" is the usual iterated CGS).  h = V^T w in one pass over w, w -= P h in one
+        # pass over P: half the memory traffic of MGS and 2 reductions per pass instead of j+1.
+        if inner is not None:
+            raise ValueError('ortho="cgs" needs the default inner product')
+        nre = 1 if len(ortho) == 3 else int(ortho[3:])
+        householder = False
+        cgs = True
     else:  # gmres.py:158-162
         assert ortho == "householder"
         assert inner is None
@@ -157,13 +168,25 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
             for j, op in enumerate(csr_chain[:-1]):
                 ops.spmv(op, src, Tbuf[j])
                 src = Tbuf[j]
-            ops.spmv(csr_chain[-1], src, w, dot=1, w=Vbuf[0], out=dots[0])
+            if cgs:
+                ops.spmv(csr_chain[-1], src, w)
+            else:
+                ops.spmv(csr_chain[-1], src, w, dot=1, w=Vbuf[0], out=dots[0])
         else:
             w.copy_(alg.apply_chain(chain, Vbuf[i]))
-            _dot(Vbuf[0], w, dots[0])
+            if not cgs:
+                _dot(Vbuf[0], w, dots[0])
         idx = 0
         last_fused = False
-        for sweep in range(nre):
+        for sweep in range(nre if cgs else 0):
+            rows = dots[sweep * (i + 1):]
+            ops.multi_dot(i + 1, Vbuf, w, rows)  # h = V^T w
+            if sweep == nre - 1 and M is None:
+                ops.multi_axpy(i + 1, rows, Pbuf, w, dot=2, out=ww)  # w -= P h, <w, w>
+                last_fused = True
+            else:
+                ops.multi_axpy(i + 1, rows, Pbuf, w)
+        for sweep in range(0 if cgs else nre):
             for j in range(i + 1):  # arnoldi.py:157-162
                 last = sweep == nre - 1 and j == i
                 if last:

@@ -17,6 +17,11 @@ on seeded inputs and stores its outputs in ``tests/golden/*.npz``;
 fixtures and against the reference's own known-answer vectors
 (reference ``tests/test_solvers.py:123-144``).
 
+One extension has no reference counterpart and therefore no pin: ``ortho="cgs<N>"``
+(classical Gram-Schmidt, ``ArnoldiMGS(classical=True)``) -- parity UNPINNED for it; the tests
+tie it to the pinned MGS results (same Krylov space => same residual history up to the loss of
+orthogonality, which they bound).
+
 Each function cites the reference file:line it restates (paths relative to
 /root/reference/src/krylov/).  The arithmetic order of the reference is kept
 (e.g. ``yk += alpha * p`` is a rounded product followed by a rounded add) so
@@ -247,11 +252,16 @@ class ArnoldiMGS:
     which may be None), the resolved inner product is used for the initial
     norm -- the solvers always pass ``inner`` so behaviour there is equal."""
 
-    def __init__(self, A, v, num_reorthos=1, M=None, Mv=None, Mv_norm=None, inner=None):
+    def __init__(self, A, v, num_reorthos=1, M=None, Mv=None, Mv_norm=None, inner=None,
+                 classical=False):
         self.inner = default_inner(v.shape) if inner is None else inner
         self.A = A
         self.v = v
         self.num_reorthos = num_reorthos
+        # classical=True is NOT in the reference: checker for the product's additive
+        # ortho="cgs<N>" extension (all projections of a pass taken from the same w).
+        # Parity for it is UNPINNED by construction; tests tie it to MGS instead.
+        self.classical = classical
         self.M = _as_op(M)
         self.dtype = np.result_type(np.dtype(A.dtype), np.dtype(self.M.dtype), v.dtype)
         self.iter = 0
@@ -275,6 +285,12 @@ class ArnoldiMGS:
         w = self.A @ self.V[k]  # arnoldi.py:176
         h = np.zeros([k + 2] + list(self.v.shape[1:]), dtype=self.dtype)
         for _ in range(self.num_reorthos):  # arnoldi.py:181-182
+            if self.classical:  # extension, see __init__
+                a_all = [self.inner(self.V[j], w) for j in range(k + 1)]
+                for j in range(k + 1):
+                    h[j] += a_all[j]
+                    w -= a_all[j] * self.P[j]
+                continue
             for j in range(k + 1):  # arnoldi.py:157-162
                 a = self.inner(self.V[j], w)
                 h[j] += a
@@ -644,6 +660,10 @@ def gmres(A, b, M=None, Ml=None, Mr=None, inner=None, ortho="mgs", x0=None,
     if ortho.startswith("mgs"):  # gmres.py:147-157
         nre = 1 if len(ortho) == 3 else int(ortho[3:])
         arn = ArnoldiMGS(op, r0, num_reorthos=nre, M=M, Mv=z0, Mv_norm=nrm0, inner=inner)
+    elif ortho.startswith("cgs"):  # extension (not in the reference): classical Gram-Schmidt
+        nre = 1 if len(ortho) == 3 else int(ortho[3:])
+        arn = ArnoldiMGS(op, r0, num_reorthos=nre, M=M, Mv=z0, Mv_norm=nrm0, inner=inner,
+                         classical=True)
     else:  # gmres.py:158-162
         assert ortho == "householder"
         assert not inner_given

@@ -288,3 +288,49 @@ def test_device_generator_equals_host_generator():
         np.testing.assert_array_equal(B.indptr, Ah.indptr)
         np.testing.assert_array_equal(B.indices, Ah.indices)
         np.testing.assert_array_equal(B.data, Ah.data)
+
+
+@pytest.mark.parametrize("k", [1, 3, 16, 64])
+@pytest.mark.parametrize("jc", [8, 16])
+def test_classical_gram_schmidt_kernels(k, jc):
+    """Tall-skinny V^T w (several basis vectors per pass over w) to rounding and bitwise
+    reproducible; w -= P h bit-identical to the NumPy statement (rounded product, rounded
+    subtraction, j ascending); the fused <w, w> to rounding."""
+    from krylov_b200._lib import lib
+
+    lib.kb_tune(9, jc)
+    try:
+        for n in (1, 777, 50001):
+            ops = Ops(n, k)
+            for cnt in (0, 1, 2, 5, 8, 9, 17, 33):
+                V = rng.standard_normal((max(cnt, 1), n, k))
+                w = rng.standard_normal((n, k))
+                Vd, wd = torch.from_numpy(V).cuda(), torch.from_numpy(w).cuda()
+                out = torch.full((max(cnt, 1) + 1, k), 7.0, dtype=torch.float64, device="cuda")
+                ops.multi_dot(cnt, Vd, wd, out)
+                got = out.cpu().numpy()
+                ref = np.einsum("jnk,nk->jk", V[:cnt], w)
+                scale = np.einsum("jnk,nk->jk", np.abs(V[:cnt]), np.abs(w))
+                assert np.all(np.abs(got[:cnt] - ref) <= 1e-12 * scale + 1e-300)
+                assert np.all(got[cnt:] == 7.0)                   # nothing beyond cnt rows touched
+                out2 = torch.zeros_like(out)
+                ops.multi_dot(cnt, Vd, wd, out2)
+                assert torch.equal(out2[:cnt], out[:cnt])         # run-to-run bitwise
+                # w -= sum_j h_j P_j
+                h = rng.standard_normal((max(cnt, 1), k))
+                hd = torch.from_numpy(h).cuda()
+                ww = torch.zeros((1, k), dtype=torch.float64, device="cuda")
+                wref = w.copy()
+                for j in range(cnt):
+                    wref -= h[j] * V[j]
+                w1 = wd.clone()
+                ops.multi_axpy(cnt, hd, Vd, w1)
+                np.testing.assert_array_equal(w1.cpu().numpy(), wref)
+                w2 = wd.clone()
+                ops.multi_axpy(cnt, hd, Vd, w2, dot=2, out=ww[0])
+                np.testing.assert_array_equal(w2.cpu().numpy(), wref)
+                nn = np.einsum("nk,nk->k", wref, wref)
+                assert np.all(np.abs(ww[0].cpu().numpy() - nn) <= 1e-13 * nn + 1e-300)
+            del ops
+    finally:
+        lib.kb_tune(9, 8)

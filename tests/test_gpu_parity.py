@@ -12,6 +12,7 @@ import os
 
 import numpy as np
 import pytest
+import scipy.sparse
 import torch
 
 import cases
@@ -403,3 +404,40 @@ def test_householder_matches_reference():
         np.testing.assert_allclose(H @ x, SML[f"house{i}_Hx"], rtol=0, atol=4e-15)
     with pytest.raises(AssertionError):
         kb.Householder(np.ones((4, 2)))
+
+
+@pytest.mark.parametrize("ortho", ["cgs", "cgs2"])
+@pytest.mark.parametrize("k", [1, 4])
+def test_gmres_classical_gram_schmidt_extension(ortho, k):
+    """ortho="cgs"/"cgs2" (additive: not in the reference, so the oracle statement of it is
+    unpinned).  Checked (1) against the oracle's classical variant, (2) against the PINNED
+    modified variant with the same number of passes -- same Krylov space, so the same residual
+    history up to the loss of orthogonality -- and (3) through the true residual."""
+    A = cases.st.convection_diffusion3d(10)
+    N = A.shape[0]
+    _, b = cases.rhs(A, (N,) if k == 1 else (N, k))
+    kw = dict(tol=1e-9, maxiter=120)
+    sol, info = kb.gmres(A, b, ortho=ortho, **kw)
+    so, io = orc.gmres(A, b, ortho=ortho, **kw)
+    sm, im = orc.gmres(A, b, ortho=ortho.replace("cgs", "mgs"), **kw)
+    assert info.success and io.success and im.success
+    assert abs(info.numsteps - io.numsteps) <= 1 and abs(info.numsteps - im.numsteps) <= 2
+    for other, tol in ((io, 1e-8), (im, 1e-6)):
+        m = min(info.numsteps, other.numsteps)
+        ro = np.asarray(other.resnorms, float)[:m]
+        rg = np.asarray(info.resnorms, float)[:m]
+        live = ro / ro[0] >= 1e-6
+        assert np.all(np.abs(rg - ro)[live] <= tol * ro[live])
+    assert np.linalg.norm(sol - so) <= 1e-8 * np.linalg.norm(so)
+    assert np.linalg.norm(sol - sm) <= 1e-7 * np.linalg.norm(sm)
+    r = b - A @ sol
+    assert np.all(np.linalg.norm(r.reshape(N, -1), axis=0)
+                  <= 1.0001e-9 * np.linalg.norm(b.reshape(N, -1), axis=0) + 1e-15)
+    # preconditioned: two bases (dots against V, subtraction with P)
+    M = scipy.sparse.diags(1.0 / (1.0 + np.arange(N) % 3)).tocsr()
+    sol, info = kb.gmres(A, b, M=M, ortho=ortho, **kw)
+    so, io = orc.gmres(A, b, M=M, ortho=ortho, **kw)
+    assert info.success and abs(info.numsteps - io.numsteps) <= 1
+    assert np.linalg.norm(sol - so) <= 1e-7 * np.linalg.norm(so)
+    with pytest.raises(ValueError):
+        kb.gmres(A, b, ortho=ortho, inner=lambda x, y: np.einsum("i...,i...->...", x, y))
