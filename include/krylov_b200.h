@@ -87,7 +87,12 @@ int kb_csr_destroy(kb_csr_t h);
 /* schedule: 0 = auto, 1 = row-wise generic kernel, 2 = TMA-staged stream kernel (k == 1),
  * 3 = TMA-staged stream kernel on offset-pattern compressed indices (k == 1; needs <= 16
  * distinct diagonals col-row and ascending columns, detected by kb_csr_create, which then
- * owns one 16-bit mask per row) */
+ * owns one 16-bit mask per row),
+ * 4 = "stencil": schedule 3 with constant diagonals (k == 1; <= 8 diagonals whose stored values
+ * are all bitwise equal, tested exactly by kb_csr_create): the <= 8 coefficients travel as kernel
+ * parameters and neither indices nor values are streamed.  Bit-identical to the other schedules.
+ * Schedules 3 and 4 snapshot structure (3) and values (4) at creation: a caller that rewrites
+ * colidx / vals in place must create a new handle. */
 int kb_csr_set_schedule(kb_csr_t h, int schedule);
 int kb_csr_get_info(kb_csr_t h, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
                     int* max_row_len, int* schedule);

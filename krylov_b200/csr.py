@@ -14,7 +14,7 @@ import torch
 from ._lib import check, lib
 from .device import Ops, as_device_matrix, cur_stream, ptr, require_cuda
 
-_SCHEDULES = {"auto": 0, "rowwise": 1, "stream": 2, "pattern": 3}
+_SCHEDULES = {"auto": 0, "rowwise": 1, "stream": 2, "pattern": 3, "stencil": 4}
 _PAD = 4  # elements readable past nnz (TMA tiles are 4-aligned windows)
 
 
@@ -117,7 +117,7 @@ class CsrMatrix:
                                   C.byref(sc)))
         return {"n_rows": nr.value, "n_cols": nc.value, "nnz": nz.value,
                 "max_row_len": mx.value,
-                "schedule": {1: "rowwise", 2: "stream", 3: "pattern"}[sc.value]}
+                "schedule": {1: "rowwise", 2: "stream", 3: "pattern", 4: "stencil"}[sc.value]}
 
     def set_schedule(self, name: str):
         check(lib.kb_csr_set_schedule(self.handle, _SCHEDULES[name]))
@@ -130,10 +130,14 @@ class CsrMatrix:
 
     def moved_bytes(self, k=1):
         """Bytes the chosen schedule actually streams per product: the offset-pattern
-        schedule replaces the 4-byte column index per nonzero by a 2-byte mask per row."""
+        schedule replaces the 4-byte column index per nonzero by a 2-byte mask per row; the
+        stencil schedule (constant diagonals) streams no matrix values or row pointers either."""
         n = self.shape[0]
-        if k == 1 and self.info()["schedule"] == "pattern":
+        sched = self.info()["schedule"]
+        if k == 1 and sched == "pattern":
             return 8 * self.nnz + 2 * n + 4 * (n + 1) + 16 * n
+        if k == 1 and sched == "stencil":
+            return 2 * n + 16 * n
         return self.spmv_bytes(k)
 
     def to_scipy(self):

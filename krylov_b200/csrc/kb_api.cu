@@ -27,12 +27,15 @@ struct kb_csr_s {
   const double* vals;
   int padded;
   int max_row_len;
-  int schedule;  // 1 row-wise, 2 TMA stream, 3 offset-pattern compressed TMA stream
+  int schedule;  // 1 row-wise, 2 TMA stream, 3 offset-pattern compressed TMA stream,
+                 // 4 stencil (offset pattern + constant diagonals: no value stream either)
   int forced;    // user override (0 = auto)
   // offset-pattern compression (library-owned): one 16-bit mask per row
   uint16_t* masks;
   KbPattern pat;
   int pattern_ok;
+  KbConstVals cv;  // one value per diagonal when constv
+  int constv;
 };
 
 
@@ -43,6 +46,8 @@ static int g_stream_cfg = 0;
 static int g_stream_ctas = 0;  // 0 = configuration default
 static int g_pattern_ctas = 0; // kb_tune key 3 (0 = default)
 static int g_window_cfg = 0;   // kb_tune key 4
+static int g_stencil_cfg = 0;   // kb_tune key 10: tile shape of the constant-diagonal kernel
+static int g_stencil_ctas = 0;  // kb_tune key 11: CTAs/SM cap of it (0 = occupancy limit)
 static int g_cgs_jc = 8;  // kb_tune key 9: basis vectors per multi-dot launch (8 or 16)
 static int g_rowwise_contig = -1;  // kb_tune key 5: -1 auto, 0 strided, 1 contiguous rows per block
 static int g_rowwise_ctas = 0;     // kb_tune key 6: CTAs/SM of the contiguous row-wise grid
@@ -138,6 +143,32 @@ static int kb_detect_pattern(kb_csr_s* h, cudaStream_t st) {
   return KB_OK;
 }
 
+// Constant-coefficient stencil?  Exact test: every stored value equals (64-bit compare) the
+// representative of its diagonal.  Only for the windowed kernel's reach (<= 8 diagonals).
+static int kb_detect_constdiag(kb_csr_s* h, cudaStream_t st) {
+  h->constv = 0;
+  if (!h->pattern_ok || h->pat.nd > 8 || h->pat.nw == 0 || h->nnz == 0) return KB_OK;
+  unsigned long long* d_c = nullptr;  // 16 representatives + fail flag
+  KB_CUDA(cudaMalloc(&d_c, sizeof(unsigned long long) * 17));
+  cudaError_t e = cudaMemsetAsync(d_c, 0, sizeof(unsigned long long) * 17, st);
+  int grid = (int)((h->n_rows + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  unsigned long long res[17];
+  if (e == cudaSuccess) {
+    kb_constdiag_fill_kernel<<<grid, 256, 0, st>>>(h->n_rows, h->rowptr, h->vals, h->masks, d_c);
+    kb_constdiag_check_kernel<<<grid, 256, 0, st>>>(h->n_rows, h->rowptr, h->vals, h->masks, d_c,
+                                                    reinterpret_cast<int*>(d_c + 16));
+    e = cudaMemcpyAsync(res, d_c, sizeof(res), cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_c);
+  if (e != cudaSuccess) return kb_fail(KB_ECUDA, "kb_detect_constdiag: %s", cudaGetErrorString(e));
+  if ((int)(res[16] & 0xffffffffull) != 0) return KB_OK;
+  for (int d = 0; d < 8; ++d) memcpy(&h->cv.c[d], &res[d], sizeof(double));
+  h->constv = 1;
+  return KB_OK;
+}
+
 extern "C" {
 
 int kb_version(void) { return 100; }
@@ -161,6 +192,8 @@ int kb_tune(int key, int value) {
     case 7: g_spmm_cfg = value; return KB_OK;
     case 8: g_tile_block = value; return KB_OK;
     case 9: g_cgs_jc = value; return KB_OK;
+    case 10: g_stencil_cfg = value; return KB_OK;
+    case 11: g_stencil_ctas = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -328,10 +361,11 @@ static void kb_csr_pick(kb_csr_s* h) {
   if (h->padded && h->n_rows >= 1 && h->n_rows < (1ll << 31) - 512 && mean <= 32.0 &&
       h->max_row_len <= 8 * (mean + 8.0))
     sched = 2;
-  if (sched == 2 && h->pattern_ok) sched = 3;
+  if (sched == 2 && h->pattern_ok) sched = h->constv ? 4 : 3;
   if (h->forced == 1) sched = 1;
   if (h->forced == 2 && h->padded) sched = 2;
   if (h->forced == 3 && h->pattern_ok) sched = 3;
+  if (h->forced == 4 && h->constv) sched = 4;
   h->schedule = sched;
 }
 
@@ -376,11 +410,14 @@ int kb_csr_create(kb_csr_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz,
   }
   h->masks = nullptr;
   h->pattern_ok = 0;
+  h->constv = 0;
   h->pat.nd = 0;
   if (padded && n_rows > 0 && n_rows < (1ll << 31) - 1024 && n_cols < (1ll << 31) &&
       h->max_row_len >= 1 && h->max_row_len <= 16) {
     int rc = kb_detect_pattern(h, S(stream));
+    if (rc == KB_OK) rc = kb_detect_constdiag(h, S(stream));
     if (rc != KB_OK) {
+      if (h->masks) cudaFree(h->masks);
       delete h;
       return rc;
     }
@@ -398,7 +435,10 @@ int kb_csr_destroy(kb_csr_t h) {
 
 int kb_csr_set_schedule(kb_csr_t h, int schedule) {
   KB_REQUIRE(h != nullptr, "null matrix");
-  KB_REQUIRE(schedule >= 0 && schedule <= 3, "schedule must be 0, 1, 2 or 3");
+  KB_REQUIRE(schedule >= 0 && schedule <= 4, "schedule must be 0 ... 4");
+  if (schedule == 4 && !h->constv)
+    return kb_fail(KB_EUNSUPPORTED,
+                   "stencil schedule needs <= 8 diagonals with one constant value each");
   if (schedule == 2 && !h->padded)
     return kb_fail(KB_EUNSUPPORTED, "stream schedule needs padded, 16-byte aligned CSR arrays");
   if (schedule == 3 && !h->pattern_ok)
@@ -488,18 +528,18 @@ static int kb_launch_pattern_cfg(kb_csr_s* A, kb_ws_s* ws, const double* x, doub
   return KB_OK;
 }
 
-template <int ROWS, int STAGES, int MINB, int DOT>
+template <int ROWS, int STAGES, int MINB, int DOT, bool CONSTV>
 static int kb_launch_window_cfg(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
                                 const double* z, const double* coef, const double* w, double* out,
                                 cudaStream_t st) {
   static int max_smem[64] = {0};  // per device: opt-in dynamic shared memory limit once set
-  auto kern = kb_spmv_window_kernel<ROWS, STAGES, MINB, DOT>;
+  auto kern = kb_spmv_window_kernel<ROWS, STAGES, MINB, DOT, CONSTV>;
   int dev = 0;
   KB_CUDA(cudaGetDevice(&dev));
   // stage buffers sized from the actual pattern
   int span = 0;
   for (int g = 0; g < A->pat.nw; ++g) span = A->pat.wspan[g] > span ? A->pat.wspan[g] : span;
-  const int cap = (ROWS * A->pat.nd + 8 + 3) & ~3;
+  const int cap = CONSTV ? 0 : ((ROWS * A->pat.nd + 8 + 3) & ~3);
   const int wlen = (ROWS + span + 6 + 1) & ~1;
   const size_t smem = ((size_t)STAGES * cap + (size_t)STAGES * A->pat.nw * wlen) * 8 + 16 * STAGES;
   if (dev < 0 || dev >= 64 || max_smem[dev] == 0) {
@@ -512,6 +552,7 @@ static int kb_launch_window_cfg(kb_csr_s* A, kb_ws_s* ws, const double* x, doubl
   int ctas = 0;
   KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, ROWS + 32, smem));
   if (ctas < 1) return kb_fail(KB_EUNSUPPORTED, "windowed SpMV: stage buffers do not fit");
+  if (CONSTV && g_stencil_ctas > 0 && g_stencil_ctas < ctas) ctas = g_stencil_ctas;
   if (g_pattern_ctas > 0 && g_pattern_ctas < ctas) ctas = g_pattern_ctas;
   const int n_tiles = (int)((A->n_rows + ROWS - 1) / ROWS);
   int grid = ws->num_sms * ctas;
@@ -537,7 +578,7 @@ static int kb_launch_window_cfg(kb_csr_s* A, kb_ws_s* ws, const double* x, doubl
     }
   }
   kern<<<grid, ROWS + 32, smem, st>>>((int)A->n_rows, (int)A->n_cols, n_tiles, cap, wlen, ord, A->rowptr,
-                                      A->masks, A->vals, A->pat, x, y, mode, z, coef, w, out,
+                                      A->masks, A->vals, A->pat, A->cv, x, y, mode, z, coef, w, out,
                                       kb_red(ws));
   KB_LAUNCH_CHECK();
   return KB_OK;
@@ -555,14 +596,29 @@ static int kb_launch_window(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y
   // measured (profiles/r1_window_sweep.txt): 512-row tiles win by ~4 % on the 512^3 matrix,
   // 256-row tiles (4 CTAs/SM) at 256^3 and below
   if (g_window_cfg == 0 && A->n_rows > (40ll << 20))
-    return kb_launch_window_cfg<512, 2, 2, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    return kb_launch_window_cfg<512, 2, 2, DOT, false>(A, ws, x, y, mode, z, coef, w, out, st);
   switch (g_window_cfg) {
-    case 1: return kb_launch_window_cfg<256, 3, 3, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
-    case 2: return kb_launch_window_cfg<512, 2, 2, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
-    case 3: return kb_launch_window_cfg<128, 2, 7, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
-    case 4: return kb_launch_window_cfg<128, 3, 6, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
-    case 5: return kb_launch_window_cfg<256, 2, 5, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
-    default: return kb_launch_window_cfg<256, 2, 4, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 1: return kb_launch_window_cfg<256, 3, 3, DOT, false>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 2: return kb_launch_window_cfg<512, 2, 2, DOT, false>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 3: return kb_launch_window_cfg<128, 2, 7, DOT, false>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 4: return kb_launch_window_cfg<128, 3, 6, DOT, false>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 5: return kb_launch_window_cfg<256, 2, 5, DOT, false>(A, ws, x, y, mode, z, coef, w, out, st);
+    default: return kb_launch_window_cfg<256, 2, 4, DOT, false>(A, ws, x, y, mode, z, coef, w, out, st);
+  }
+}
+
+// constant diagonals: x windows only (no value stream), more stages fit
+template <int DOT>
+static int kb_launch_stencil(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                             const double* z, const double* coef, const double* w, double* out,
+                             cudaStream_t st) {
+  switch (g_stencil_cfg) {
+    case 1: return kb_launch_window_cfg<256, 2, 4, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 2: return kb_launch_window_cfg<512, 2, 2, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 3: return kb_launch_window_cfg<512, 3, 2, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 4: return kb_launch_window_cfg<256, 4, 4, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 5: return kb_launch_window_cfg<128, 4, 8, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
+    default: return kb_launch_window_cfg<256, 3, 4, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
   }
 }
 
@@ -637,12 +693,17 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
     if (dot) KB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * k, st));
     return KB_OK;
   }
-  if (k == 1 && A->schedule == 3 && g_window_cfg >= 0 && kb_window_ok(A, x)) {
+  if (k == 1 && A->schedule == 4 && kb_window_ok(A, x)) {
+    if (dot == 0) return kb_launch_stencil<0>(A, ws, x, y, mode, z, coef, w, out, st);
+    if (dot == 1) return kb_launch_stencil<1>(A, ws, x, y, mode, z, coef, w, out, st);
+    return kb_launch_stencil<2>(A, ws, x, y, mode, z, coef, w, out, st);
+  }
+  if (k == 1 && A->schedule >= 3 && g_window_cfg >= 0 && kb_window_ok(A, x)) {
     if (dot == 0) return kb_launch_window<0>(A, ws, x, y, mode, z, coef, w, out, st);
     if (dot == 1) return kb_launch_window<1>(A, ws, x, y, mode, z, coef, w, out, st);
     return kb_launch_window<2>(A, ws, x, y, mode, z, coef, w, out, st);
   }
-  if (k == 1 && A->schedule == 3) {
+  if (k == 1 && A->schedule >= 3) {
     if (dot == 0) return kb_launch_pattern<0>(A, ws, x, y, mode, z, coef, w, out, st);
     if (dot == 1) return kb_launch_pattern<1>(A, ws, x, y, mode, z, coef, w, out, st);
     return kb_launch_pattern<2>(A, ws, x, y, mode, z, coef, w, out, st);

@@ -376,6 +376,49 @@ kb_pattern_build_kernel(int64_t n_rows, const int32_t* __restrict__ rowptr,
   }
 }
 
+// Constant diagonals ("stencil" schedule).  On constant-coefficient stencils every entry of a
+// diagonal carries the same value (boundary rows only lack entries, which the mask records), so
+// the 8 B/nonzero value stream can go too: <= 8 doubles travel as kernel parameters and the
+// product streams 2 (mask) + 8 (x) + 8 (y) bytes per row.  Same products in the same order with
+// bitwise the same values -> bit-identical result.  Detection is exact (64-bit compare of every
+// stored value against its diagonal's representative) and runs once in kb_csr_create.
+struct KbConstVals {
+  double c[8];
+};
+
+__global__ void __launch_bounds__(256)
+kb_constdiag_fill_kernel(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                         const double* __restrict__ vals, const uint16_t* __restrict__ masks,
+                         unsigned long long* cbits) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
+       row += (int64_t)gridDim.x * blockDim.x) {
+    int j = rowptr[row];
+    const unsigned m = masks[row];
+    for (int d = 0; d < 16; ++d)
+      if ((m >> d) & 1u) cbits[d] = (unsigned long long)__double_as_longlong(vals[j++]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kb_constdiag_check_kernel(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                          const double* __restrict__ vals, const uint16_t* __restrict__ masks,
+                          const unsigned long long* __restrict__ cbits, int* fail) {
+  unsigned long long c[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) c[d] = cbits[d];
+  bool bad = false;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
+       row += (int64_t)gridDim.x * blockDim.x) {
+    int j = rowptr[row];
+    const unsigned m = masks[row];
+#pragma unroll
+    for (int d = 0; d < 16; ++d)
+      if ((m >> d) & 1u)
+        bad |= (unsigned long long)__double_as_longlong(vals[j++]) != c[d];
+  }
+  if (bad) *fail = 1;
+}
+
 template <int STAGES, int CAP>
 struct KbPatternSmem {
   double vals[STAGES][CAP];
@@ -565,11 +608,13 @@ __device__ __forceinline__ int kb_tile_of(int i, const KbTileOrder& o) {
 // Shared memory (dynamic, sized by the host from the actual pattern so that as many
 // CTAs as possible are resident):  vals[STAGES][cap] | win[STAGES][nw][wlen] | barriers
 // cap = 4-aligned (ROWS * nd + 8), wlen = even (ROWS + max span + 6).
-template <int ROWS, int STAGES, int MINB, int DOT>
+// CONSTV (constant diagonals): no value stream and no row pointers at all -- cap == 0, the stage
+// buffers hold x windows only, the coefficients come from `cv`.
+template <int ROWS, int STAGES, int MINB, int DOT, bool CONSTV>
 __global__ void __launch_bounds__(ROWS + 32, MINB)
 kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen, KbTileOrder ord,
                       const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ masks,
-                      const double* __restrict__ vals, KbPattern pat,
+                      const double* __restrict__ vals, KbPattern pat, KbConstVals cv,
                       const double* __restrict__ x, double* __restrict__ y, int mode,
                       const double* __restrict__ z, const double* __restrict__ coef,
                       const double* __restrict__ w, double* __restrict__ out, KbRed rd) {
@@ -605,8 +650,8 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen, Kb
     const uint64_t pol_keep = kb_policy_evict_last();     // x windows: re-read by later tiles
     for (int64_t base = blockIdx.x; base < n_tiles; base += 32ll * gridDim.x) {
       const int64_t my_tile = base + (int64_t)lane * gridDim.x;  // position in the visiting order
-      int my_s = 0, my_e = 0;
-      if (my_tile < n_tiles) {
+      int my_s = 0, my_e = CONSTV ? 1 : 0;
+      if (!CONSTV && my_tile < n_tiles) {
         const int r0 = kb_tile_of((int)my_tile, ord) * ROWS;
         const int r1 = min(r0 + ROWS, n_rows);
         my_s = rowptr[r0];
@@ -619,7 +664,7 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen, Kb
         const int e = __shfl_sync(0xffffffffu, my_e, q);
         if (lane == 0 && e > s) {
           const int r0 = kb_tile_of((int)tile, ord) * ROWS;
-          const int a0 = s & ~3, a1 = (e + 3) & ~3;  // <= ROWS*nd + 6 <= cap entries
+          const int a0 = s & ~3, a1 = CONSTV ? a0 : ((e + 3) & ~3);  // <= ROWS*nd + 6 <= cap entries
           kb_mbar_wait(&s_empty[stage], phase ^ 1u);
           uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
           for (int g = 0; g < nw; ++g) {  // pass 1: transaction size
@@ -628,8 +673,9 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen, Kb
             bytes += (uint32_t)gn * 8u;  // n_cols is even: the rounded end stays in bounds
           }
           kb_mbar_expect_tx(&s_full[stage], bytes);
-          kb_bulk_g2s_hint(s_vals + (size_t)stage * cap, vals + a0, (uint32_t)(a1 - a0) * 8u,
-                           &s_full[stage], pol_stream);
+          if (!CONSTV)
+            kb_bulk_g2s_hint(s_vals + (size_t)stage * cap, vals + a0, (uint32_t)(a1 - a0) * 8u,
+                             &s_full[stage], pol_stream);
           for (int g = 0; g < nw; ++g) {  // pass 2: issue
             const int ge = min(r0 + pat.wlo[g] + ROWS + pat.wspan[g], n_cols);
             const int ga = kb_win_start(r0, pat.wlo[g]);
@@ -651,16 +697,18 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen, Kb
     uint32_t phase = 0;
     const double cf = (mode == 1) ? coef[0] : 0.0;
     int tile = blockIdx.x;
-    int lo_n = 0, s_n = 0, e_n = 0;
+    int lo_n = 0, s_n = 0, e_n = CONSTV ? 1 : 0;
     unsigned m_n = 0;
     if (tile < n_tiles) {
       const int r0 = kb_tile_of(tile, ord) * ROWS;
       const int r1 = min(r0 + ROWS, n_rows);
       const int row = r0 + tid;
-      s_n = rowptr[r0];
-      e_n = rowptr[r1];
+      if (!CONSTV) {
+        s_n = rowptr[r0];
+        e_n = rowptr[r1];
+      }
       if (row < n_rows) {
-        lo_n = rowptr[row];
+        if (!CONSTV) lo_n = rowptr[row];
         m_n = masks[row];
       }
     }
@@ -675,14 +723,17 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen, Kb
           const int q0 = kb_tile_of(nt, ord) * ROWS;
           const int q1 = min(q0 + ROWS, n_rows);
           const int qrow = q0 + tid;
-          s_n = rowptr[q0];
-          e_n = rowptr[q1];
+          if (!CONSTV) {
+            s_n = rowptr[q0];
+            e_n = rowptr[q1];
+          }
           lo_n = 0;
           m_n = 0;
           if (qrow < n_rows) {
-            lo_n = rowptr[qrow];
+            if (!CONSTV) lo_n = rowptr[qrow];
             m_n = masks[qrow];
           }
+          (void)q1;
         }
       }
       // epilogue operands do not depend on the tile data: fetch them early
@@ -702,7 +753,7 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen, Kb
           if (d < pat.nd && (mask >> d) & 1u) {
             const int idx = row + pat.off[d] - kb_win_start(r0, pat.dwlo[d]);
             const double xv = sw[pat.grp[d] * wlen + idx];
-            sum = __dadd_rn(sum, __dmul_rn(sv[j], xv));
+            sum = __dadd_rn(sum, __dmul_rn(CONSTV ? cv.c[d] : sv[j], xv));
             ++j;
           }
         }

@@ -33,12 +33,13 @@ def _mats():
 def test_spmv_bit_exact_vs_scipy(name, A, k):
     x = rng.standard_normal((A.shape[1], k)) if k > 1 else rng.standard_normal(A.shape[1])
     ref = A @ x
-    for sched in ("rowwise", "stream", "pattern", "auto"):
+    for sched in ("rowwise", "stream", "pattern", "stencil", "auto"):
         Ad = kb.CsrMatrix.from_scipy(A)
         try:
             Ad.set_schedule(sched)
         except kb.KrylovB200Error:
-            assert sched == "pattern"  # not stencil-like: the library refuses, CSR schedules stay
+            # not stencil-like / not constant-coefficient: the library refuses, CSR schedules stay
+            assert sched in ("pattern", "stencil")
             continue
         np.testing.assert_array_equal(Ad @ x, ref)
 
@@ -57,6 +58,8 @@ def test_pattern_kernel_variants_bit_exact(cfg):
                 st.to_scipy(st.stencil7_csr(2, 2, 300)), st.to_scipy(st.stencil5_csr(700, 3))]
         for A in mats:
             Ad = kb.CsrMatrix.from_scipy(A)
+            assert Ad.info()["schedule"] in ("pattern", "stencil")
+            Ad.set_schedule("pattern")
             assert Ad.info()["schedule"] == "pattern"
             n = A.shape[0]
             x = rng.standard_normal(n)
@@ -93,7 +96,7 @@ def test_cache_blocked_tile_order_bit_exact(cfg, block):
     try:
         for (nx, ny, nz) in ((32, 32, 5), (64, 16, 3), (32, 16, 7)):
             A = st.to_scipy(st.stencil7_csr(nx, ny, nz, coeffs=st.convdiff_coeffs()))
-            Ad = kb.CsrMatrix.from_scipy(A)
+            Ad = kb.CsrMatrix.from_scipy(A).set_schedule("pattern")
             assert Ad.info()["schedule"] == "pattern"
             n = A.shape[0]
             x, z = rng.standard_normal(n), rng.standard_normal(n)
@@ -145,10 +148,22 @@ def test_windowed_spmm_variants_bit_exact(cfg, k):
 
 
 def test_pattern_schedule_selection():
-    """Offset-pattern compression is chosen for stencil-like matrices only."""
-    assert kb.CsrMatrix.from_scipy(st.poisson3d(9)).info()["schedule"] == "pattern"
-    assert kb.CsrMatrix.from_scipy(st.poisson2d(40)).info()["schedule"] == "pattern"
-    assert kb.CsrMatrix.from_scipy(st.convection_diffusion3d(8)).info()["schedule"] == "pattern"
+    """Offset-pattern compression is chosen for stencil-like matrices only, and the value
+    stream is dropped only when every diagonal is bitwise constant."""
+    assert kb.CsrMatrix.from_scipy(st.poisson3d(9)).info()["schedule"] == "stencil"
+    assert kb.CsrMatrix.from_scipy(st.poisson2d(40)).info()["schedule"] == "stencil"
+    assert kb.CsrMatrix.from_scipy(st.convection_diffusion3d(8)).info()["schedule"] == "stencil"
+    assert kb.CsrMatrix.from_scipy(st.shifted_laplace3d(8)).info()["schedule"] == "stencil"
+    # one value off by one ulp, or a signed zero: variable coefficients -> values are streamed
+    for pos, val in ((17, np.nextafter(-1.0, 0.0)), (401, None)):
+        P = st.poisson3d(9).tocsr()
+        P.data[pos] = np.nextafter(P.data[pos], 0.0) if val is None else val
+        Pd = kb.CsrMatrix.from_scipy(P)
+        assert Pd.info()["schedule"] == "pattern"
+        with pytest.raises(kb.KrylovB200Error):
+            Pd.set_schedule("stencil")
+        xx = rng.standard_normal(P.shape[0])
+        np.testing.assert_array_equal(Pd @ xx, P @ xx)
     R = scipy.sparse.random(3000, 3000, density=0.003, random_state=1, format="csr")
     assert kb.CsrMatrix.from_scipy(R).info()["schedule"] == "stream"
     # 27 diagonals (> 16): stays on the CSR stream kernel
@@ -170,7 +185,51 @@ def test_pattern_schedule_selection():
     np.testing.assert_array_equal(Ud @ x, U @ x)
 
 
-@pytest.mark.parametrize("sched", ["rowwise", "stream", "pattern"])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5])
+def test_stencil_kernel_variants_bit_exact(cfg):
+    """Constant-diagonal ("stencil") schedule: no index, value or row-pointer stream -- the
+    coefficients are kernel parameters.  Every tile configuration, ragged grids, fused
+    epilogues, misaligned x (falls back to the kernels that stream values): bit-identical to
+    SciPy and to the "pattern" / "stream" schedules."""
+    from krylov_b200._lib import lib
+
+    lib.kb_tune(10, cfg)
+    try:
+        mats = [st.poisson3d(8), st.poisson3d(7), st.poisson2d(64), st.poisson2d(33),
+                st.convection_diffusion3d(12), st.shifted_laplace3d(9),
+                st.to_scipy(st.stencil7_csr(40, 6, 4)), st.to_scipy(st.stencil7_csr(2, 2, 300)),
+                st.to_scipy(st.stencil5_csr(700, 3)),
+                st.to_scipy(st.stencil7_csr(64, 16, 9, coeffs=st.convdiff_coeffs()))]
+        for A in mats:
+            Ad = kb.CsrMatrix.from_scipy(A)
+            assert Ad.info()["schedule"] == "stencil"
+            n = A.shape[0]
+            x = rng.standard_normal(n)
+            ref = A @ x
+            np.testing.assert_array_equal(Ad @ x, ref)
+            big = torch.from_numpy(np.concatenate([[0.0], x])).cuda()
+            np.testing.assert_array_equal(Ad.matvec_device(big[1:]).cpu().numpy(), ref)
+            ops = Ops(n, 1)
+            z, w = rng.standard_normal(n), rng.standard_normal(n)
+            xd, zd, wd = (torch.from_numpy(a).cuda().reshape(n, 1) for a in (x, z, w))
+            cf = torch.tensor([0.37], dtype=torch.float64, device="cuda")
+            yd = torch.empty_like(xd)
+            out = ops.slots(2)
+            for mode, r in ((0, ref), (1, ref - 0.37 * z), (2, z - ref)):
+                ops.spmv(Ad, xd, yd, mode=mode, z=zd, coef=cf, dot=1, w=wd, out=out[0])
+                np.testing.assert_array_equal(yd.cpu().numpy().ravel(), r)
+                np.testing.assert_allclose(out[0].cpu().numpy()[0], w @ r, rtol=1e-12, atol=1e-12)
+                ops.spmv(Ad, xd, yd, mode=mode, z=zd, coef=cf, dot=2, out=out[1])
+                np.testing.assert_allclose(out[1].cpu().numpy()[0], r @ r, rtol=1e-13)
+            # same bits as the schedules that stream the values
+            for other in ("pattern", "stream", "rowwise"):
+                Ao = kb.CsrMatrix.from_scipy(A).set_schedule(other)
+                assert torch.equal(Ao.matvec_device(xd), Ad.matvec_device(xd))
+    finally:
+        lib.kb_tune(10, 0)
+
+
+@pytest.mark.parametrize("sched", ["rowwise", "stream", "pattern", "stencil"])
 @pytest.mark.parametrize("k", [1, 4])
 def test_spmv_fused_modes(sched, k):
     A = st.convection_diffusion3d(9)
