@@ -47,6 +47,7 @@ static int g_stream_ctas = 0;  // 0 = configuration default
 static int g_pattern_ctas = 0; // kb_tune key 3 (0 = default)
 static int g_window_cfg = 0;   // kb_tune key 4
 static int g_stencil_cfg = 0;   // kb_tune key 10: tile shape of the constant-diagonal kernel
+static int g_stencil_l2pol = 0; // kb_tune key 12: L2 hint of the x windows (0 evict_last, 1 none, 2 evict_first)
 static int g_stencil_ctas = 0;  // kb_tune key 11: CTAs/SM cap of it (0 = occupancy limit)
 static int g_cgs_jc = 8;  // kb_tune key 9: basis vectors per multi-dot launch (8 or 16)
 static int g_rowwise_contig = -1;  // kb_tune key 5: -1 auto, 0 strided, 1 contiguous rows per block
@@ -194,6 +195,7 @@ int kb_tune(int key, int value) {
     case 9: g_cgs_jc = value; return KB_OK;
     case 10: g_stencil_cfg = value; return KB_OK;
     case 11: g_stencil_ctas = value; return KB_OK;
+    case 12: g_stencil_l2pol = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -607,18 +609,126 @@ static int kb_launch_window(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y
   }
 }
 
-// constant diagonals: x windows only (no value stream), more stages fit
+// constant diagonals: x windows only, no matrix stream (kb_spmv_stencil_kernel)
+template <int RPT, int STAGES, int MINB, int DOT>
+static int kb_launch_stencil_cfg(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                                 const double* z, const double* coef, const double* w,
+                                 double* out, cudaStream_t st) {
+  static int max_smem[64] = {0};
+  auto kern = kb_spmv_stencil_kernel<RPT, STAGES, MINB, DOT>;
+  constexpr int TR = 256 * RPT;
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  int span = 0;
+  for (int g = 0; g < A->pat.nw; ++g) span = A->pat.wspan[g] > span ? A->pat.wspan[g] : span;
+  const int wlen = (TR + span + 6 + 1) & ~1;
+  const size_t smem = (size_t)STAGES * A->pat.nw * wlen * 8 + 16 * STAGES;
+  if (dev < 0 || dev >= 64 || max_smem[dev] == 0) {
+    int lim = 0;
+    KB_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lim - 8 * 1024));
+    if (dev >= 0 && dev < 64) max_smem[dev] = lim - 8 * 1024;
+  }
+  int ctas = 0;
+  KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 288, smem));
+  if (ctas < 1) return kb_fail(KB_EUNSUPPORTED, "stencil SpMV: stage buffers do not fit");
+  if (g_stencil_ctas > 0 && g_stencil_ctas < ctas) ctas = g_stencil_ctas;
+  const int n_tiles = (int)((A->n_rows + TR - 1) / TR);
+  int grid = ws->num_sms * ctas;
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
+  int d_center = -1, center_base = 0;  // <w, y> with w == x: the operand is in the centre window
+  if (DOT == 1 && w == x)
+    for (int d = 0; d < A->pat.nd; ++d)
+      if (A->pat.off[d] == 0) {
+        d_center = d;
+        center_base = A->pat.grp[d] * wlen - A->pat.dwlo[d] + (A->pat.dwlo[d] & 1);
+      }
+  kern<<<grid, 288, smem, st>>>((int)A->n_rows, (int)A->n_cols, n_tiles, wlen, A->masks, A->pat,
+                                A->cv, x, y, mode, z, coef, w, d_center, center_base,
+                                g_stencil_l2pol, out, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+// second version (kb_spmv_stencil2_kernel): the number of diagonals is a template parameter
+template <int ND, int RPT, int STAGES, int MINB, int DOT, bool WX>
+static int kb_launch_stencil2_wx(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                                 const double* z, const double* coef, const double* w,
+                                 double* out, cudaStream_t st) {
+  static int max_smem[64] = {0};
+  auto kern = kb_spmv_stencil2_kernel<ND, RPT, STAGES, MINB, DOT, WX>;
+  constexpr int TR = 256 * RPT;
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  int span = 0;
+  for (int g = 0; g < A->pat.nw; ++g) span = A->pat.wspan[g] > span ? A->pat.wspan[g] : span;
+  const int wlen = (TR + span + 6 + 1) & ~1;
+  const size_t smem = (size_t)STAGES * A->pat.nw * wlen * 8 + 16 * STAGES;
+  if (dev < 0 || dev >= 64 || max_smem[dev] == 0) {
+    int lim = 0;
+    KB_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lim - 8 * 1024));
+    if (dev >= 0 && dev < 64) max_smem[dev] = lim - 8 * 1024;
+  }
+  int ctas = 0;
+  KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 288, smem));
+  if (ctas < 1) return kb_fail(KB_EUNSUPPORTED, "stencil SpMV: stage buffers do not fit");
+  if (g_stencil_ctas > 0 && g_stencil_ctas < ctas) ctas = g_stencil_ctas;
+  const int n_tiles = (int)((A->n_rows + TR - 1) / TR);
+  int grid = ws->num_sms * ctas;
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
+  kern<<<grid, 288, smem, st>>>((int)A->n_rows, (int)A->n_cols, n_tiles, wlen, A->masks, A->pat,
+                                A->cv, x, y, mode, z, coef, w, g_stencil_l2pol, out, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+template <int ND, int RPT, int STAGES, int MINB, int DOT>
+static int kb_launch_stencil2_cfg(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                                  const double* z, const double* coef, const double* w,
+                                  double* out, cudaStream_t st) {
+  // <w, y> with w == x and a main diagonal in the middle of the pattern: the dot operand is the
+  // value the row sum loads anyway
+  if (DOT == 1 && w == x && (ND & 1) && A->pat.off[ND / 2] == 0)
+    return kb_launch_stencil2_wx<ND, RPT, STAGES, MINB, DOT, (DOT == 1)>(A, ws, x, y, mode, z, coef,
+                                                                         w, out, st);
+  return kb_launch_stencil2_wx<ND, RPT, STAGES, MINB, DOT, false>(A, ws, x, y, mode, z, coef, w,
+                                                                  out, st);
+}
+
+template <int ND, int DOT>
+static int kb_launch_stencil2(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                              const double* z, const double* coef, const double* w, double* out,
+                              cudaStream_t st) {
+  switch (g_stencil_cfg) {
+    case 1: return kb_launch_stencil2_cfg<ND, 2, 3, 4, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 2: return kb_launch_stencil2_cfg<ND, 1, 3, 6, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 3: return kb_launch_stencil2_cfg<ND, 4, 2, 2, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 4: return kb_launch_stencil2_cfg<ND, 2, 2, 5, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 5: return kb_launch_stencil2_cfg<ND, 4, 2, 3, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    default: return kb_launch_stencil2_cfg<ND, 2, 2, 4, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+  }
+}
+
+// kb_tune key 10: 0-5 second version (5 or 7 diagonals), 6 the generic windowed kernel with
+// constant values (the first implementation), 7-9 kb_spmv_stencil_kernel (any <= 8 diagonals)
 template <int DOT>
 static int kb_launch_stencil(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
                              const double* z, const double* coef, const double* w, double* out,
                              cudaStream_t st) {
+  if (g_stencil_cfg <= 5 && A->pat.nd == 7)
+    return kb_launch_stencil2<7, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+  if (g_stencil_cfg <= 5 && A->pat.nd == 5)
+    return kb_launch_stencil2<5, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
   switch (g_stencil_cfg) {
-    case 1: return kb_launch_window_cfg<256, 2, 4, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
-    case 2: return kb_launch_window_cfg<512, 2, 2, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
-    case 3: return kb_launch_window_cfg<512, 3, 2, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
-    case 4: return kb_launch_window_cfg<256, 4, 4, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
-    case 5: return kb_launch_window_cfg<128, 4, 8, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
-    default: return kb_launch_window_cfg<256, 3, 4, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 6: return kb_launch_window_cfg<256, 3, 4, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 8: return kb_launch_stencil_cfg<2, 3, 3, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    case 9: return kb_launch_stencil_cfg<1, 3, 6, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    default: return kb_launch_stencil_cfg<2, 2, 4, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
   }
 }
 

@@ -777,6 +777,365 @@ kb_spmv_window_kernel(int n_rows, int n_cols, int n_tiles, int cap, int wlen, Kb
   if (DOT != 0) kb_grid_colsum(acc, 1, rd, out, red_sm);
 }
 
+// ------------------------------------------ constant-diagonal stencil kernel ---
+// The windowed kernel without any matrix stream (see KbConstVals): 256 consumer threads own
+// RPT rows each of a (256 * RPT)-row tile, one producer lane TMA-copies the x windows.
+// Measured on the windowed kernel run with constant values (profiles/prof_stencil512_r1*):
+// ~200 instructions per row-warp at 68 % issue utilisation -- instruction-bound, not
+// memory-bound.  So everything that does not depend on the tile is hoisted (one shared-memory
+// offset per diagonal and thread) and interior warps (all masks full: 98.8 % of the rows at
+// 512^3) run a branch-free 7 x (LDS, DMUL, DADD) sequence; boundary warps keep the masked
+// generic path.  Products and their order are unchanged -> bit-identical.
+// With WX (w aliases x, the CG case <p, A p>) the dot operand comes from the centre window.
+template <int RPT, int STAGES, int MINB, int DOT>
+__global__ void __launch_bounds__(256 + 32, MINB)
+kb_spmv_stencil_kernel(int n_rows, int n_cols, int n_tiles, int wlen,
+                       const uint16_t* __restrict__ masks, KbPattern pat, KbConstVals cv,
+                       const double* __restrict__ x, double* __restrict__ y, int mode,
+                       const double* __restrict__ z, const double* __restrict__ coef,
+                       const double* __restrict__ w, int d_center, int center_base, int l2pol,
+                       double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  constexpr int TR = 256 * RPT;
+  extern __shared__ __align__(128) unsigned char kb_dyn_smem[];
+  double* const s_win = reinterpret_cast<double*>(kb_dyn_smem);
+  const int nw = pat.nw;
+  uint64_t* const s_full = reinterpret_cast<uint64_t*>(s_win + (size_t)STAGES * nw * wlen);
+  uint64_t* const s_empty = s_full + STAGES;
+  __shared__ double red_sm[256 + 32];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      kb_mbar_init(&s_full[s], 1);
+      kb_mbar_init(&s_empty[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc = 0.0;
+  if (warp == 8) {
+    if ((tid & 31) == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      // x windows are re-read by later tiles: evict_last (kb_tune 12: 1 = no hint, 2 = evict_first)
+      const uint64_t pol_keep = l2pol == 2 ? kb_policy_evict_first() : kb_policy_evict_last();
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int r0 = tile * TR;
+        kb_mbar_wait(&s_empty[stage], phase ^ 1u);
+        uint32_t bytes = 0;
+        for (int g = 0; g < nw; ++g) {
+          const int ge = min(r0 + pat.wlo[g] + TR + pat.wspan[g], n_cols);
+          bytes += (uint32_t)max(((ge + 1) & ~1) - kb_win_start(r0, pat.wlo[g]), 0) * 8u;
+        }
+        kb_mbar_expect_tx(&s_full[stage], bytes);
+        for (int g = 0; g < nw; ++g) {
+          const int ge = min(r0 + pat.wlo[g] + TR + pat.wspan[g], n_cols);
+          const int ga = kb_win_start(r0, pat.wlo[g]);
+          const int gn = max(((ge + 1) & ~1) - ga, 0);
+          if (gn > 0) {
+            if (l2pol == 1)
+              kb_bulk_g2s(s_win + ((size_t)stage * nw + g) * wlen, x + ga, (uint32_t)gn * 8u,
+                          &s_full[stage]);
+            else
+              kb_bulk_g2s_hint(s_win + ((size_t)stage * nw + g) * wlen, x + ga, (uint32_t)gn * 8u,
+                               &s_full[stage], pol_keep);
+          }
+        }
+        if (bytes == 0) kb_mbar_arrive(&s_full[stage]);  // (cannot happen: n_cols > 0)
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    const int nd = pat.nd;
+    const unsigned full = (1u << nd) - 1u;
+    // shared-memory index of diagonal d for this thread's row q = 0, valid while the windows
+    // are not clamped at 0 (r0 + wlo >= 0; r0 is even): idx = row + off - ((r0 + wlo) & ~1)
+    int so[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+      so[d] = pat.grp[d] * wlen + tid + pat.off[d] - pat.dwlo[d] + (pat.dwlo[d] & 1);
+    const bool wx = DOT == 1 && d_center >= 0;
+    const int sc = center_base + tid;  // so[d_center], computed by the host
+    const double cf = (mode == 1) ? coef[0] : 0.0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int r0 = tile * TR;
+      const bool unclamped = r0 + pat.wlo[0] >= 0;  // wlo[0] is the lowest window
+      unsigned m[RPT];
+      double zv[RPT], wv[RPT];
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        const int row = r0 + tid + q * 256;
+        m[q] = 0;
+        zv[q] = wv[q] = 0.0;
+        if (row < n_rows) {
+          m[q] = masks[row];
+          if (mode != 0) zv[q] = z[row];
+          if (DOT == 1 && !wx) wv[q] = w[row];
+        }
+      }
+      kb_mbar_wait(&s_full[stage], phase);
+      const double* sw = s_win + (size_t)stage * nw * wlen;
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        const int row = r0 + tid + q * 256;
+        double sum = 0.0;
+        if (unclamped && __all_sync(0xffffffffu, m[q] == full)) {
+#pragma unroll
+          for (int d = 0; d < 8; ++d)
+            if (d < nd) sum = __dadd_rn(sum, __dmul_rn(cv.c[d], sw[so[d] + q * 256]));
+          if (wx) wv[q] = sw[sc + q * 256];
+        } else {
+#pragma unroll
+          for (int d = 0; d < 8; ++d) {
+            if (d < nd && (m[q] >> d) & 1u) {
+              const int idx = row + pat.off[d] - kb_win_start(r0, pat.dwlo[d]);
+              sum = __dadd_rn(sum, __dmul_rn(cv.c[d], sw[pat.grp[d] * wlen + idx]));
+            }
+          }
+          if (wx && row < n_rows) wv[q] = w[row];
+        }
+        if (row < n_rows) {
+          double yv = sum;
+          if (mode == 1) yv = kb_mul_sub(cf, zv[q], sum);
+          if (mode == 2) yv = __dsub_rn(zv[q], sum);
+          __stcs(&y[row], yv);
+          if (DOT == 1) acc = fma(wv[q], yv, acc);
+          if (DOT == 2) acc = fma(yv, yv, acc);
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) kb_mbar_arrive(&s_empty[stage]);
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
+  if (DOT != 0) kb_grid_colsum(acc, 1, rd, out, red_sm);
+}
+
+// ------------------------------ constant-diagonal stencil kernel, second version ---
+// ncu of kb_spmv_stencil_kernel at 512^3 (profiles/r1_stencil_v1_ncu.txt): 169 instructions per
+// row-warp, issue slots 68 % busy, DRAM 39 % -- the row sum was compiled into 11 instructions per
+// diagonal (the generic->shared address conversion S2UR/UMOV/ULEA redone for every load, a
+// `d < nd` branch per diagonal, each DMUL waiting on its own LDS) and the warps stalled on the
+// per-tile mask load right after the barrier.  This version
+//   * takes the number of diagonals as a template parameter (no branches in the row sum),
+//   * keeps one 32-bit shared-memory address per diagonal and thread and issues
+//     `ld.shared.f64 [addr + imm]` directly, all loads of a row before its multiply/add chain,
+//   * prefetches the next tile's masks one tile ahead.
+// Products, their order and the rounding of each are those of kb_spmv_stencil_kernel.
+template <int IMM>
+__device__ __forceinline__ double kb_lds_f64(uint32_t addr) {
+  double v;
+  // volatile: stays between the (volatile) barrier wait and arrive; no memory clobber, so the
+  // arithmetic and the global stores of neighbouring rows may be scheduled around it
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+
+template <int ND, int Q>
+__device__ __forceinline__ void kb_st2_load(const uint32_t (&a)[ND], double (&xv)[ND]) {
+#pragma unroll
+  for (int d = 0; d < ND; ++d) xv[d] = kb_lds_f64<Q * 2048>(a[d]);
+}
+
+template <int ND>
+__device__ __forceinline__ double kb_st2_sum(const double (&xv)[ND], const KbConstVals& cv) {
+  double sum = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) sum = __dadd_rn(sum, __dmul_rn(cv.c[d], xv[d]));
+  return sum;
+}
+
+__device__ __forceinline__ void kb_st2_finish(double sum, int row, int mode, double cf, double zv,
+                                              double wv, double* __restrict__ y, int dot,
+                                              double& acc) {
+  double yv = sum;
+  if (mode == 1) yv = kb_mul_sub(cf, zv, sum);
+  if (mode == 2) yv = __dsub_rn(zv, sum);
+  __stcs(&y[row], yv);
+  if (dot == 1) acc = fma(wv, yv, acc);
+  if (dot == 2) acc = fma(yv, yv, acc);
+}
+
+// NQ (1 or 2) rows of the tile, Q0-th and following rows of this thread (row = r0 + tid + 256 q).
+// Interior warps (every mask of the group full, windows not clamped: 98 % at 512^3) take the
+// branch-free path: all loads first, then the multiply/add chains.  WX: the dot operand w is x
+// itself and the middle diagonal has offset 0 -- it is the value already loaded for the sum.
+template <int ND, int Q0, int NQ, int DOT, bool WX>
+__device__ __forceinline__ void kb_st2_rows(const uint32_t (&a)[ND], bool unclamped,
+                                            const unsigned* m, const double* zv, const double* wv,
+                                            int r0, int n_rows, const double* sw, int wlen,
+                                            const KbPattern& pat, const KbConstVals& cv, int mode,
+                                            double cf, const double* __restrict__ w,
+                                            double* __restrict__ y, double& acc) {
+  constexpr unsigned full = (1u << ND) - 1u;
+  const int tid = threadIdx.x;
+  bool allfull = unclamped && m[Q0] == full;
+  if constexpr (NQ == 2) allfull = allfull && m[Q0 + 1] == full;
+  if (__all_sync(0xffffffffu, allfull)) {
+    double xa[ND], xb[ND];
+    kb_st2_load<ND, Q0>(a, xa);
+    if constexpr (NQ == 2) kb_st2_load<ND, Q0 + 1>(a, xb);
+    const double sa = kb_st2_sum<ND>(xa, cv);
+    kb_st2_finish(sa, r0 + tid + Q0 * 256, mode, cf, zv[Q0], WX ? xa[ND / 2] : wv[Q0], y, DOT, acc);
+    if constexpr (NQ == 2) {
+      const double sb = kb_st2_sum<ND>(xb, cv);
+      kb_st2_finish(sb, r0 + tid + (Q0 + 1) * 256, mode, cf, zv[Q0 + 1],
+                    WX ? xb[ND / 2] : wv[Q0 + 1], y, DOT, acc);
+    }
+  } else {
+#pragma unroll
+    for (int q = Q0; q < Q0 + NQ; ++q) {
+      const int row = r0 + tid + q * 256;
+      double sum = 0.0;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        if ((m[q] >> d) & 1u) {
+          const int idx = row + pat.off[d] - kb_win_start(r0, pat.dwlo[d]);
+          sum = __dadd_rn(sum, __dmul_rn(cv.c[d], sw[pat.grp[d] * wlen + idx]));
+        }
+      }
+      if (row < n_rows) kb_st2_finish(sum, row, mode, cf, zv[q], WX ? w[row] : wv[q], y, DOT, acc);
+    }
+  }
+}
+
+template <int ND, int RPT, int STAGES, int MINB, int DOT, bool WX>
+__global__ void __launch_bounds__(256 + 32, MINB)
+kb_spmv_stencil2_kernel(int n_rows, int n_cols, int n_tiles, int wlen,
+                        const uint16_t* __restrict__ masks, KbPattern pat, KbConstVals cv,
+                        const double* __restrict__ x, double* __restrict__ y, int mode,
+                        const double* __restrict__ z, const double* __restrict__ coef,
+                        const double* __restrict__ w, int l2pol, double* __restrict__ out,
+                        KbRed rd) {
+  static_assert(RPT == 1 || RPT == 2 || RPT == 4, "rows per thread");
+  if (kb_gated(rd)) return;
+  constexpr int TR = 256 * RPT;
+  extern __shared__ __align__(128) unsigned char kb_dyn_smem[];
+  double* const s_win = reinterpret_cast<double*>(kb_dyn_smem);
+  const int nw = pat.nw;
+  uint64_t* const s_full = reinterpret_cast<uint64_t*>(s_win + (size_t)STAGES * nw * wlen);
+  uint64_t* const s_empty = s_full + STAGES;
+  __shared__ double red_sm[256 + 32];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      kb_mbar_init(&s_full[s], 1);
+      kb_mbar_init(&s_empty[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc = 0.0;
+  if (warp == 8) {
+    if ((tid & 31) == 0) {  // producer lane: the x windows of every tile of this CTA
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint64_t pol_keep = l2pol == 2 ? kb_policy_evict_first() : kb_policy_evict_last();
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int r0 = tile * TR;
+        kb_mbar_wait(&s_empty[stage], phase ^ 1u);
+        uint32_t bytes = 0;
+        for (int g = 0; g < nw; ++g) {
+          const int ge = min(r0 + pat.wlo[g] + TR + pat.wspan[g], n_cols);
+          bytes += (uint32_t)max(((ge + 1) & ~1) - kb_win_start(r0, pat.wlo[g]), 0) * 8u;
+        }
+        kb_mbar_expect_tx(&s_full[stage], bytes);
+        for (int g = 0; g < nw; ++g) {
+          const int ge = min(r0 + pat.wlo[g] + TR + pat.wspan[g], n_cols);
+          const int ga = kb_win_start(r0, pat.wlo[g]);
+          const int gn = max(((ge + 1) & ~1) - ga, 0);
+          if (gn > 0) {
+            if (l2pol == 1)
+              kb_bulk_g2s(s_win + ((size_t)stage * nw + g) * wlen, x + ga, (uint32_t)gn * 8u,
+                          &s_full[stage]);
+            else
+              kb_bulk_g2s_hint(s_win + ((size_t)stage * nw + g) * wlen, x + ga, (uint32_t)gn * 8u,
+                               &s_full[stage], pol_keep);
+          }
+        }
+        if (bytes == 0) kb_mbar_arrive(&s_full[stage]);  // (cannot happen: n_cols > 0)
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // byte address (shared window) of diagonal d for this thread's row q = 0 in stage 0, valid
+    // while the windows are not clamped at 0: element  row + off - ((r0 + wlo) & ~1), r0 even
+    const uint32_t sbase = kb_smem_u32(s_win);
+    uint32_t a0[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      a0[d] = sbase + 8u * (uint32_t)(pat.grp[d] * wlen + tid + pat.off[d] - pat.dwlo[d] +
+                                      (pat.dwlo[d] & 1));
+    const uint32_t stage_bytes = (uint32_t)(nw * wlen) * 8u;
+    const double cf = (mode == 1) ? coef[0] : 0.0;
+    int stage = 0;
+    uint32_t phase = 0;
+    unsigned mn[RPT];  // masks of the next tile, fetched one tile ahead
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      const int row = blockIdx.x * TR + tid + q * 256;
+      mn[q] = (blockIdx.x < n_tiles && row < n_rows) ? masks[row] : 0u;
+    }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int r0 = tile * TR;
+      const bool unclamped = r0 + pat.wlo[0] >= 0;  // wlo[0] is the lowest window
+      unsigned m[RPT];
+      double zv[RPT], wv[RPT];
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        const int row = r0 + tid + q * 256;
+        m[q] = mn[q];
+        zv[q] = wv[q] = 0.0;
+        if (row < n_rows) {
+          if (mode != 0) zv[q] = z[row];
+          if (DOT == 1 && !WX) wv[q] = w[row];
+        }
+        const int nrow = row + gridDim.x * TR;
+        mn[q] = (tile + (int)gridDim.x < n_tiles && nrow < n_rows) ? masks[nrow] : 0u;
+      }
+      kb_mbar_wait(&s_full[stage], phase);
+      const uint32_t so = (uint32_t)stage * stage_bytes;
+      uint32_t a[ND];
+#pragma unroll
+      for (int d = 0; d < ND; ++d) a[d] = a0[d] + so;
+      const double* sw = s_win + (size_t)stage * nw * wlen;
+      if constexpr (RPT == 1)
+        kb_st2_rows<ND, 0, 1, DOT, WX>(a, unclamped, m, zv, wv, r0, n_rows, sw, wlen, pat, cv, mode,
+                                       cf, w, y, acc);
+      if constexpr (RPT >= 2)
+        kb_st2_rows<ND, 0, 2, DOT, WX>(a, unclamped, m, zv, wv, r0, n_rows, sw, wlen, pat, cv, mode,
+                                       cf, w, y, acc);
+      if constexpr (RPT == 4)
+        kb_st2_rows<ND, 2, 2, DOT, WX>(a, unclamped, m, zv, wv, r0, n_rows, sw, wlen, pat, cv, mode,
+                                       cf, w, y, acc);
+      __syncwarp();
+      if ((tid & 31) == 0) kb_mbar_arrive(&s_empty[stage]);
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
+  if (DOT != 0) kb_grid_colsum(acc, 1, rd, out, red_sm);
+}
+
 // ------------------------------------------ windowed pattern kernel, k > 1 ----
 // SpMM for k right-hand sides in lock-step (x, y are (n, k) row-major): the same
 // compressed matrix and TMA x windows; a window is now rows_t + span consecutive

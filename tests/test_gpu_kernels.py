@@ -185,7 +185,7 @@ def test_pattern_schedule_selection():
     np.testing.assert_array_equal(Ud @ x, U @ x)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_stencil_kernel_variants_bit_exact(cfg):
     """Constant-diagonal ("stencil") schedule: no index, value or row-pointer stream -- the
     coefficients are kernel parameters.  Every tile configuration, ragged grids, fused
@@ -199,7 +199,9 @@ def test_stencil_kernel_variants_bit_exact(cfg):
                 st.convection_diffusion3d(12), st.shifted_laplace3d(9),
                 st.to_scipy(st.stencil7_csr(40, 6, 4)), st.to_scipy(st.stencil7_csr(2, 2, 300)),
                 st.to_scipy(st.stencil5_csr(700, 3)),
-                st.to_scipy(st.stencil7_csr(64, 16, 9, coeffs=st.convdiff_coeffs()))]
+                st.to_scipy(st.stencil7_csr(64, 16, 9, coeffs=st.convdiff_coeffs())),
+                # more tiles than resident CTAs: every CTA loops (mask prefetch, stage ring)
+                st.to_scipy(st.stencil7_csr(96, 80, 70)), st.to_scipy(st.stencil5_csr(1000, 611))]
         for A in mats:
             Ad = kb.CsrMatrix.from_scipy(A)
             assert Ad.info()["schedule"] == "stencil"
@@ -221,6 +223,10 @@ def test_stencil_kernel_variants_bit_exact(cfg):
                 np.testing.assert_allclose(out[0].cpu().numpy()[0], w @ r, rtol=1e-12, atol=1e-12)
                 ops.spmv(Ad, xd, yd, mode=mode, z=zd, coef=cf, dot=2, out=out[1])
                 np.testing.assert_allclose(out[1].cpu().numpy()[0], r @ r, rtol=1e-13)
+                # <x, y>: the dot operand aliases x (CG's <p, Ap>; read from the centre window)
+                ops.spmv(Ad, xd, yd, mode=mode, z=zd, coef=cf, dot=1, w=xd, out=out[0])
+                np.testing.assert_array_equal(yd.cpu().numpy().ravel(), r)
+                np.testing.assert_allclose(out[0].cpu().numpy()[0], x @ r, rtol=1e-12, atol=1e-12)
             # same bits as the schedules that stream the values
             for other in ("pattern", "stream", "rowwise"):
                 Ao = kb.CsrMatrix.from_scipy(A).set_schedule(other)

@@ -36,8 +36,8 @@ def run(sched, tag, reps=20):
 
 say(f"schedule chosen: {A.info()['schedule']}")
 best = (1e9, 0, 0)
-for cfg in (0, 1, 2, 3, 4, 5):
-    for ctas in (0, 2, 3, 4, 6):
+for cfg in (0, 1, 2, 3, 4, 5, 6, 7, 8):
+    for ctas in ((0, 3, 4) if cfg < 6 else (0,)):
         lib.kb_tune(10, cfg); lib.kb_tune(11, ctas)
         ms = run("stencil", f"cfg={cfg} ctas={ctas}")
         best = min(best, (ms, cfg, ctas))
