@@ -191,8 +191,18 @@ typedef struct {
   const double* crit;
   double* hist;
   int* stop_at;
+  /* Optional second search-direction buffer.  When given, k == 1 and A is a 3-D constant-
+   * coefficient stencil, an iteration is two launches: the p (and x) update fused with A p and
+   * <p, A p> -- it reads p with its halo, so the new p goes to the *other* buffer -- and the r
+   * update with A p recomputed on chip.  pcur (0: p, 1: p2) names the buffer that holds the search
+   * direction on entry; it changes with every executed iteration i > 0 (the caller derives the
+   * new value from the number of executed steps).  p2 == NULL: three launches, p in place. */
+  double* p2;
+  int pcur;
 } kb_cg_state;
 int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending, void* stream);
+/* *fused = 1 if kb_cg_run would take the two-launch path for this state (see p2 above). */
+int kb_cg_is_fused(const kb_cg_state* s, int* fused);
 
 /* --- generic vector kernels (fallback path for M/Ml/Mr/custom inner) ---- */
 /* y += sign * coef[c] * x   (product rounded, then sum: NumPy temporaries) */

@@ -41,7 +41,7 @@ class MinresState(C.Structure):
 class CgState(C.Structure):
     _fields_ = [
         ("A", vp), ("n", i64), ("k", i32), ("x", vp), ("r", vp), ("p", vp), ("Ap", vp),
-        ("slots", vp), ("crit", vp), ("hist", vp), ("stop_at", vp),
+        ("slots", vp), ("crit", vp), ("hist", vp), ("stop_at", vp), ("p2", vp), ("pcur", i32),
     ]
 
 
@@ -89,6 +89,7 @@ SIGNATURES = {
     "kb_cg_update_xr_record": [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "kb_cg_update_p": [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "kb_cg_run": [vp, C.POINTER(CgState), i32, i32, i32, vp],
+    "kb_cg_is_fused": [C.POINTER(CgState), C.POINTER(i32)],
     "kb_axpy": [vp, i64, i32, f64, vp, vp, vp, vp],
     "kb_xpby": [vp, i64, i32, vp, vp, vp, vp],
     "kb_div_scale": [vp, i64, i32, vp, vp, vp, vp],

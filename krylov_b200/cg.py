@@ -138,18 +138,31 @@ class FusedCG:
         self.nrm0 = np.sqrt(self.rho0)
         self.crit = np.maximum(tol * self.nrm0, atol)  # cg.py:154
         self.crit_d = torch.from_numpy(np.ascontiguousarray(self.crit)).to(self.dev)
-        self.p = self.z.clone()
+        # search direction: pbuf[pcur].  The fused marching kernels (single GPU, k = 1, 3-D
+        # constant-coefficient stencil: kb_cg_run with a second buffer) read p with its halo
+        # and write the new p to the other buffer; every other path updates pbuf[pcur] in place.
+        self.pbuf = [self.z.clone(), None]
+        self.pcur = 0
         self.kk = 0
         self._cstate = None
         if self.comm is None and hasattr(A, "handle") and M is None and Ml is None:
+            if k == 1 and A.info()["schedule"] == "stencil":
+                self.pbuf[1] = ops.vec(zero=False)
             self._cstate = CgState(A=A.handle, n=n, k=k, x=ptr(self.yk), r=ptr(self.r),
-                                   p=ptr(self.p), Ap=ptr(self.Ap), slots=ptr(self.sl),
+                                   p=ptr(self.pbuf[0]), Ap=ptr(self.Ap), slots=ptr(self.sl),
                                    crit=ptr(self.crit_d), hist=ptr(self.hist),
-                                   stop_at=ptr(self.stop_at))
+                                   stop_at=ptr(self.stop_at),
+                                   p2=ptr(self.pbuf[1]) if self.pbuf[1] is not None else None,
+                                   pcur=0)
         # x += alpha p of the last enqueued iteration is deferred into the next p
         # update (which streams p anyway: 64 instead of 72 B/element for the two
         # vector kernels of a step); current_x() flushes it
         self.x_pending = False
+        self.fused_march = False
+
+    @property
+    def p(self):
+        return self.pbuf[self.pcur]
 
     def _residual_norm2(self, x, out_r, out_z, slot):
         """out_r = Ml (b - A x); out_z = M out_r; returns host <out_r, out_z> (k,)
@@ -221,11 +234,17 @@ class FusedCG:
         residual norms of the steps that actually ran (the rest were gated)."""
         kk, k = self.kk, self.k
         self.stop_at.fill_(INT_MAX)
-        if self.comm is None and self.spmv_events is None and self._cstate is not None:
+        via_c = self.comm is None and self.spmv_events is None and self._cstate is not None
+        if via_c:
             # single GPU: the whole batch is enqueued by one C call (kb_cg_run)
+            self._cstate.pcur = self.pcur
+            fz = C.c_int(0)
+            check(lib.kb_cg_is_fused(C.byref(self._cstate), C.byref(fz)))
+            self.fused_march = bool(fz.value)
             check(lib.kb_cg_run(self.ops.ws.handle, C.byref(self._cstate), kk, nb,
                                 1 if self.x_pending else 0, cur_stream()))
-            self.ops.launches += 3 * nb - (1 if kk == 0 else 0)
+            self.ops.launches += (2 if self.fused_march else 3) * nb - (
+                (0 if self.fused_march else 1) if kk == 0 else 0)
             self.x_pending = True
         else:
             hist_ptr = self.hist.data_ptr() - (kk + 1) * k * 8  # history row kk+1 == hist[0]
@@ -234,6 +253,9 @@ class FusedCG:
             self.ops.gate(None, 0)
         s = int(self.stop_at.item())  # one host read per batch
         done = min(s, kk + nb) - kk
+        if via_c and self.fused_march:
+            # every executed iteration i > 0 moved p to the other buffer
+            self.pcur = (self.pcur + done - (1 if kk == 0 and done > 0 else 0)) % 2
         rows = self.hist[:done].cpu().numpy()
         self.kk += done
         return [rows[j].copy() for j in range(done)]

@@ -9,6 +9,7 @@
 #include "kb_scalar.cuh"
 #include "kb_spmv.cuh"
 #include "kb_vec.cuh"
+#include "kb_march.cuh"
 
 thread_local char kb_errbuf[512] = {0};
 
@@ -48,6 +49,9 @@ static int g_pattern_ctas = 0; // kb_tune key 3 (0 = default)
 static int g_window_cfg = 0;   // kb_tune key 4
 static int g_stencil_cfg = 0;   // kb_tune key 10: tile shape of the constant-diagonal kernel
 static int g_stencil_l2pol = 0; // kb_tune key 12: L2 hint of the x windows (0 evict_last, 1 none, 2 evict_first)
+static int g_march_ch = 0;     // kb_tune key 13: planes per work item of the marching kernel (0 auto)
+static int g_march_cfg = 0;    // kb_tune key 14: tile / ring shape of the marching kernel
+static int g_cg_fuse = 1;      // kb_tune key 15: fused marching CG kernels in kb_cg_run (0 off)
 static int g_stencil_ctas = 0;  // kb_tune key 11: CTAs/SM cap of it (0 = occupancy limit)
 static int g_cgs_jc = 8;  // kb_tune key 9: basis vectors per multi-dot launch (8 or 16)
 static int g_rowwise_contig = -1;  // kb_tune key 5: -1 auto, 0 strided, 1 contiguous rows per block
@@ -196,6 +200,9 @@ int kb_tune(int key, int value) {
     case 10: g_stencil_cfg = value; return KB_OK;
     case 11: g_stencil_ctas = value; return KB_OK;
     case 12: g_stencil_l2pol = value; return KB_OK;
+    case 13: g_march_ch = value; return KB_OK;
+    case 14: g_march_cfg = value; return KB_OK;
+    case 15: g_cg_fuse = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -714,15 +721,110 @@ static int kb_launch_stencil2(kb_csr_s* A, kb_ws_s* ws, const double* x, double*
   }
 }
 
+// ------------------------------------------------ plane-marching stencil kernel ---
+// Geometry of kb_stencil_march_kernel for this matrix and tile height; false if the pattern is
+// not {-P, inner diagonals within +-1024, +P} with constant coefficients.
+static bool kb_march_geom(const kb_csr_s* A, int RPT, KbMarch* g) {
+  if (!A->constv || A->pat.nd != 7 || A->masks == nullptr) return false;
+  const int* off = A->pat.off;
+  const int P = off[6];
+  if (P <= 0 || off[0] != -P || (P & 1)) return false;
+  int L = 1;
+  for (int d = 1; d < 6; ++d) {
+    const int a = off[d] < 0 ? -off[d] : off[d];
+    L = a > L ? a : L;
+  }
+  const int LP = ((L + 255) / 256) * 256;
+  const int TR = 256 * RPT;
+  if (LP > 1024 || L >= P || P < TR) return false;
+  if ((A->n_cols & 1) || A->n_rows >= (1ll << 31) - 4096 || A->n_cols >= (1ll << 31) - 4096)
+    return false;
+  g->P = P;
+  g->LP = LP;
+  g->wlen = TR + 2 * LP;
+  g->ncol = (P + TR - 1) / TR;
+  g->nplanes = (int)((A->n_rows + P - 1) / P);
+  int ch = g_march_ch > 0 ? g_march_ch : (g->nplanes >= 256 ? 32 : 16);
+  if (ch > g->nplanes) ch = g->nplanes;
+  g->ch = ch;
+  g->nitems = g->ncol * ((g->nplanes + ch - 1) / ch);
+  return true;
+}
+
+template <int RPT, int NS, int MINB, int KIND, int DOT, bool WX>
+static int kb_launch_march_t(kb_csr_s* A, kb_ws_s* ws, const KbMarch& g, const double* x, double* y,
+                             int mode, const double* z, const double* coef, const double* w,
+                             const KbMarchCg& cg, double* out, cudaStream_t st) {
+  static int max_smem[64] = {0};
+  auto kern = kb_stencil_march_kernel<7, RPT, NS, MINB, KIND, DOT, WX>;
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  const size_t smem = (size_t)(NS + (KIND == 1 ? 2 : 0)) * g.wlen * 8 + (2 * NS + 2) * 8;
+  if (dev < 0 || dev >= 64 || max_smem[dev] == 0) {
+    int lim = 0;
+    KB_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lim - 8 * 1024));
+    if (dev >= 0 && dev < 64) max_smem[dev] = lim - 8 * 1024;
+  }
+  int ctas = 0;
+  KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 288, smem));
+  if (ctas < 1) return kb_fail(KB_EUNSUPPORTED, "marching stencil kernel: ring does not fit");
+  if (g_stencil_ctas > 0 && g_stencil_ctas < ctas) ctas = g_stencil_ctas;
+  int grid = ws->num_sms * ctas;
+  if (grid > g.nitems) grid = g.nitems;
+  if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
+  kern<<<grid, 288, smem, st>>>((int)A->n_rows, (int)A->n_cols, g, A->masks, A->pat, A->cv, x, y,
+                                mode, z, coef, w, cg, g_stencil_l2pol, out, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+// kb_tune 14: 0 = 1024-row tiles, ring of 4; 1 = 1024 rows, ring of 5; 2 = 512 rows, ring of 4;
+// 3 = 512 rows, ring of 5
+static int kb_march_rpt() { return (g_march_cfg == 2 || g_march_cfg == 3) ? 2 : 4; }
+
+template <int KIND, int DOT, bool WX>
+static int kb_launch_march(kb_csr_s* A, kb_ws_s* ws, const KbMarch& g, const double* x, double* y,
+                           int mode, const double* z, const double* coef, const double* w,
+                           const KbMarchCg& cg, double* out, cudaStream_t st) {
+  // the fused p update keeps two more windows (r staging): one CTA per SM less
+  switch (g_march_cfg) {
+    case 1: return kb_launch_march_t<4, 5, 2, KIND, DOT, WX>(A, ws, g, x, y, mode, z, coef, w, cg, out, st);
+    case 2: return kb_launch_march_t<2, 4, (KIND == 1 ? 3 : 4), KIND, DOT, WX>(A, ws, g, x, y, mode, z, coef, w, cg, out, st);
+    case 3: return kb_launch_march_t<2, 5, 3, KIND, DOT, WX>(A, ws, g, x, y, mode, z, coef, w, cg, out, st);
+    default: return kb_launch_march_t<4, 4, (KIND == 1 ? 2 : 3), KIND, DOT, WX>(A, ws, g, x, y, mode, z, coef, w, cg, out, st);
+  }
+}
+
+// A x (+ epilogue, dot) by the marching kernel; KB_EUNSUPPORTED if the matrix does not qualify
+template <int DOT>
+static int kb_launch_march_spmv(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
+                                const double* z, const double* coef, const double* w, double* out,
+                                cudaStream_t st) {
+  KbMarch g;
+  if (!kb_march_geom(A, kb_march_rpt(), &g)) return KB_EUNSUPPORTED;
+  KbMarchCg cg;
+  memset(&cg, 0, sizeof(cg));
+  cg.rec.step = -1;
+  if (DOT == 1 && w == x && A->pat.off[3] == 0)
+    return kb_launch_march<0, DOT, (DOT == 1)>(A, ws, g, x, y, mode, z, coef, w, cg, out, st);
+  return kb_launch_march<0, DOT, false>(A, ws, g, x, y, mode, z, coef, w, cg, out, st);
+}
+
 // kb_tune key 10: 0-5 second version (5 or 7 diagonals), 6 the generic windowed kernel with
 // constant values (the first implementation), 7-9 kb_spmv_stencil_kernel (any <= 8 diagonals)
 template <int DOT>
 static int kb_launch_stencil(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
                              const double* z, const double* coef, const double* w, double* out,
                              cudaStream_t st) {
-  if (g_stencil_cfg <= 5 && A->pat.nd == 7)
+  if (g_stencil_cfg == 10) {  // plane-marching kernel (3-D stencils); else fall through
+    const int rc = kb_launch_march_spmv<DOT>(A, ws, x, y, mode, z, coef, w, out, st);
+    if (rc != KB_EUNSUPPORTED) return rc;
+  }
+  if ((g_stencil_cfg <= 5 || g_stencil_cfg == 10) && A->pat.nd == 7)
     return kb_launch_stencil2<7, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
-  if (g_stencil_cfg <= 5 && A->pat.nd == 5)
+  if ((g_stencil_cfg <= 5 || g_stencil_cfg == 10) && A->pat.nd == 5)
     return kb_launch_stencil2<5, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
   switch (g_stencil_cfg) {
     case 6: return kb_launch_window_cfg<256, 3, 4, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
@@ -1058,16 +1160,39 @@ int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new
   return KB_OK;
 }
 
+// Fused CG iteration on a 3-D constant-coefficient stencil (kb_march.cuh): p/x update fused with
+// A p and <p, A p> (reads p_in with halo, writes the other p buffer), r update with A p
+// recomputed from the ring.  Two launches and 64 n + masks bytes per iteration.
+static bool kb_cg_fusable(const kb_cg_state* s, KbMarch* g) {
+  if (!g_cg_fuse || s->k != 1 || s->p2 == nullptr || s->A->schedule != 4) return false;
+  if (!kb_march_geom(s->A, kb_march_rpt(), g) || s->A->pat.off[3] != 0) return false;
+  if (s->A->n_rows != s->n || s->A->n_cols != s->n) return false;
+  return ((uintptr_t)s->p % 16 == 0) && ((uintptr_t)s->p2 % 16 == 0) && ((uintptr_t)s->r % 16 == 0);
+}
+
+int kb_cg_is_fused(const kb_cg_state* s, int* fused) {
+  KB_REQUIRE(s != nullptr && fused != nullptr && s->A != nullptr, "null argument");
+  KbMarch geo;
+  *fused = kb_cg_fusable(s, &geo) ? 1 : 0;
+  return KB_OK;
+}
+
 int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending, void* stream) {
   KB_REQUIRE(ws != nullptr && s != nullptr, "null argument");
   KB_REQUIRE(s->A && s->x && s->r && s->p && s->Ap && s->slots && s->crit && s->hist && s->stop_at,
              "null field in kb_cg_state");
   KB_REQUIRE(i0 >= 0 && n_iters >= 0, "negative iteration range");
+  KB_REQUIRE(s->pcur == 0 || (s->pcur == 1 && s->p2 != nullptr), "pcur must name an existing buffer");
   const int k = s->k;
   double* sl = s->slots;
   const int* saved_gate = ws->gate;
   const int saved_tag = ws->gate_tag;
   int rc = KB_OK;
+  KbMarch geo;
+  const bool fused = kb_cg_fusable(s, &geo);
+  double* pb[2] = {s->p, s->p2};
+  int pc = s->pcur;
+  cudaStream_t st = S(stream);
   for (int i = i0; i < i0 + n_iters && rc == KB_OK; ++i) {
     double* cur = sl + (size_t)(i % 2) * k;        // rho_i
     double* nxt = sl + (size_t)((i + 1) % 2) * k;  // rho_{i-1}, then rho_{i+1}
@@ -1076,11 +1201,46 @@ int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pendi
     double* rr = sl + 4 * (size_t)k;
     ws->gate = s->stop_at;
     ws->gate_tag = i;
+    if (fused) {
+      KbMarchCg cg;
+      memset(&cg, 0, sizeof(cg));
+      cg.rec.step = -1;
+      if (i > 0) {  // [x += alpha p;] p' = r + omega p (into the other buffer); <p', A p'>
+        cg.rho_a = cur;
+        cg.rho_b = nxt;
+        cg.alpha_in = alpha;
+        cg.r_in = s->r;
+        cg.xv = x_pending ? s->x : nullptr;
+        cg.p_out = pb[pc ^ 1];
+        rc = kb_launch_march<1, 1, false>(s->A, ws, geo, pb[pc], nullptr, 0, nullptr, nullptr,
+                                          nullptr, cg, pAp, st);
+        pc ^= 1;
+      } else {
+        rc = kb_spmv(s->A, ws, k, pb[pc], s->Ap, 0, nullptr, nullptr, 1, pb[pc], pAp, stream);
+      }
+      if (rc == KB_OK) {  // alpha; r -= alpha (A p); <r, r>; record step i+1, rho_{i+1} -> nxt
+        memset(&cg, 0, sizeof(cg));
+        cg.rho_a = cur;
+        cg.rho_b = pAp;
+        cg.alpha_out = alpha;
+        cg.r = s->r;
+        cg.rec.step = i + 1;
+        cg.rec.crit = s->crit;
+        cg.rec.hist = s->hist - (size_t)(i0 + 1) * k;
+        cg.rec.stop_at = s->stop_at;
+        cg.rec.rho_keep = nxt;
+        rc = kb_launch_march<2, 2, false>(s->A, ws, geo, pb[pc], nullptr, 0, nullptr, nullptr,
+                                          nullptr, cg, rr, st);
+      }
+      x_pending = 1;
+      continue;
+    }
+    double* p = pb[pc];
     if (i > 0)
       rc = kb_cg_update_p(ws, s->n, k, 0, cur, nxt, alpha, nullptr, nullptr, nullptr, nullptr, s->r,
-                          s->p, x_pending ? s->x : nullptr, x_pending ? 5 : 1, stream);
+                          p, x_pending ? s->x : nullptr, x_pending ? 5 : 1, stream);
     if (rc == KB_OK)
-      rc = kb_spmv(s->A, ws, k, s->p, s->Ap, 0, nullptr, nullptr, 1, s->p, pAp, stream);
+      rc = kb_spmv(s->A, ws, k, p, s->Ap, 0, nullptr, nullptr, 1, p, pAp, stream);
     if (rc == KB_OK)  // r update + <r,r> + record: hist row (i - i0) <- step i+1, rho_{i+1} -> nxt
       rc = kb_cg_update_xr_record(ws, s->n, k, cur, pAp, nullptr, s->Ap, nullptr, s->r, rr, alpha,
                                   i + 1, s->crit, s->hist - (size_t)(i0 + 1) * k, s->stop_at, nxt,

@@ -1,0 +1,325 @@
+// Plane-marching kernel for constant-coefficient 3-D stencils (sm_100a).
+//
+// kb_spmv_stencil2_kernel brings every x entry into shared memory once per window that holds
+// it: five windows for the 7-point stencil, 40 B of L2->SM traffic per row.  ncu at 512^3
+// (profiles/r1_stencil2_ncu.txt): 5.9 GB over the crossbar in 0.76 ms = ~80 % of the measured
+// L2 throughput cap while DRAM idles at 46 % -- the kernel is L2-bound, and half of the stall
+// samples sit on the "window landed?" barrier.
+//
+// Here a CTA owns a tile of TR consecutive in-plane positions and *marches* through the planes
+// (row = plane * P + position, P = the largest diagonal offset):  the window
+//     W_j = x[j P + c TR - LP,  j P + c TR + TR + LP)
+// serves the diagonals |off| <= LP of plane j, the +P diagonal of plane j-1 and the -P diagonal
+// of plane j+1.  A ring of NS windows stays in shared memory, one 1-D TMA bulk copy per plane
+// brings the next one: (TR + 2 LP) / TR entries per row instead of 5 (2 at TR = 1024, 512-wide
+// lines).  Products, their order and rounding are those of every other schedule -> bit-identical.
+//
+// The same skeleton carries the two halves of a fused CG iteration (KIND 1 / 2): because the
+// neighbouring planes of the *updated* search direction are already in the ring,
+//     p <- r + omega p,  [x <- x + alpha_old p_old,]  <p, A p>          (KIND 1)
+// needs no separate pass over p, r, x, and
+//     r <- r - alpha (A p),  <r, r>, record / stopping test               (KIND 2)
+// recomputes A p from the ring instead of reading a stored copy: a CG step streams
+// 40 n + 24 n (+ masks) bytes instead of 40 n + 18 n + 24 n  (cg.py:175-217).
+#pragma once
+#include "kb_spmv.cuh"
+#include "kb_vec.cuh"
+
+struct KbMarch {
+  int P;        // plane stride = largest diagonal offset (even)
+  int LP;       // halo entries on each side of a tile's window (multiple of 256, >= inner offsets)
+  int wlen;     // TR + 2 LP
+  int ncol;     // tiles per plane
+  int nplanes;  // ceil(n_rows / P)
+  int ch;       // planes per work item
+  int nitems;   // ncol * ceil(nplanes / ch)
+};
+
+// operands of the fused CG kernels (KIND 1 / 2)
+struct KbMarchCg {
+  const double* rho_a;   // KIND 1: rho_i (omega = rho_a / nz(rho_b));  KIND 2: rho_i
+  const double* rho_b;   // KIND 1: rho_{i-1};                           KIND 2: <p, Ap>
+  const double* alpha_in;  // KIND 1: alpha of the previous iteration (x update)
+  double* alpha_out;       // KIND 2: state slot of alpha
+  const double* r_in;      // KIND 1: r (read with halo)
+  double* r;               // KIND 2: r (updated in place, own rows)
+  double* xv;              // KIND 1: x (own rows), may be null: no x update
+  double* p_out;           // KIND 1: the new search direction (a buffer different from p_in)
+  KbCgRecord rec;          // KIND 2
+};
+
+__device__ __forceinline__ void kb_st_f64_shared(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ double kb_ld_f64_shared(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// row sums of NQ (1 or 2) rows: q = Q0, Q0 + 1 of this thread.  a[d]: shared address of
+// diagonal d for row q = 0 in the current ring position.
+template <int ND, int Q0, int NQ>
+__device__ __forceinline__ void kb_march_rows(const uint32_t (&a)[ND], const unsigned* m,
+                                              const KbConstVals& cv, double* sum, double* ctr) {
+  constexpr unsigned full = (1u << ND) - 1u;
+  bool allfull = m[Q0] == full;
+  if constexpr (NQ == 2) allfull = allfull && m[Q0 + 1] == full;
+  if (__all_sync(0xffffffffu, allfull)) {
+    double xa[ND], xb[ND];
+    kb_st2_load<ND, Q0>(a, xa);
+    if constexpr (NQ == 2) kb_st2_load<ND, Q0 + 1>(a, xb);
+    sum[Q0] = kb_st2_sum<ND>(xa, cv);
+    ctr[Q0] = xa[ND / 2];
+    if constexpr (NQ == 2) {
+      sum[Q0 + 1] = kb_st2_sum<ND>(xb, cv);
+      ctr[Q0 + 1] = xb[ND / 2];
+    }
+  } else {  // rows next to a boundary: the absent diagonals are skipped, never loaded
+    // the middle entry is the row's own x (dot operand when w aliases x): always inside the window
+    double s0 = 0.0, s1 = 0.0, c1 = 0.0;
+    const double c0 = kb_lds_f64<Q0 * 2048>(a[ND / 2]);
+    if constexpr (NQ == 2) c1 = kb_lds_f64<(Q0 + 1) * 2048>(a[ND / 2]);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      if ((m[Q0] >> d) & 1u) {
+        const double v = kb_lds_f64<Q0 * 2048>(a[d]);
+        s0 = __dadd_rn(s0, __dmul_rn(cv.c[d], v));
+      }
+      if constexpr (NQ == 2) {
+        if ((m[Q0 + 1] >> d) & 1u) {
+          const double v = kb_lds_f64<(Q0 + 1) * 2048>(a[d]);
+          s1 = __dadd_rn(s1, __dmul_rn(cv.c[d], v));
+        }
+      }
+    }
+    sum[Q0] = s0;
+    ctr[Q0] = c0;
+    if constexpr (NQ == 2) {
+      sum[Q0 + 1] = s1;
+      ctr[Q0 + 1] = c1;
+    }
+  }
+}
+
+// KIND 0: y = epilogue(A x) (+ dot), 1: CG p/x update + <p, A p>, 2: CG r update + <r, r> + record
+// WX (KIND 0): the dot operand w is x itself and the middle diagonal is the main diagonal.
+template <int ND, int RPT, int NS, int MINB, int KIND, int DOT, bool WX>
+__global__ void __launch_bounds__(256 + 32, MINB)
+kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __restrict__ masks,
+                        KbPattern pat, KbConstVals cv, const double* __restrict__ x,
+                        double* __restrict__ y, int mode, const double* __restrict__ z,
+                        const double* __restrict__ coef, const double* __restrict__ w,
+                        KbMarchCg cg, int l2pol, double* __restrict__ out, KbRed rd) {
+  static_assert(RPT == 2 || RPT == 4, "rows per thread");
+  static_assert(NS >= 4, "ring: previous, current, next plane + one in flight");
+  if (kb_gated(rd)) return;
+  constexpr int TR = 256 * RPT;
+  constexpr int NR = KIND == 1 ? 2 : 0;  // staging windows of r (KIND 1)
+  extern __shared__ __align__(128) unsigned char kb_dyn_smem[];
+  double* const s_win = reinterpret_cast<double*>(kb_dyn_smem);
+  double* const s_rwin = s_win + (size_t)NS * g.wlen;
+  uint64_t* const s_full = reinterpret_cast<uint64_t*>(s_rwin + (size_t)NR * g.wlen);
+  uint64_t* const s_empty = s_full + NS;
+  uint64_t* const s_rempty = s_empty + NS;  // [2], KIND 1
+  __shared__ double red_sm[256 + 32];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      kb_mbar_init(&s_full[s], 1);
+      kb_mbar_init(&s_empty[s], 8);
+    }
+    if (KIND == 1) {
+      kb_mbar_init(&s_rempty[0], 8);
+      kb_mbar_init(&s_rempty[1], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc = 0.0;
+  if (warp == 8) {
+    // ------------------------------------------------ producer: one window per plane ---
+    if ((tid & 31) == 0) {
+      const uint64_t pol = l2pol == 2 ? kb_policy_evict_first() : kb_policy_evict_last();
+      unsigned cnt = 0;
+      for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
+        const int c = item % g.ncol;
+        const int j0 = (item / g.ncol) * g.ch;
+        const int j1 = min(j0 + g.ch, g.nplanes);
+        const int nload = j1 - j0 + 2;
+        for (int l = 0; l < nload; ++l, ++cnt) {
+          const int slot = (int)(cnt % NS);
+          const unsigned use = cnt / NS;
+          if (use > 0) kb_mbar_wait(&s_empty[slot], (use - 1u) & 1u);
+          if (KIND == 1 && cnt >= 2) kb_mbar_wait(&s_rempty[cnt & 1u], ((cnt >> 1) - 1u) & 1u);
+          const long long g0 = (long long)(j0 - 1 + l) * g.P + (long long)c * TR - g.LP;
+          const long long lo = g0 > 0 ? g0 : 0;
+          const long long hi = (g0 + g.wlen < (long long)n_cols) ? g0 + g.wlen : (long long)n_cols;
+          if (hi > lo) {
+            const uint32_t bytes = (uint32_t)(hi - lo) * 8u;
+            double* dst = s_win + (size_t)slot * g.wlen + (lo - g0);
+            kb_mbar_expect_tx(&s_full[slot], KIND == 1 ? 2u * bytes : bytes);
+            if (l2pol == 1)
+              kb_bulk_g2s(dst, x + lo, bytes, &s_full[slot]);
+            else
+              kb_bulk_g2s_hint(dst, x + lo, bytes, &s_full[slot], pol);
+            if (KIND == 1) {
+              double* rdst = s_rwin + (size_t)(cnt & 1u) * g.wlen + (lo - g0);
+              if (l2pol == 1)
+                kb_bulk_g2s(rdst, cg.r_in + lo, bytes, &s_full[slot]);
+              else
+                kb_bulk_g2s_hint(rdst, cg.r_in + lo, bytes, &s_full[slot], pol);
+            }
+          } else {
+            kb_mbar_arrive(&s_full[slot]);  // window entirely outside the vector
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------ consumers: RPT rows per thread ---
+    const uint32_t sbase = kb_smem_u32(s_win);
+    const uint32_t rbase = kb_smem_u32(s_rwin);
+    const uint32_t wbytes = (uint32_t)g.wlen * 8u;
+    const uint32_t tb = (uint32_t)(g.LP + tid) * 8u;  // this thread's row q = 0 in a window
+    uint32_t od[ND];  // byte offset of diagonal d relative to the window start (inner diagonals)
+#pragma unroll
+    for (int d = 0; d < ND; ++d) od[d] = tb + (uint32_t)(8 * ((d == 0 || d == ND - 1) ? 0 : pat.off[d]));
+    double omega = 0.0, alpha = 0.0, cf = 0.0;
+    if (KIND == 0 && mode == 1) cf = coef[0];
+    if (KIND == 1) {
+      omega = cg.rho_a[0] / kb_nz(cg.rho_b[0]);
+      if (cg.xv != nullptr) alpha = cg.alpha_in[0];
+    }
+    if (KIND == 2) {
+      alpha = cg.rho_a[0] / kb_nz(cg.rho_b[0]);
+      if (cg.alpha_out != nullptr && blockIdx.x == 0 && tid == 0) cg.alpha_out[0] = alpha;
+    }
+    unsigned cnt = 0;
+    for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
+      const int c = item % g.ncol;
+      const int j0 = (item / g.ncol) * g.ch;
+      const int j1 = min(j0 + g.ch, g.nplanes);
+      const int nload = j1 - j0 + 2;
+      const int pos0 = c * TR + tid;  // in-plane position of row q = 0
+      for (int l = 0; l < nload; ++l, ++cnt) {
+        const int slot = (int)(cnt % NS);
+        // --- operands from global memory, requested before the barrier wait ---
+        const int jc = j0 + l - 2;  // plane whose rows are computed in this pass (l >= 2)
+        unsigned m[RPT];
+        double zv[RPT], wv[RPT];
+        int row[RPT];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+          const int pos = pos0 + q * 256;
+          const long long r64 = (long long)jc * g.P + pos;
+          const bool ok = l >= 2 && pos < g.P && r64 < (long long)n_rows;
+          row[q] = ok ? (int)r64 : -1;
+          m[q] = ok ? (unsigned)masks[row[q]] : 0u;
+          zv[q] = wv[q] = 0.0;
+          if (ok) {
+            if (KIND == 0 && mode != 0) zv[q] = z[row[q]];
+            if (KIND == 0 && DOT == 1 && !WX) wv[q] = w[row[q]];
+            if (KIND == 2) zv[q] = cg.r[row[q]];
+          }
+        }
+        // KIND 1: x of the own rows of the arriving plane (j0 - 1 + l), if it belongs to the item
+        double xo[RPT];
+        int trow[RPT];
+        if (KIND == 1) {
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) {
+            const int pos = pos0 + q * 256;
+            const long long r64 = (long long)(j0 - 1 + l) * g.P + pos;
+            const bool ok = l >= 1 && l <= nload - 2 && pos < g.P && r64 < (long long)n_rows;
+            trow[q] = ok ? (int)r64 : -1;
+            xo[q] = (ok && cg.xv != nullptr) ? cg.xv[trow[q]] : 0.0;
+          }
+        }
+        kb_mbar_wait(&s_full[slot], (cnt / NS) & 1u);
+        if (KIND == 1) {
+          // p <- r + omega p on the whole arriving window (halo included), in place; the own
+          // rows also go to global memory together with x += alpha p_old  (cg.py:178,196)
+          const uint32_t pw = sbase + (uint32_t)slot * wbytes + (uint32_t)tid * 8u;
+          const uint32_t rw = rbase + (cnt & 1u) * wbytes + (uint32_t)tid * 8u;
+          const int nel = g.wlen >> 8;       // window entries per thread
+          const int own0 = g.LP >> 8;        // entries [own0, own0 + RPT) are this thread's rows
+          for (int u = 0; u < nel; ++u) {
+            const double pold = kb_ld_f64_shared(pw + (uint32_t)u * 2048u);
+            const double rv = kb_ld_f64_shared(rw + (uint32_t)u * 2048u);
+            const double pn = kb_mul_add(omega, pold, rv);
+            kb_st_f64_shared(pw + (uint32_t)u * 2048u, pn);
+            const int q = u - own0;
+            if (q >= 0 && q < RPT) {
+#pragma unroll
+              for (int qq = 0; qq < RPT; ++qq) {
+                if (qq == q && trow[qq] >= 0) {
+                  if (cg.xv != nullptr) cg.xv[trow[qq]] = kb_mul_add(alpha, pold, xo[qq]);
+                  cg.p_out[trow[qq]] = pn;
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if ((tid & 31) == 0) kb_mbar_arrive(&s_rempty[cnt & 1u]);
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // the window is complete for everyone
+        }
+        if (l >= 2) {
+          const uint32_t wprev = sbase + (uint32_t)((cnt - 2u) % NS) * wbytes;
+          const uint32_t wcur = sbase + (uint32_t)((cnt - 1u) % NS) * wbytes;
+          const uint32_t wnext = sbase + (uint32_t)slot * wbytes;
+          uint32_t a[ND];
+          a[0] = wprev + od[0];
+#pragma unroll
+          for (int d = 1; d < ND - 1; ++d) a[d] = wcur + od[d];
+          a[ND - 1] = wnext + od[ND - 1];
+          double sum[RPT], ctr[RPT];
+          kb_march_rows<ND, 0, 2>(a, m, cv, sum, ctr);
+          if constexpr (RPT == 4) kb_march_rows<ND, 2, 2>(a, m, cv, sum, ctr);
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) {
+            if (row[q] >= 0) {
+              if (KIND == 0) {
+                double yv = sum[q];
+                if (mode == 1) yv = kb_mul_sub(cf, zv[q], sum[q]);
+                if (mode == 2) yv = __dsub_rn(zv[q], sum[q]);
+                __stcs(&y[row[q]], yv);
+                if (DOT == 1) acc = fma(WX ? ctr[q] : wv[q], yv, acc);
+                if (DOT == 2) acc = fma(yv, yv, acc);
+              } else if (KIND == 1) {
+                acc = fma(ctr[q], sum[q], acc);  // <p, A p>
+              } else {
+                const double rn = kb_mul_sub(alpha, sum[q], zv[q]);  // r - alpha (A p)
+                cg.r[row[q]] = rn;
+                acc = fma(rn, rn, acc);
+              }
+            }
+          }
+          __syncwarp();
+          if ((tid & 31) == 0) kb_mbar_arrive(&s_empty[(cnt - 2u) % NS]);
+        }
+      }
+      // the last two windows of the item are not needed by a later pass
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        kb_mbar_arrive(&s_empty[(cnt - 2u) % NS]);
+        kb_mbar_arrive(&s_empty[(cnt - 1u) % NS]);
+      }
+    }
+  }
+  if (KIND == 0 && DOT == 0) return;
+  const bool last = kb_grid_colsum(acc, 1, rd, out, red_sm);
+  if (KIND == 2 && last && cg.rec.step >= 0) {  // cg.py:156,214-217 in the finishing block
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double rn = out[0];
+      if (cg.rec.rho_keep != nullptr) cg.rec.rho_keep[0] = rn;
+      const double nrm = sqrt(rn);
+      cg.rec.hist[(size_t)cg.rec.step] = nrm;
+      if (nrm <= cg.rec.crit[0]) *cg.rec.stop_at = cg.rec.step;
+    }
+  }
+}

@@ -399,3 +399,115 @@ def test_classical_gram_schmidt_kernels(k, jc):
             del ops
     finally:
         lib.kb_tune(9, 8)
+
+
+@pytest.mark.parametrize("mcfg", [0, 1, 2, 3])
+def test_marching_stencil_kernel_bit_exact(mcfg):
+    """Plane-marching kernel (kb_march.cuh, kb_tune 10 = 10): windows of x kept in a shared-memory
+    ring while a CTA walks through the planes.  Partial tiles (plane size not a multiple of the
+    tile), short last chunks, more work items than CTAs, every epilogue and dot variant:
+    bit-identical to SciPy; matrices it does not cover fall through to the tiled kernel."""
+    from krylov_b200._lib import lib
+
+    lib.kb_tune(10, 10)
+    lib.kb_tune(14, mcfg)
+    try:
+        cases = [(st.to_scipy(st.stencil7_csr(40, 30, 9)), 0),          # P = 1200: partial 2nd tile
+                 (st.to_scipy(st.stencil7_csr(64, 64, 20)), 3),         # chunks of 3 planes, ragged end
+                 (st.to_scipy(st.stencil7_csr(96, 80, 70, coeffs=st.convdiff_coeffs())), 0),
+                 (st.to_scipy(st.stencil7_csr(512, 64, 5, shift=0.37)), 1),  # 512-wide lines, halo 512
+                 (st.to_scipy(st.stencil7_csr(256, 256, 12)), 2),       # 64*6 = 384.. items, CTAs loop
+                 (st.poisson3d(33), 0),                                  # odd plane size: tiled kernel
+                 (st.poisson3d(12), 0)]                                  # plane smaller than a tile
+        for A, ch in cases:
+            lib.kb_tune(13, ch)
+            Ad = kb.CsrMatrix.from_scipy(A)
+            assert Ad.info()["schedule"] == "stencil"
+            n = A.shape[0]
+            x, z, w = (rng.standard_normal(n) for _ in range(3))
+            ref = A @ x
+            np.testing.assert_array_equal(Ad @ x, ref)
+            ops = Ops(n, 1)
+            xd, zd, wd = (torch.from_numpy(a).cuda().reshape(n, 1) for a in (x, z, w))
+            cf = torch.tensor([-1.7], dtype=torch.float64, device="cuda")
+            yd = torch.empty_like(xd)
+            out = ops.slots(2)
+            for mode, r in ((0, ref), (1, ref - (-1.7) * z), (2, z - ref)):
+                ops.spmv(Ad, xd, yd, mode=mode, z=zd, coef=cf, dot=1, w=wd, out=out[0])
+                np.testing.assert_array_equal(yd.cpu().numpy().ravel(), r)
+                np.testing.assert_allclose(out[0].cpu().numpy()[0], w @ r, rtol=1e-12, atol=1e-11)
+                ops.spmv(Ad, xd, yd, mode=mode, z=zd, coef=cf, dot=2, out=out[1])
+                np.testing.assert_array_equal(yd.cpu().numpy().ravel(), r)
+                np.testing.assert_allclose(out[1].cpu().numpy()[0], r @ r, rtol=1e-13)
+                ops.spmv(Ad, xd, yd, mode=mode, z=zd, coef=cf, dot=1, w=xd, out=out[0])
+                np.testing.assert_array_equal(yd.cpu().numpy().ravel(), r)
+                np.testing.assert_allclose(out[0].cpu().numpy()[0], x @ r, rtol=1e-12, atol=1e-11)
+                ops.spmv(Ad, xd, yd, mode=mode, z=zd, coef=cf, dot=0)
+                np.testing.assert_array_equal(yd.cpu().numpy().ravel(), r)
+    finally:
+        lib.kb_tune(10, 0)
+        lib.kb_tune(13, 0)
+        lib.kb_tune(14, 0)
+
+
+@pytest.mark.parametrize("mcfg,ch", [(0, 0), (1, 5), (2, 0), (3, 2), (0, 1)])
+def test_fused_marching_cg_matches_three_kernel_cg(mcfg, ch):
+    """kb_cg_run with a second p buffer on a 3-D constant-coefficient stencil: p/x update fused
+    with A p and <p, A p>, r update with A p recomputed on chip (two launches per step).  Every
+    element-wise statement is the one of the three-kernel path, only the summation order of the
+    two dots differs: same step count, histories within 1e-8 while above 1e-6 of the start,
+    solution to 1e-10, and both match
+    the oracle.  Batches end on converged and unconverged steps (p buffer parity)."""
+    from krylov_b200._lib import lib
+    from oracle import krylov_oracle as orc
+
+    for A, tol in ((st.to_scipy(st.stencil7_csr(40, 30, 9)), 1e-10),
+                   (st.to_scipy(st.stencil7_csr(64, 32, 17, coeffs=st.STENCIL_POISSON, shift=-0.3)), 1e-9),
+                   (st.poisson3d(32), 1e-8)):
+        n = A.shape[0]
+        b = A @ rng.standard_normal(n)
+        res = {}
+        for fuse in (0, 1):
+            lib.kb_tune(15, fuse)
+            lib.kb_tune(14, mcfg)
+            lib.kb_tune(13, ch)
+            try:
+                sol, info = kb.cg(A, b, tol=tol, maxiter=3000)
+            finally:
+                lib.kb_tune(15, 1)
+                lib.kb_tune(14, 0)
+                lib.kb_tune(13, 0)
+            assert info.success
+            res[fuse] = (sol, np.asarray(info.resnorms), info.numsteps)
+        assert res[0][2] == res[1][2]
+        r0, r1 = res[0][1], res[1][1]
+        live = r0 / r0[0] >= 1e-6
+        assert np.all(np.abs(r1 - r0)[live] <= 1e-8 * r0[live])
+        assert np.linalg.norm(res[1][0] - res[0][0]) <= 1e-10 * np.linalg.norm(res[0][0])
+        sol_o, info_o = orc.cg(A, b, tol=tol, maxiter=3000)
+        assert info_o.numsteps == res[1][2]
+        ro = np.asarray(info_o.resnorms)
+        live = ro / ro[0] >= 1e-6
+        assert np.all(np.abs(res[1][1] - ro)[live] <= 1e-8 * ro[live])
+        assert np.linalg.norm(res[1][0] - sol_o) <= 1e-10 * np.linalg.norm(sol_o)
+
+
+def test_fused_marching_cg_is_selected():
+    """The two-launch path is what runs for k = 1 on a 3-D constant stencil, and only there."""
+    from krylov_b200.cg import FusedCG
+
+    def fused(A, k=1):
+        n = A.shape[0]
+        Ad = kb.CsrMatrix.from_scipy(A)
+        b = torch.from_numpy(rng.standard_normal((n, k))).cuda()
+        s = FusedCG(Ad, b, torch.zeros_like(b), 1e-8, 0.0)
+        s.run(4)
+        return s.fused_march
+
+    assert fused(st.poisson3d(32))
+    assert not fused(st.poisson3d(32), k=2)
+    assert not fused(st.poisson2d(64))
+    assert not fused(st.poisson3d(12))      # plane smaller than a tile
+    P = st.poisson3d(32).tocsr()
+    P.data[5] = np.nextafter(P.data[5], 0.0)  # variable coefficients
+    assert not fused(P)
