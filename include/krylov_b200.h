@@ -203,6 +203,11 @@ typedef struct {
 int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending, void* stream);
 /* *fused = 1 if kb_cg_run would take the two-launch path for this state (see p2 above). */
 int kb_cg_is_fused(const kb_cg_state* s, int* fused);
+/* kb_cg_run with CUDA events around every launch (measurement only; synchronises the stream).
+ * ms[3]: mean duration of the phases of a step -- fused path: {p/x update + A p + <p,Ap>,
+ * r update + <r,r>, 0}; three-kernel path: {p/x update, A p + <p,Ap>, r update + <r,r>}. */
+int kb_cg_run_timed(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending,
+                    void* stream, float* ms, float* total_ms);
 
 /* --- generic vector kernels (fallback path for M/Ml/Mr/custom inner) ---- */
 /* y += sign * coef[c] * x   (product rounded, then sum: NumPy temporaries) */

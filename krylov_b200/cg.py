@@ -261,6 +261,34 @@ class FusedCG:
         return [rows[j].copy() for j in range(done)]
 
 
+    def run_timed(self, nb):
+        """Measurement hook (bench.py): run(nb) through kb_cg_run_timed -- the same launches with
+        CUDA events around each one on the launching stream.  Returns (mean ms of the step's
+        phases, total ms, fused?).  Phases: fused path {p/x update + A p + <p,Ap>, r update +
+        <r,r>}; three-kernel path {p/x update, A p + <p,Ap>, r update + <r,r>}."""
+        assert self.comm is None and self._cstate is not None, "single-GPU C path only"
+        kk = self.kk
+        self.stop_at.fill_(INT_MAX)
+        self._cstate.pcur = self.pcur
+        fz = C.c_int(0)
+        check(lib.kb_cg_is_fused(C.byref(self._cstate), C.byref(fz)))
+        self.fused_march = bool(fz.value)
+        ms = (C.c_float * 3)()
+        tot = C.c_float(0)
+        check(lib.kb_cg_run_timed(self.ops.ws.handle, C.byref(self._cstate), kk, nb,
+                                  1 if self.x_pending else 0, cur_stream(), ms, C.byref(tot)))
+        self.ops.launches += (2 if self.fused_march else 3) * nb - (
+            (0 if self.fused_march else 1) if kk == 0 else 0)
+        self.x_pending = True
+        s = int(self.stop_at.item())
+        done = min(s, kk + nb) - kk
+        if self.fused_march:
+            self.pcur = (self.pcur + done - (1 if kk == 0 and done > 0 else 0)) % 2
+        self.kk += done
+        n_ph = 2 if self.fused_march else 3
+        return [float(ms[i]) for i in range(n_ph)], float(tot.value), self.fused_march
+
+
 def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback, M=None, Ml=None):
     st = FusedCG(prob.A_csr, prob.b, prob.x0, tol, atol, M=M, Ml=Ml)
     ops, crit = st.ops, st.crit

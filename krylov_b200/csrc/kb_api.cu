@@ -812,19 +812,21 @@ static int kb_launch_march_spmv(kb_csr_s* A, kb_ws_s* ws, const double* x, doubl
   return kb_launch_march<0, DOT, false>(A, ws, g, x, y, mode, z, coef, w, cg, out, st);
 }
 
-// kb_tune key 10: 0-5 second version (5 or 7 diagonals), 6 the generic windowed kernel with
-// constant values (the first implementation), 7-9 kb_spmv_stencil_kernel (any <= 8 diagonals)
+// kb_tune key 10: 0 (default) / 10 the plane-marching kernel where the matrix qualifies (3-D, plane
+// >= one tile), else the tiled second version; 1-5 and 11 tiled second version (5 or 7 diagonals;
+// 11 = its default shape); 6 the generic windowed kernel with constant values (the first
+// implementation); 7-9 kb_spmv_stencil_kernel (any <= 8 diagonals)
 template <int DOT>
 static int kb_launch_stencil(kb_csr_s* A, kb_ws_s* ws, const double* x, double* y, int mode,
                              const double* z, const double* coef, const double* w, double* out,
                              cudaStream_t st) {
-  if (g_stencil_cfg == 10) {  // plane-marching kernel (3-D stencils); else fall through
+  if (g_stencil_cfg == 0 || g_stencil_cfg == 10) {  // plane-marching kernel (3-D stencils); else fall through
     const int rc = kb_launch_march_spmv<DOT>(A, ws, x, y, mode, z, coef, w, out, st);
     if (rc != KB_EUNSUPPORTED) return rc;
   }
-  if ((g_stencil_cfg <= 5 || g_stencil_cfg == 10) && A->pat.nd == 7)
+  if ((g_stencil_cfg <= 5 || g_stencil_cfg >= 10) && A->pat.nd == 7)
     return kb_launch_stencil2<7, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
-  if ((g_stencil_cfg <= 5 || g_stencil_cfg == 10) && A->pat.nd == 5)
+  if ((g_stencil_cfg <= 5 || g_stencil_cfg >= 10) && A->pat.nd == 5)
     return kb_launch_stencil2<5, DOT>(A, ws, x, y, mode, z, coef, w, out, st);
   switch (g_stencil_cfg) {
     case 6: return kb_launch_window_cfg<256, 3, 4, DOT, true>(A, ws, x, y, mode, z, coef, w, out, st);
@@ -1177,7 +1179,8 @@ int kb_cg_is_fused(const kb_cg_state* s, int* fused) {
   return KB_OK;
 }
 
-int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending, void* stream) {
+static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending,
+                          void* stream, cudaEvent_t* ev) {
   KB_REQUIRE(ws != nullptr && s != nullptr, "null argument");
   KB_REQUIRE(s->A && s->x && s->r && s->p && s->Ap && s->slots && s->crit && s->hist && s->stop_at,
              "null field in kb_cg_state");
@@ -1201,6 +1204,7 @@ int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pendi
     double* rr = sl + 4 * (size_t)k;
     ws->gate = s->stop_at;
     ws->gate_tag = i;
+    if (ev) cudaEventRecord(ev[3 * (i - i0)], st);
     if (fused) {
       KbMarchCg cg;
       memset(&cg, 0, sizeof(cg));
@@ -1218,6 +1222,7 @@ int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pendi
       } else {
         rc = kb_spmv(s->A, ws, k, pb[pc], s->Ap, 0, nullptr, nullptr, 1, pb[pc], pAp, stream);
       }
+      if (ev) cudaEventRecord(ev[3 * (i - i0) + 1], st);
       if (rc == KB_OK) {  // alpha; r -= alpha (A p); <r, r>; record step i+1, rho_{i+1} -> nxt
         memset(&cg, 0, sizeof(cg));
         cg.rho_a = cur;
@@ -1232,6 +1237,7 @@ int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pendi
         rc = kb_launch_march<2, 2, false>(s->A, ws, geo, pb[pc], nullptr, 0, nullptr, nullptr,
                                           nullptr, cg, rr, st);
       }
+      if (ev) cudaEventRecord(ev[3 * (i - i0) + 2], st);
       x_pending = 1;
       continue;
     }
@@ -1239,8 +1245,10 @@ int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pendi
     if (i > 0)
       rc = kb_cg_update_p(ws, s->n, k, 0, cur, nxt, alpha, nullptr, nullptr, nullptr, nullptr, s->r,
                           p, x_pending ? s->x : nullptr, x_pending ? 5 : 1, stream);
+    if (ev) cudaEventRecord(ev[3 * (i - i0) + 1], st);  // here: after the p update
     if (rc == KB_OK)
       rc = kb_spmv(s->A, ws, k, p, s->Ap, 0, nullptr, nullptr, 1, p, pAp, stream);
+    if (ev) cudaEventRecord(ev[3 * (i - i0) + 2], st);  // after A p
     if (rc == KB_OK)  // r update + <r,r> + record: hist row (i - i0) <- step i+1, rho_{i+1} -> nxt
       rc = kb_cg_update_xr_record(ws, s->n, k, cur, pAp, nullptr, s->Ap, nullptr, s->r, rr, alpha,
                                   i + 1, s->crit, s->hist - (size_t)(i0 + 1) * k, s->stop_at, nxt,
@@ -1250,6 +1258,56 @@ int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pendi
   ws->gate = saved_gate;
   ws->gate_tag = saved_tag;
   return rc;
+}
+
+int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending, void* stream) {
+  return kb_cg_run_impl(ws, s, i0, n_iters, x_pending, stream, nullptr);
+}
+
+// kb_cg_run with CUDA events around every launch (on the launching stream).  Synchronises the
+// stream at the end and returns the mean duration in ms of the step's phases:
+//   fused path:        ms[0] = p/x update + A p + <p,Ap>,  ms[1] = r update + <r,r>,  ms[2] = 0
+//   three-kernel path: ms[0] = p/x update,  ms[1] = A p + <p,Ap>,  ms[2] = r update + <r,r>
+// total_ms: first event of the first iteration to the end of the last.  For measurement only.
+int kb_cg_run_timed(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending,
+                    void* stream, float* ms, float* total_ms) {
+  KB_REQUIRE(ms != nullptr && total_ms != nullptr && n_iters >= 1 && n_iters <= 100000,
+             "bad argument");
+  KbMarch geo;
+  const bool fused = s != nullptr && s->A != nullptr && kb_cg_fusable(s, &geo);
+  const int ne = 3 * n_iters + 1;
+  cudaEvent_t* ev = new (std::nothrow) cudaEvent_t[ne];
+  if (!ev) return kb_fail(KB_ECUDA, "kb_cg_run_timed: out of memory");
+  for (int i = 0; i < ne; ++i) cudaEventCreate(&ev[i]);
+  int rc = kb_cg_run_impl(ws, s, i0, n_iters, x_pending, stream, ev);
+  cudaEventRecord(ev[ne - 1], S(stream));
+  cudaError_t e = cudaStreamSynchronize(S(stream));
+  ms[0] = ms[1] = ms[2] = 0.f;
+  *total_ms = 0.f;
+  if (rc == KB_OK && e == cudaSuccess) {
+    double acc[3] = {0, 0, 0};
+    for (int i = 0; i < n_iters; ++i) {
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, ev[3 * i], ev[3 * i + 1]);
+      cudaEventElapsedTime(&b, ev[3 * i + 1], ev[3 * i + 2]);
+      cudaEventElapsedTime(&c, ev[3 * i + 2], ev[3 * i + 3]);
+      if (fused) {  // events: start, after the first launch, after the second (== next start)
+        acc[0] += a;
+        acc[1] += b;
+      } else {
+        acc[0] += a;
+        acc[1] += b;
+        acc[2] += c;
+      }
+    }
+    for (int q = 0; q < 3; ++q) ms[q] = (float)(acc[q] / n_iters);
+    cudaEventElapsedTime(total_ms, ev[0], ev[ne - 1]);
+  }
+  for (int i = 0; i < ne; ++i) cudaEventDestroy(ev[i]);
+  delete[] ev;
+  if (rc != KB_OK) return rc;
+  if (e != cudaSuccess) return kb_fail(KB_ECUDA, "kb_cg_run_timed: %s", cudaGetErrorString(e));
+  return KB_OK;
 }
 
 int kb_axpy(kb_ws_t ws, int64_t n, int k, double sign, const double* coef, const double* x,

@@ -205,38 +205,51 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
       const int j1 = min(j0 + g.ch, g.nplanes);
       const int nload = j1 - j0 + 2;
       const int pos0 = c * TR + tid;  // in-plane position of row q = 0
+      // Operands that come from global memory (masks, z / r, w, x of the own rows) are requested
+      // one pass ahead: the windows are usually there when a pass starts, so a load issued at
+      // the top of the pass that needs it would be waited for in full (ncu: the top stall).
+      unsigned mn[RPT];
+      double zn[RPT], wn[RPT], xn[RPT];
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        mn[q] = 0u;
+        zn[q] = wn[q] = xn[q] = 0.0;
+      }
       for (int l = 0; l < nload; ++l, ++cnt) {
         const int slot = (int)(cnt % NS);
-        // --- operands from global memory, requested before the barrier wait ---
         const int jc = j0 + l - 2;  // plane whose rows are computed in this pass (l >= 2)
         unsigned m[RPT];
-        double zv[RPT], wv[RPT];
-        int row[RPT];
+        double zv[RPT], wv[RPT], xo[RPT];
+        int row[RPT], trow[RPT];
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
           const int pos = pos0 + q * 256;
           const long long r64 = (long long)jc * g.P + pos;
           const bool ok = l >= 2 && pos < g.P && r64 < (long long)n_rows;
           row[q] = ok ? (int)r64 : -1;
-          m[q] = ok ? (unsigned)masks[row[q]] : 0u;
-          zv[q] = wv[q] = 0.0;
-          if (ok) {
-            if (KIND == 0 && mode != 0) zv[q] = z[row[q]];
-            if (KIND == 0 && DOT == 1 && !WX) wv[q] = w[row[q]];
-            if (KIND == 2) zv[q] = cg.r[row[q]];
+          m[q] = mn[q];
+          zv[q] = zn[q];
+          wv[q] = wn[q];
+          xo[q] = xn[q];
+          // rows computed in the next pass (plane jc + 1)
+          const long long n64 = r64 + g.P;
+          const bool nok = l >= 1 && l + 1 < nload && pos < g.P && n64 < (long long)n_rows;
+          mn[q] = nok ? (unsigned)masks[n64] : 0u;
+          zn[q] = wn[q] = 0.0;
+          if (nok) {
+            if (KIND == 0 && mode != 0) zn[q] = z[n64];
+            if (KIND == 0 && DOT == 1 && !WX) wn[q] = w[n64];
+            if (KIND == 2) zn[q] = cg.r[n64];
           }
-        }
-        // KIND 1: x of the own rows of the arriving plane (j0 - 1 + l), if it belongs to the item
-        double xo[RPT];
-        int trow[RPT];
-        if (KIND == 1) {
-#pragma unroll
-          for (int q = 0; q < RPT; ++q) {
-            const int pos = pos0 + q * 256;
-            const long long r64 = (long long)(j0 - 1 + l) * g.P + pos;
-            const bool ok = l >= 1 && l <= nload - 2 && pos < g.P && r64 < (long long)n_rows;
-            trow[q] = ok ? (int)r64 : -1;
-            xo[q] = (ok && cg.xv != nullptr) ? cg.xv[trow[q]] : 0.0;
+          if (KIND == 1) {
+            // own rows of the arriving plane j0 - 1 + l (inside the item for 1 <= l <= nload - 2)
+            const long long t64 = r64 + g.P;
+            const bool tok = l >= 1 && l <= nload - 2 && pos < g.P && t64 < (long long)n_rows;
+            trow[q] = tok ? (int)t64 : -1;
+            // x of the own rows of the plane arriving in the next pass
+            const long long u64 = t64 + g.P;
+            const bool uok = l + 1 <= nload - 2 && pos < g.P && u64 < (long long)n_rows;
+            xn[q] = (uok && cg.xv != nullptr) ? cg.xv[u64] : 0.0;
           }
         }
         kb_mbar_wait(&s_full[slot], (cnt / NS) & 1u);
@@ -245,22 +258,41 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
           // rows also go to global memory together with x += alpha p_old  (cg.py:178,196)
           const uint32_t pw = sbase + (uint32_t)slot * wbytes + (uint32_t)tid * 8u;
           const uint32_t rw = rbase + (cnt & 1u) * wbytes + (uint32_t)tid * 8u;
-          const int nel = g.wlen >> 8;       // window entries per thread
-          const int own0 = g.LP >> 8;        // entries [own0, own0 + RPT) are this thread's rows
-          for (int u = 0; u < nel; ++u) {
-            const double pold = kb_ld_f64_shared(pw + (uint32_t)u * 2048u);
-            const double rv = kb_ld_f64_shared(rw + (uint32_t)u * 2048u);
-            const double pn = kb_mul_add(omega, pold, rv);
-            kb_st_f64_shared(pw + (uint32_t)u * 2048u, pn);
-            const int q = u - own0;
-            if (q >= 0 && q < RPT) {
+          const uint32_t own = (uint32_t)g.LP * 8u;  // entries LP/256 ... + RPT are this thread's rows
+          {
+            double po[RPT], ro[RPT];
 #pragma unroll
-              for (int qq = 0; qq < RPT; ++qq) {
-                if (qq == q && trow[qq] >= 0) {
-                  if (cg.xv != nullptr) cg.xv[trow[qq]] = kb_mul_add(alpha, pold, xo[qq]);
-                  cg.p_out[trow[qq]] = pn;
-                }
+            for (int q = 0; q < RPT; ++q) {
+              po[q] = kb_ld_f64_shared(pw + own + (uint32_t)q * 2048u);
+              ro[q] = kb_ld_f64_shared(rw + own + (uint32_t)q * 2048u);
+            }
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+              const double pn = kb_mul_add(omega, po[q], ro[q]);
+              kb_st_f64_shared(pw + own + (uint32_t)q * 2048u, pn);
+              if (trow[q] >= 0) {
+                if (cg.xv != nullptr) __stcs(&cg.xv[trow[q]], kb_mul_add(alpha, po[q], xo[q]));
+                __stcs(&cg.p_out[trow[q]], pn);
               }
+            }
+          }
+          // halo entries on both sides: LP / 256 per side and thread, two at a time
+          const int nh = g.LP >> 8;
+          for (int side = 0; side < 2; ++side) {
+            const uint32_t hb = side == 0 ? 0u : own + (uint32_t)RPT * 2048u;
+            int u = 0;
+            for (; u + 1 < nh; u += 2) {
+              const uint32_t o0 = hb + (uint32_t)u * 2048u, o1 = o0 + 2048u;
+              const double p0 = kb_ld_f64_shared(pw + o0), p1 = kb_ld_f64_shared(pw + o1);
+              const double r0 = kb_ld_f64_shared(rw + o0), r1 = kb_ld_f64_shared(rw + o1);
+              kb_st_f64_shared(pw + o0, kb_mul_add(omega, p0, r0));
+              kb_st_f64_shared(pw + o1, kb_mul_add(omega, p1, r1));
+            }
+            if (u < nh) {
+              const uint32_t o0 = hb + (uint32_t)u * 2048u;
+              const double p0 = kb_ld_f64_shared(pw + o0);
+              const double r0 = kb_ld_f64_shared(rw + o0);
+              kb_st_f64_shared(pw + o0, kb_mul_add(omega, p0, r0));
             }
           }
           __syncwarp();

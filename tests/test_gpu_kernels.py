@@ -185,7 +185,7 @@ def test_pattern_schedule_selection():
     np.testing.assert_array_equal(Ud @ x, U @ x)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 11])
 def test_stencil_kernel_variants_bit_exact(cfg):
     """Constant-diagonal ("stencil") schedule: no index, value or row-pointer stream -- the
     coefficients are kernel parameters.  Every tile configuration, ragged grids, fused

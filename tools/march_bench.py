@@ -33,10 +33,11 @@ def tune(**kw):
     for k, v in kw.items(): lib.kb_tune({"st": 10, "ctas": 11, "l2": 12, "ch": 13, "mc": 14, "fuse": 15}[k], v)
 
 moved = A.moved_bytes(1)
-tune(st=0); ms = spmv_ms(); say(f"N={N} SpMV+dot tiled (stencil2)      : {ms:.4f} ms  {moved/ms/1e6:.0f} GB/s moved")
-for mc in (0, 1, 2, 3):
-    for ch in (0, 16, 64):
-        for l2 in (0, 1):
+tune(st=11); ms = spmv_ms(); say(f"N={N} SpMV+dot tiled (stencil2)      : {ms:.4f} ms  {moved/ms/1e6:.0f} GB/s moved")
+QUICK = len(sys.argv) > 2 and sys.argv[2] == "quick"
+for mc in ((0, 2) if QUICK else (0, 1, 2, 3)):
+    for ch in ((0, 64) if QUICK else (0, 16, 64)):
+        for l2 in ((0,) if QUICK else (0, 1)):
             tune(st=10, mc=mc, ch=ch, l2=l2)
             ms = spmv_ms()
             say(f"N={N} SpMV+dot march mc={mc} ch={ch:2d} l2={l2}: {ms:.4f} ms  {moved/ms/1e6:.0f} GB/s moved")
@@ -54,12 +55,12 @@ def cg_ms(tag):
     say(f"CG step N={N} {tag}: {ms:.4f} ms = {1e3/ms:.1f} it/s  (fused={st.fused_march}, resnorm[36]={h[-1][0]:.15e})")
     del st
 
-tune(fuse=0, st=0); cg_ms("three kernels, tiled SpMV  ")
+tune(fuse=0, st=11); cg_ms("three kernels, tiled SpMV  ")
 tune(fuse=0, st=10); cg_ms("three kernels, march SpMV  ")
 tune(st=0)
-for mc in (0, 2, 3, 1):
-    for ch in (0, 16, 64):
-        for l2 in ((0, 1) if ch == 0 else (0,)):
+for mc in ((0, 2) if QUICK else (0, 2, 3, 1)):
+    for ch in ((0, 64) if QUICK else (0, 16, 64)):
+        for l2 in ((0, 1) if ch == 0 and not QUICK else (0,)):
             tune(fuse=1, mc=mc, ch=ch, l2=l2)
             cg_ms(f"fused march mc={mc} ch={ch:2d} l2={l2}")
 tune(fuse=1, mc=0, ch=0, l2=0)
