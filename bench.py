@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--size", type=int, default=512, help="grid points per dimension")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-trace", action="store_true",
+                    help="diagnostic: synchronising stage timers inside the e2e solve (adds 'stages')")
     ap.add_argument("--cpu-size", type=int, default=0, help="grid size of the CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -521,9 +523,17 @@ def run_e2e(args, A, b, world, rank, dev, barrier):
         A_host.has_canonical_format = True
         b_np = b_host.numpy()
         barrier()
+        if args.e2e_trace:
+            from krylov_b200 import _trace
+            _trace.enable(True)
         t0 = time.perf_counter()
         sol, info = kb.cg(A_host, b_np, tol=1e-8, maxiter=20000)  # numpy in -> numpy out
         dt = time.perf_counter() - t0
+        if args.e2e_trace:
+            stages = _trace.take()
+            _trace.enable(False)
+            for lab, sec in stages:
+                print(f"[e2e-trace] {sec*1e3:9.1f} ms  {lab}", file=sys.stderr)
         h2d = rp.numel() * 4 + ci.numel() * 4 + va.numel() * 8 + n * 8
         d2h = n * 8
         how = ("krylov_b200.cg(scipy.sparse.csr_matrix in pinned host memory, NumPy b, tol=1e-8) "

@@ -22,6 +22,7 @@ import torch
 
 import ctypes as C
 
+from . import _trace
 from ._alg import Alg, nz
 from ._lib import CgState, check, lib
 from .device import Ops, cur_stream, ptr
@@ -35,7 +36,9 @@ def cg(A, b, M=None, Ml=None, inner=None, x0=None, tol=1e-5, atol=1.0e-15, maxit
        return_arnoldi=False, callback=None, inner_product=None):
     if inner is None and inner_product is not None:  # alias used by BASELINE.json's wording
         inner = inner_product
+    _trace.mark("cg: enter")
     prob = Problem(A, b, x0)
+    _trace.mark("cg: Problem (b, x0, A on the device)")
     maxiter = prob.n if maxiter is None else int(maxiter)
     with torch.cuda.device(prob.device):
         if inner is None and prob.A_csr is not None:
@@ -291,6 +294,7 @@ class FusedCG:
 
 def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback, M=None, Ml=None):
     st = FusedCG(prob.A_csr, prob.b, prob.x0, tol, atol, M=M, Ml=Ml)
+    _trace.mark("cg: FusedCG set-up (vectors, r0 = b - A x0)")
     ops, crit = st.ops, st.crit
     if callback is not None:
         callback(prob.to_user(prob.x0), prob.to_user(st.r))
@@ -329,8 +333,11 @@ def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback, M=None, Ml=Non
     if xk is None:
         xk = st.current_x()
     prob.launches = ops.launches
-    return _finish(prob, success, xk, st.kk, resn,
-                   log.result(st.kk) if log is not None else None)
+    _trace.mark("cg: iterations + explicit residual check")
+    out = _finish(prob, success, xk, st.kk, resn,
+                  log.result(st.kk) if log is not None else None)
+    _trace.mark("cg: result to the caller's array kind (download)")
+    return out
 
 
 # ---------------------------------------------------------------------------

@@ -11,6 +11,7 @@ import ctypes as C
 import numpy as np
 import torch
 
+from . import _trace
 from ._lib import check, lib
 from .device import Ops, as_device_matrix, cur_stream, ptr, require_cuda
 
@@ -48,10 +49,14 @@ class CsrMatrix:
         if int(torch.as_tensor(colidx).numel()) != self.nnz:
             raise ValueError("colidx and vals differ in length")
         self.rowptr = rowptr
+        _trace.mark("csr: rowptr uploaded")
         with torch.cuda.device(dev):
             self.colidx = _padded_upload(colidx, torch.int32, dev)
+            _trace.mark("csr: colidx uploaded")
             self.vals = _padded_upload(vals, torch.float64, dev)
+        _trace.mark("csr: vals uploaded")
         self._finish()
+        _trace.mark("csr: kb_csr_create (statistics, pattern, constant diagonals)")
 
     @classmethod
     def _from_device_arrays(cls, rowptr, colidx_padded, vals_padded, nnz, shape):
