@@ -213,6 +213,12 @@ int kb_cg_run_timed(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x
 /* y += sign * coef[c] * x   (product rounded, then sum: NumPy temporaries) */
 int kb_axpy(kb_ws_t ws, int64_t n, int k, double sign, const double* coef, const double* x,
             double* y, void* stream);
+/* out = ca[c] * x + cb[c] * y, every product rounded before the sum (NumPy temporaries).
+ * ca == NULL: the first term is x itself; cb == NULL: out = ca * x.  out may alias x or y.
+ * Vector statements of the short-recurrence solvers (bicgstab.py:100-133, cgs.py:92-104,
+ * qmr.py:101-146, cgr.py:83-84, chebyshev.py:86). */
+int kb_lincomb(kb_ws_t ws, int64_t n, int k, const double* ca, const double* x, const double* cb,
+               const double* y, double* out, void* stream);
 /* y = x + coef[c] * y */
 int kb_xpby(kb_ws_t ws, int64_t n, int k, const double* x, const double* coef, double* y,
             void* stream);

@@ -60,9 +60,17 @@ class Alg:
     def xpby(self, y, x, a):
         self.ops.xpby(y, x, self.coef(a))
 
-    def div(self, x, d):
-        out = torch.empty_like(x)
+    def div(self, x, d, out=None):
+        out = torch.empty_like(x) if out is None else out
         self.ops.div_scale(out, x, self.coef(d))
+        return out
+
+    def lincomb(self, x, ca=None, y=None, cb=None, out=None):
+        """ca * x + cb * y with NumPy's rounding (each product, then the sum); ``ca=None``: x
+        itself, ``y=None``: no second term.  ``out`` may be x or y."""
+        out = torch.empty_like(x) if out is None else out
+        self.ops.lincomb(out, None if ca is None else self.coef(ca), x,
+                         None if y is None else self.coef(cb), y)
         return out
 
     def add(self, x, y):

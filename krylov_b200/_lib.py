@@ -93,6 +93,7 @@ SIGNATURES = {
     "kb_cg_run_timed": [vp, C.POINTER(CgState), i32, i32, i32, vp, C.POINTER(C.c_float),
                         C.POINTER(C.c_float)],
     "kb_axpy": [vp, i64, i32, f64, vp, vp, vp, vp],
+    "kb_lincomb": [vp, i64, i32, vp, vp, vp, vp, vp, vp],
     "kb_xpby": [vp, i64, i32, vp, vp, vp, vp],
     "kb_div_scale": [vp, i64, i32, vp, vp, vp, vp],
     "kb_add": [vp, i64, i32, vp, vp, vp, vp],

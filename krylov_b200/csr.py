@@ -114,6 +114,25 @@ class CsrMatrix:
         return cls(A.crow_indices(), A.col_indices(), A.values(), A.shape,
                    device or (A.device if A.is_cuda else None))
 
+    @property
+    def T(self):
+        """Transposed matrix as a CsrMatrix with ascending columns (cached): ``A.T @ x`` then
+        accumulates every entry over the rows of A in ascending order -- the order of SciPy's
+        ``csc_matvec`` behind the reference's ``rmatvec`` (_helpers.py:65-77), so the adjoint
+        product is bit-identical too.  Built once on the host (set-up, not the hot path)."""
+        t = getattr(self, "_T", None)
+        if t is None:
+            import scipy.sparse
+
+            nnz = self.nnz
+            host = scipy.sparse.csr_matrix(
+                (self.vals[:nnz].cpu().numpy(), self.colidx[:nnz].cpu().numpy(),
+                 self.rowptr.cpu().numpy()), shape=self.shape)
+            t = CsrMatrix.from_scipy(host.T.tocsr(), self.device)
+            t._T = self
+            self._T = t
+        return t
+
     # ------------------------------------------------------------- queries --
     def info(self):
         nr, nc, nz = C.c_int64(), C.c_int64(), C.c_int64()

@@ -1320,6 +1320,19 @@ int kb_axpy(kb_ws_t ws, int64_t n, int k, double sign, const double* coef, const
   return KB_OK;
 }
 
+int kb_lincomb(kb_ws_t ws, int64_t n, int k, const double* ca, const double* x, const double* cb,
+               const double* y, double* out, void* stream) {
+  KB_VEC_PROLOGUE();
+  KB_REQUIRE(x != nullptr && out != nullptr, "null argument");
+  KB_REQUIRE(cb == nullptr || y != nullptr, "cb needs y");
+  KB_REQUIRE(ca != nullptr || cb != nullptr, "nothing to do: give ca and/or cb");
+  if (total == 0) return KB_OK;
+  const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
+  kb_lincomb_kernel<<<grid, block, 0, st>>>(total, k, ca, x, cb, y, out, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
 int kb_xpby(kb_ws_t ws, int64_t n, int k, const double* x, const double* coef, double* y,
             void* stream) {
   KB_VEC_PROLOGUE();

@@ -219,6 +219,43 @@ kb_axpy_kernel(int64_t total, int k, double sign, const double* __restrict__ coe
   KB_TILE_LOOP_END
 }
 
+// out = ca[c] * x + cb[c] * y   (each product rounded, then the sum: NumPy temporaries).
+// ca == nullptr: the x term is x itself; cb == nullptr: no y term (out = ca * x, a scaling).
+// out may alias x or y.  Statements of the short-recurrence solvers (qmr.py:141-146,
+// bicgstab.py:100,110,113,132-133, cgs.py:92-93,100).            16-24 B/element
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_lincomb_kernel(int64_t total, int k, const double* __restrict__ ca, const double* x,
+                  const double* __restrict__ cb, const double* y, double* out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const int c = threadIdx.x % k;
+  const bool hx = ca != nullptr, hy = cb != nullptr;
+  const double a = hx ? ca[c] : 1.0;
+  const double b = hy ? cb[c] : 0.0;
+  KB_TILE_LOOP_BEGIN(total)
+  if (kb_full) {
+    double xv[KB_UNROLL], yv[KB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      xv[u] = x[KB_IDX(u)];
+      yv[u] = hy ? y[KB_IDX(u)] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      const double t = hx ? __dmul_rn(a, xv[u]) : xv[u];
+      out[KB_IDX(u)] = hy ? __dadd_rn(t, __dmul_rn(b, yv[u])) : t;
+    }
+  } else {
+    for (int u = 0; u < KB_UNROLL; ++u) {
+      const int64_t i = KB_IDX(u);
+      if (i < total) {
+        const double t = hx ? __dmul_rn(a, x[i]) : x[i];
+        out[i] = hy ? __dadd_rn(t, __dmul_rn(b, y[i])) : t;
+      }
+    }
+  }
+  KB_TILE_LOOP_END
+}
+
 // y = x + coef[c] * y         24 B/element
 __global__ void __launch_bounds__(KB_BLOCK)
 kb_xpby_kernel(int64_t total, int k, const double* __restrict__ x,

@@ -189,6 +189,13 @@ class Ops:
         check(lib.kb_axpy(self.ws.handle, self.n, self.k, float(sign), ptr(coef), ptr(x), ptr(y),
                           cur_stream()))
 
+    def lincomb(self, out, ca, x, cb=None, y=None):
+        """out = ca * x + cb * y (products rounded, then the sum); ca None: x itself; cb None:
+        no y term.  out may alias x or y."""
+        self.launches += 1
+        check(lib.kb_lincomb(self.ws.handle, self.n, self.k, ptr(ca), ptr(x), ptr(cb), ptr(y),
+                             ptr(out), cur_stream()))
+
     def xpby(self, y, x, coef):
         self.launches += 1
         check(lib.kb_xpby(self.ws.handle, self.n, self.k, ptr(x), ptr(coef), ptr(y), cur_stream()))

