@@ -69,12 +69,21 @@ _WS_POOL = {}
 
 def _borrow_workspace(device, k):
     free = _WS_POOL.setdefault((device.index, int(k)), [])
+    # A pooled workspace can be dead: when an Ops object dies as part of a reference cycle the
+    # garbage collector runs the finalizers in arbitrary order, so Workspace.__del__ may have
+    # destroyed the handle before or after Ops.__del__ put the object back here.
+    while free:
+        ws = free.pop()
+        if getattr(ws, "handle", None):
+            return ws
     # room for the multi-sum reductions of classical Gram-Schmidt (up to 16 sums per launch)
-    return free.pop() if free else Workspace(max(int(k), min(256, 16 * int(k))))
+    return Workspace(max(int(k), min(256, 16 * int(k))))
 
 
 def _return_workspace(device, k, ws):
     try:
+        if not getattr(ws, "handle", None):
+            return
         lib.kb_ws_set_gate(ws.handle, None, 0)
         lib.kb_ws_set_comm(ws.handle, None, 0)
         free = _WS_POOL.setdefault((device.index, int(k)), [])
