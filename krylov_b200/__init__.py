@@ -19,7 +19,8 @@ from .operators import (  # noqa: F401
 from .cg import cg  # noqa: F401
 from .minres import minres  # noqa: F401
 from .gmres import gmres  # noqa: F401
-from .shortrec import bicg, bicgstab, cgne, cgnr, cgr, cgs, chebyshev, gcr, qmr  # noqa: F401
+from .shortrec import (  # noqa: F401
+    bicg, bicgstab, cgne, cgnr, cgr, cgs, chebyshev, gcr, qmr, symmlq)
 from .givens import givens  # noqa: F401
 from .householder import Householder  # noqa: F401
 from .arnoldi import ArnoldiHouseholder, ArnoldiLanczos, ArnoldiMGS  # noqa: F401

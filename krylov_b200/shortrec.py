@@ -1,7 +1,7 @@
 """Short-recurrence solvers next to cg / minres / gmres: ``bicgstab``, ``cgs``,
-``bicg``, ``qmr``, ``cgne``, ``cgnr``, ``cgr``, ``gcr``, ``chebyshev`` with the reference's
-signatures, defaults, stopping rule and ``Info`` (reference bicgstab.py, cgs.py, bicg.py, qmr.py,
-cgne.py, cgnr.py, cgr.py, gcr.py, chebyshev.py).
+``bicg``, ``qmr``, ``cgne``, ``cgnr``, ``cgr``, ``gcr``, ``chebyshev``, ``symmlq`` with the
+reference's signatures, defaults, stopping rule and ``Info`` (reference bicgstab.py, cgs.py,
+bicg.py, qmr.py, cgne.py, cgnr.py, cgr.py, gcr.py, chebyshev.py, symmlq.py).
 
 They run on the *general* device path: every vector statement of the reference loop is one kernel
 launch through the C ABI (kb_spmv incl. the transposed matrix for ``rmatvec``, kb_dot, kb_axpy,
@@ -19,7 +19,7 @@ import torch
 from ._alg import Alg, nz
 from .operators import Info, Problem
 
-__all__ = ["bicgstab", "cgs", "bicg", "qmr", "cgne", "cgnr", "cgr", "gcr", "chebyshev"]
+__all__ = ["bicgstab", "cgs", "bicg", "qmr", "cgne", "cgnr", "cgr", "gcr", "chebyshev", "symmlq"]
 
 
 class _Drive:
@@ -48,11 +48,35 @@ class _Drive:
     def user(self, *vecs):
         return tuple(self.prob.to_user(v) for v in vecs)
 
-    def run(self, norm, step, first, cb_vecs):
+    def run(self, norm, step, first, cb_vecs, xout=None):
         """step(k, crit) advances self.x and returns the new residual norm (host (k,) array), or
         ("leave", resnorm) to finish successfully at once (bicgstab.py:119-122).  cb_vecs() gives
-        the callback's arguments in the caller's array kind."""
+        the callback's arguments in the caller's array kind.  xout(): the point that is checked
+        and returned when it is not self.x itself (symmlq's CG point; the step then calls the
+        callback on its own)."""
         prob, alg = self.prob, self.alg
+        if xout is not None:
+            with prob.on_device():
+                if self.callback is not None:
+                    self.callback(*cb_vecs())
+                res = [first]
+                crit = np.maximum(self.tol * res[0], self.atol)
+                k, ok, xo = 0, False, None
+                while True:
+                    if np.all(res[-1] <= crit):
+                        xo = xout()
+                        res[-1] = norm(alg.residual(self.A, self.b, xo))
+                        if np.all(res[-1] <= crit):
+                            ok = True
+                            break
+                    if k == self.maxiter:
+                        xo = xout()
+                        break
+                    res.append(step(k, crit))
+                    k += 1
+            prob.launches = alg.ops.launches
+            xk = prob.to_user(xo) if xo is not None else None
+            return (xk if ok else None), Info(ok, xk, k, [prob.scalars_to_user(r) for r in res])
         with prob.on_device():
             if self.callback is not None:
                 self.callback(*cb_vecs())
@@ -395,3 +419,65 @@ def chebyshev(A, b, eigenvalue_estimates, M=None, x0=None, inner=None, tol=1e-5,
         return norm(s["r"])
 
     return d.run(norm, step, norm(s["r"]), lambda: d.user(d.x, s["r"]))
+
+
+def symmlq(A, b, M=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15, maxiter=None, callback=None):
+    """reference symmlq.py:15-161.  As in the reference, ``resnorms`` holds the norm of the
+    unnormalised Lanczos vector and what is checked / returned is the CG point."""
+    d = _Drive(A, b, x0, inner, tol, atol, maxiter, callback)
+    alg, Aop = d.alg, d.A
+    M = d.op(M)
+    norm = d.norm_with(None)
+    s = {"zeta": [None, 0.0, None], "c": [1.0, 1.0, None], "s": [0.0, 0.0, None],
+         "u_old": torch.zeros_like(d.b), "v_old": torch.zeros_like(d.b), "r": d.r0.clone()}
+    first = norm(s["r"])
+    s["z"] = alg.apply(M, s["r"])
+    s["beta"] = np.sqrt(alg.inner(s["r"], s["z"]))
+    beta1 = s["beta"]
+    s["v"] = alg.div(s["r"], s["beta"])
+    s["u"] = alg.div(s["z"], s["beta"])
+    s["w_bar"] = s["u"].clone()
+
+    def cg_point():
+        c0 = s["c"][0]
+        zc = s["zeta"][0] / np.where(c0 != 0.0, c0, 1.0e-15)
+        return alg.lincomb(d.x, None, s["w_bar"], zc)
+
+    def step(k, crit):
+        if k > 0:
+            s["v_old"], s["u_old"] = s["v"], s["u"]
+            rb = 1.0 / s["beta"]
+            s["v"] = alg.lincomb(s["r"], rb)
+            s["u"] = alg.lincomb(s["z"], rb)
+            c0, s0 = s["c"][0], s["s"][0]
+            w = alg.lincomb(s["w_bar"], c0, s["u"], s0)
+            alg.lincomb(s["w_bar"], -np.asarray(s0), s["u"], c0, out=s["w_bar"])
+            alg.axpy(d.x, s["zeta"][0], w)
+            s["zeta"][2], s["zeta"][1] = s["zeta"][1], s["zeta"][0]
+        r = Aop(s["u"])  # Lanczos
+        alpha = alg.inner(s["u"], r)
+        z = alg.apply(M, r)
+        if z is r:
+            z = r.clone()
+        alg.axpy(r, alpha, s["v"], sign=-1.0)
+        alg.axpy(r, s["beta"], s["v_old"], sign=-1.0)
+        alg.axpy(z, alpha, s["u"], sign=-1.0)
+        alg.axpy(z, s["beta"], s["u_old"], sign=-1.0)
+        s["r"], s["z"] = r, z
+        beta_old = s["beta"]
+        s["beta"] = np.sqrt(alg.inner(r, z))
+        c, sn, zeta = s["c"], s["s"], s["zeta"]
+        c[2], c[1] = c[1], c[0]
+        sn[2], sn[1] = sn[1], sn[0]
+        gamma_bar = c[1] * alpha - c[2] * sn[1] * beta_old
+        gamma = np.sqrt(gamma_bar * gamma_bar + s["beta"] * s["beta"])
+        delta = sn[1] * alpha + c[2] * c[1] * beta_old
+        epsilon = sn[2] * beta_old
+        c[0] = gamma_bar / gamma
+        sn[0] = s["beta"] / gamma
+        zeta[0] = beta1 / gamma if k == 0 else -(delta * zeta[1] + epsilon * zeta[2]) / gamma
+        if callback is not None:
+            callback(*d.user(cg_point(), r))
+        return norm(r)
+
+    return d.run(norm, step, first, lambda: d.user(d.x, s["r"]), xout=cg_point)

@@ -6,6 +6,7 @@ primitive set (sparse product, transposed product, inner product, axpy):
     bicgstab (bicgstab.py:24-144)   cgs  (cgs.py:24-117)    bicg (bicg.py:25-116)
     qmr      (qmr.py:22-160)        cgne (cgne.py:18-45)    cgnr (cgnr.py:15-21)
     cgr      (cgr.py:14-100)        gcr  (gcr.py:16-97)     chebyshev (chebyshev.py:13-99)
+    symmlq   (symmlq.py:15-161)
 
 Same rules as oracle/krylov_oracle.py: only tests/ (and bench legs) import it, nothing under
 krylov_b200/ does.  Parity status: PINNED -- tests/golden/make_golden_extra.py runs the real
@@ -27,7 +28,8 @@ import numpy as np
 
 from .krylov_oracle import Info, _Eye, _nz, default_inner
 
-__all__ = ["bicgstab", "cgs", "bicg", "qmr", "cgne", "cgnr", "cgr", "gcr", "chebyshev", "adjoint"]
+__all__ = ["bicgstab", "cgs", "bicg", "qmr", "cgne", "cgnr", "cgr", "gcr", "chebyshev", "symmlq",
+           "adjoint"]
 
 
 class adjoint:
@@ -91,9 +93,13 @@ class _Loop:
         self.A, self.b, self.norm = A, b, norm
         self.tol, self.atol, self.maxiter, self.callback = tol, atol, maxiter, callback
 
-    def run(self, state, step, first_norm, cb_args):
+    def run(self, state, step, first_norm, cb_args, xout=None):
         """state.x is the iterate; step(k) advances it and returns the new residual norm, or the
-        tuple ("leave", resnorm) to finish successfully without appending (bicgstab.py:119-122)."""
+        tuple ("leave", resnorm) to finish successfully without appending (bicgstab.py:119-122).
+        xout(): the point that is checked and returned when it is not state.x itself
+        (symmlq.py:84-87,95-103: the CG point)."""
+        if xout is not None:
+            return self._run_xout(state, step, first_norm, cb_args, xout)
         if self.callback is not None:
             self.callback(*cb_args())
         res = [first_norm]
@@ -117,6 +123,27 @@ class _Loop:
             res.append(out)
             k += 1
         return (state.x if ok else None), Info(ok, state.x, k, res)
+
+
+    def _run_xout(self, state, step, first_norm, cb_args, xout):
+        if self.callback is not None:
+            self.callback(*cb_args())
+        res = [first_norm]
+        crit = np.maximum(self.tol * res[0], self.atol)
+        k, ok, xo = 0, False, None
+        while True:
+            if np.all(res[-1] <= crit):
+                xo = xout()
+                res[-1] = self.norm(self.b - self.A @ xo)
+                if np.all(res[-1] <= crit):
+                    ok = True
+                    break
+            if k == self.maxiter:
+                xo = xout()
+                break
+            res.append(step(k, crit))
+            k += 1
+        return (xo if ok else None), Info(ok, xo, k, res)
 
 
 class _S:
@@ -452,3 +479,78 @@ def chebyshev(A, b, eigenvalue_estimates, M=None, x0=None, inner=None, tol=1e-5,
 
     return _Loop(A, b, norm, tol, atol, maxiter, callback).run(
         s, step, norm(s.r), lambda: (s.x, s.r))
+
+
+# -------------------------------------------------------------------- SYMMLQ --
+def symmlq(A, b, M=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15, maxiter=None, callback=None):
+    """symmlq.py:15-161 (Paige/Saunders): Lanczos + LQ; the iterate x is the LQ point, what is
+    checked and returned is the CG point x + (zeta / c) w_bar.  ``resnorms`` holds the norm of the
+    unnormalised Lanczos vector r (symmlq.py:156), not of a residual; the in-loop callback sees
+    (CG point, that r).  No guard on beta = 0 (a zero right-hand side divides by zero there)."""
+    b = np.asarray(b)
+    _shapes(A, b)
+    A, M = _op(A), _op(M)
+    inner = default_inner(b.shape) if inner is None else inner
+    norm = _make_norm(inner, _EyeR())
+    s = _S()
+    # rotation / zeta history: cur, prev, prev2  (the reference's lists [0], [-1], [-2])
+    s.zeta = [None, 0.0, None]
+    s.c = [1.0, 1.0, None]
+    s.s = [0.0, 0.0, None]
+    s.u_old = np.zeros_like(b)
+    s.v_old = np.zeros_like(b)
+    if x0 is None:
+        s.x, s.r = np.zeros_like(b), b.copy()
+    else:
+        s.x = np.array(x0)
+        s.r = b - A @ x0
+    first = norm(s.r)
+    s.z = M @ s.r
+    s.beta = np.sqrt(inner(s.r, s.z))
+    beta1 = s.beta
+    s.v = s.r / s.beta
+    s.u = s.z / s.beta
+    s.w_bar = s.u.copy()
+
+    def cg_point():
+        zc = s.zeta[0] / np.where(s.c[0] != 0.0, s.c[0], 1.0e-15)
+        return s.x + zc * s.w_bar
+
+    def step(k, crit):
+        if k > 0:
+            s.v_old, s.u_old = s.v.copy(), s.u.copy()
+            s.v = s.r * (1.0 / s.beta)
+            s.u = s.z * (1.0 / s.beta)
+            w = s.c[0] * s.w_bar + s.s[0] * s.u
+            s.w_bar = -s.s[0] * s.w_bar + s.c[0] * s.u
+            s.x += s.zeta[0] * w
+            s.zeta[2], s.zeta[1] = s.zeta[1], s.zeta[0]
+        s.r = A @ s.u  # Lanczos
+        alpha = inner(s.u, s.r)
+        s.z = M @ s.r
+        s.r = s.r - alpha * s.v - s.beta * s.v_old
+        s.z = s.z - alpha * s.u - s.beta * s.u_old
+        beta_old = s.beta
+        s.beta = np.sqrt(inner(s.r, s.z))
+        s.c[2], s.c[1] = s.c[1], s.c[0]
+        s.s[2], s.s[1] = s.s[1], s.s[0]
+        gamma_bar = s.c[1] * alpha - s.c[2] * s.s[1] * beta_old
+        gamma = np.sqrt(gamma_bar * gamma_bar + s.beta * s.beta)
+        delta = s.s[1] * alpha + s.c[2] * s.c[1] * beta_old
+        epsilon = s.s[2] * beta_old
+        s.c[0] = gamma_bar / gamma
+        s.s[0] = s.beta / gamma
+        if k == 0:
+            s.zeta[0] = beta1 / gamma
+        else:
+            s.zeta[0] = -(delta * s.zeta[1] + epsilon * s.zeta[2]) / gamma
+        if callback is not None:
+            callback(cg_point(), s.r)
+        return norm(s.r)
+
+    # the first callback gets (x, r) before the loop (symmlq.py:63-64); the driver's in-loop
+    # callback is replaced by the one inside step (it needs the CG point)
+    if callback is not None:
+        callback(s.x, s.r)
+    loop = _Loop(A, b, norm, tol, atol, maxiter, None)
+    return loop.run(s, step, first, lambda: (), xout=cg_point)

@@ -65,6 +65,19 @@ def extra_cases():
     bd = np.ones(40)
     for name in ("bicgstab", "cgs", "bicg", "qmr", "gcr"):
         c[f"dense_{name}"] = (name, D, bd, dict(tol=1e-10, maxiter=200))
+    # symmlq: the reference records the norm of the Lanczos vector, so it only "converges" when
+    # the Krylov space is exhausted -- its own tests use 5 x 5 problems (tests/test_symmlq.py)
+    a5 = np.linspace(1.0, 2.0, 5)
+    a5i = a5.copy(); a5i[-1] = -1.0   # linear_problems.py:66-72 symmetric_indefinite
+    a5p = a5.copy(); a5p[-1] = 1e-2   # linear_problems.py:5-10 spd_dense
+    c["sym5_symmlq_indef"] = ("symmlq", np.diag(a5i), np.ones(5), dict(maxiter=10))
+    c["sym5_symmlq_spd"] = ("symmlq", np.diag(a5p), np.ones(5), dict(tol=1e-7, maxiter=10))
+    c["sym5_symmlq_k3"] = ("symmlq", np.diag(a5p), np.ones((5, 3)), dict(tol=1e-7, maxiter=10))
+    S = st.shifted_laplace3d(6)
+    _, bs = rhs(S, (S.shape[0],), seed=9)
+    c["sl6_symmlq_25"] = ("symmlq", S, bs, dict(tol=1e-9, maxiter=25))
+    c["p8_symmlq_M_30"] = ("symmlq", P, bp, dict(tol=1e-9, maxiter=30, M=_jacobi(P)))
+    c["p8_symmlq_x0_30"] = ("symmlq", P, bp, dict(tol=1e-9, maxiter=30, x0=np.linspace(0.0, 1.0, npn)))
     # zero right-hand side: zero steps
     for name in ("bicgstab", "cgs", "bicg", "qmr", "cgr", "gcr"):
         c[f"zero_{name}"] = (name, P, np.zeros(npn), dict(tol=1e-7))

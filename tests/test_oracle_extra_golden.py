@@ -66,3 +66,13 @@ def test_callback_counts_like_reference():
                                          callback=lambda x, r: cnt.__setitem__(0, cnt[0] + 1))
         assert info.success
         assert cnt[0] == info.numsteps + 1
+
+
+def test_reference_known_answers_symmlq():
+    """reference tests/test_symmlq.py:16-32"""
+    a = np.linspace(1.0, 2.0, 5)
+    a[-1] = -1.0
+    _, info = orx.symmlq(np.diag(a), np.ones(5), maxiter=10)
+    ref = np.array([2.23606797749979, 0.9823441352194251, 0.5792270481089666, 0.2307060320183781,
+                    0.16833036914998076, 2.5918417478740246e-15])
+    assert np.all(np.abs(np.asarray(info.resnorms) - ref) < 1.0e-13 * (1.0 + np.abs(ref)))

@@ -1,4 +1,4 @@
-"""Host logic of krylov_b200.shortrec (bicgstab, cgs, bicg, qmr, cgr, gcr, chebyshev) against the
+"""Host logic of krylov_b200.shortrec (bicgstab, cgs, bicg, qmr, cgr, gcr, chebyshev, symmlq) against the
 reference's golden outputs, with the device layer replaced by tests/fake_device.py.  CPU suite: the
 kernels behind every statement are covered by tests/test_gpu_shortrec.py on the B200."""
 import os
