@@ -119,16 +119,24 @@ class CsrMatrix:
         """Transposed matrix as a CsrMatrix with ascending columns (cached): ``A.T @ x`` then
         accumulates every entry over the rows of A in ascending order -- the order of SciPy's
         ``csc_matvec`` behind the reference's ``rmatvec`` (_helpers.py:65-77), so the adjoint
-        product is bit-identical too.  Built once on the host (set-up, not the hot path)."""
+        product is bit-identical too.  Built once on the device (set-up, not the hot path):
+        entries sorted by (column, row), row pointers from the column counts."""
         t = getattr(self, "_T", None)
         if t is None:
-            import scipy.sparse
-
-            nnz = self.nnz
-            host = scipy.sparse.csr_matrix(
-                (self.vals[:nnz].cpu().numpy(), self.colidx[:nnz].cpu().numpy(),
-                 self.rowptr.cpu().numpy()), shape=self.shape)
-            t = CsrMatrix.from_scipy(host.T.tocsr(), self.device)
+            nnz, (nr, nc) = self.nnz, self.shape
+            with torch.cuda.device(self.device):
+                rp = self.rowptr.to(torch.int64)
+                rows = torch.repeat_interleave(torch.arange(nr, device=self.device), rp[1:] - rp[:-1])
+                cols = self.colidx[:nnz].to(torch.int64)
+                perm = torch.argsort(cols * nr + rows)  # keys are unique: any sort gives one order
+                del rows
+                new_rp = torch.zeros(nc + 1, dtype=torch.int64, device=self.device)
+                new_rp[1:] = torch.cumsum(torch.bincount(cols, minlength=nc), 0)
+                del cols
+                # row index of every sorted entry = searchsorted of its position in rowptr
+                new_cols = (torch.searchsorted(rp, perm, right=True) - 1).to(torch.int32)
+                new_vals = self.vals[:nnz][perm]
+                t = CsrMatrix(new_rp.to(torch.int32), new_cols, new_vals, (nc, nr), self.device)
             t._T = self
             self._T = t
         return t
