@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--size", type=int, default=512, help="grid points per dimension")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-general", action="store_true",
+                    help="skip the extra runs with the matrix streamed from HBM (pattern / stream)")
     ap.add_argument("--e2e-trace", action="store_true",
                     help="diagnostic: synchronising stage timers inside the e2e solve (adds 'stages')")
     ap.add_argument("--cpu-size", type=int, default=0, help="grid size of the CPU sample (0 = auto)")
@@ -337,7 +339,26 @@ def ours(args):
             others = []
             step_moved = A.moved_bytes(1) + 64 * n_own
             tkey = info_sched.get("schedule")
+        # the same workload with the matrix streamed from HBM (what a matrix with variable
+        # coefficients costs): "pattern" = values + 16-bit masks, "stream" = plain CSR
+        general = {}
+        if info_sched.get("schedule") == "stencil" and not args.no_general:
+            for sched in ("pattern", "stream"):
+                try:
+                    A.set_schedule(sched)
+                    st2 = FusedCG(A, b, x0, tol=0.0, atol=0.0)
+                    st2.run(max(W, 3))
+                    ph, tot, _ = st2.run_timed(min(K, 50))
+                    general[sched] = {"value": min(K, 50) / (tot / 1e3), "unit": UNIT,
+                                      "ms_per_step": tot / min(K, 50),
+                                      "phases_ms": {"p_x_update_ms": ph[0], "spmv_dot_ms": ph[1],
+                                                    "r_update_norm_ms": ph[2]},
+                                      "spmv_streamed_GBs": A.moved_bytes(1) / (ph[1] * 1e-3) / 1e9}
+                    del st2
+                finally:
+                    A.set_schedule("auto")
     else:
+        general = {}
         hist0 = st.hist.data_ptr()  # every record lands in history row 0 (not read in the bench)
         it = 0
         for _ in range(W):
@@ -411,6 +432,7 @@ def ours(args):
         "moved_bytes_per_launch": k_moved, "achieved_moved": achieved_moved,
         "frac_moved": achieved_moved / peak,
         "phases_ms": phases, "other_kernels": others,
+        "matrix_streamed_variants": general,
         "note": ("achieved/frac use the CSR byte model of SURVEY.md 8d (12 B per nonzero + row "
                  "pointers + every vector pass); on this matrix the library detects constant "
                  "diagonals and streams no matrix values, indices or row pointers (a 2-byte mask "

@@ -511,3 +511,38 @@ def test_fused_marching_cg_is_selected():
     P = st.poisson3d(32).tocsr()
     P.data[5] = np.nextafter(P.data[5], 0.0)  # variable coefficients
     assert not fused(P)
+
+
+def test_fused_marching_cg_step_by_step_paths():
+    """callback / return_arnoldi drive the fused two-launch path one iteration per call (p buffer
+    parity tracked across calls, x flushed for every callback): same results as the three-kernel
+    path and as the oracle."""
+    from krylov_b200._lib import lib
+    from oracle import krylov_oracle as orc
+
+    A = st.poisson3d(32)
+    n = A.shape[0]
+    b = A @ rng.standard_normal(n)
+    out = {}
+    for fuse in (0, 1):
+        lib.kb_tune(15, fuse)
+        try:
+            seen = []
+            sol, info = kb.cg(A, b, tol=1e-9, maxiter=500,
+                              callback=lambda x, r: seen.append((np.linalg.norm(b - A @ x), np.linalg.norm(r))))
+            sol2, info2 = kb.cg(A, b, tol=1e-9, maxiter=60, return_arnoldi=True)
+        finally:
+            lib.kb_tune(15, 1)
+        assert info.success and len(seen) == info.numsteps + 1
+        # the callback's x is consistent with its r: ||b - A x|| == ||r|| up to rounding
+        for true_r, rec_r in seen:
+            assert abs(true_r - rec_r) <= 1e-9 * seen[0][0]
+        out[fuse] = (sol, np.asarray(info.resnorms), info2.arnoldi[1], np.asarray(info2.resnorms))
+    assert len(out[0][1]) == len(out[1][1])
+    live = out[0][1] / out[0][1][0] >= 1e-6
+    assert np.all(np.abs(out[1][1] - out[0][1])[live] <= 1e-8 * out[0][1][live])
+    assert np.linalg.norm(out[1][0] - out[0][0]) <= 1e-10 * np.linalg.norm(out[0][0])
+    np.testing.assert_allclose(out[1][2][:41, :40], out[0][2][:41, :40], rtol=0, atol=1e-8 * np.abs(out[0][2]).max())
+    sol_o, info_o = orc.cg(A, b, tol=1e-9, maxiter=500)
+    assert info_o.numsteps == len(out[1][1]) - 1
+    assert np.linalg.norm(out[1][0] - sol_o) <= 1e-10 * np.linalg.norm(sol_o)
