@@ -295,10 +295,34 @@ int kb_multi_dot(kb_ws_t ws, int64_t n, int k, int cnt, const double* V, int64_t
 int kb_multi_axpy(kb_ws_t ws, int64_t n, int k, int m, const double* h, const double* P,
                   int64_t pstride, double* w, int dot, double* out, void* stream);
 
+/* --- tall-skinny block products on the FP64 tensor cores (utils.py) ------
+ * The reference's utils.qr / utils.angles are the one place where `inner` is a true block inner
+ * product: inner(QF, QG) -> k x l matrix (utils.py:100,117), followed by n x k times k x l
+ * updates (utils.py:101,112,118).  Row-major operands with free leading dimensions (a column
+ * sub-block of an (n, k) array is a valid operand); 1 <= k, l <= 16 per call (the host loops over
+ * 16-column panels); mma.sync m8n8k4 f64 (DMMA); deterministic summation order.
+ *
+ * G[i*ldg + j] = sum_r X[r*ldx + i] * Y[r*ldy + j]   (i < k, j < l);  8 n (k + l) bytes.
+ * flags bit 0: store sqrt(|.|) instead (norms, utils.py:37).  Gacc != NULL: additionally
+ * Gacc[i*ldacc + j] += value (R[j, i] += alpha, utils.py:34).  The workspace must have been
+ * created with max_k >= 256. */
+int kb_block_gram(kb_ws_t ws, int64_t n, int k, int l, const double* X, int64_t ldx,
+                  const double* Y, int64_t ldy, double* G, int64_t ldg, double* Gacc,
+                  int64_t ldacc, int flags, void* stream);
+/* mode 0: Z = X C;  mode 1: Z = Y - X C;  mode 2: Z = Y + X C.   X: n x k, C: k x l (device),
+ * Y, Z: n x l.  Z may alias Y or X.  8 n (k + 2 l) bytes (k + l for mode 0). */
+int kb_block_apply(kb_ws_t ws, int64_t n, int k, int l, const double* X, int64_t ldx,
+                   const double* C, int64_t ldc, const double* Y, int64_t ldy, double* Z,
+                   int64_t ldz, int mode, void* stream);
+
 /* Builds the reflector for the tail x[off:]: v (length n, zeros before off),
  * params[0..3] = alpha, beta, xnorm, sigma2-taken-from-slot.  Two launches. */
 int kb_house_make(kb_ws_t ws, int64_t n, int64_t off, const double* x, double* v,
                   double* params, double* scratch, void* stream);
+/* Same, with the pivot-sign convention selectable: lapack_sign != 0 treats a zero pivot with a
+ * nonzero tail as positive (LAPACK dlarfg, behind np.linalg.qr of utils.py:24): H x = -||x|| e_1. */
+int kb_house_make2(kb_ws_t ws, int64_t n, int64_t off, const double* x, double* v,
+                   double* params, double* scratch, int lapack_sign, void* stream);
 /* h_out[0] = |(w[off] - beta v[off] tau) * alpha|, params = output of kb_house_make,
  * tau = <v, w>  (arnoldi.py:83-85) */
 int kb_house_hlast(kb_ws_t ws, const double* w, int64_t off, const double* v, const double* params,

@@ -25,5 +25,6 @@ from .givens import givens  # noqa: F401
 from .householder import Householder  # noqa: F401
 from .arnoldi import ArnoldiHouseholder, ArnoldiLanczos, ArnoldiMGS  # noqa: F401
 from . import stencils  # noqa: F401
+from . import utils  # noqa: F401
 
 __version__ = "0.1.0"

@@ -106,7 +106,10 @@ SIGNATURES = {
     "kb_basis_combine": [vp, i64, i32, i32, vp, vp, i64, vp, vp, vp],
     "kb_multi_dot": [vp, i64, i32, i32, vp, i64, vp, vp, vp],
     "kb_multi_axpy": [vp, i64, i32, i32, vp, vp, i64, vp, i32, vp, vp],
+    "kb_block_gram": [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, vp],
+    "kb_block_apply": [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, vp],
     "kb_house_make": [vp, i64, i64, vp, vp, vp, vp, vp],
+    "kb_house_make2": [vp, i64, i64, vp, vp, vp, vp, i32, vp],
     "kb_poke": [vp, i32, vp, i64, vp, f64, vp, vp],
     "kb_lartg": [i32, vp, vp, vp, vp],
     "kb_stencil7": [i32, i32, i32, i32, i32, C.POINTER(f64), vp, vp, vp, vp],

@@ -109,10 +109,75 @@ class CsrMatrix:
 
     @classmethod
     def from_torch(cls, A, device=None):
+        if A.layout == torch.sparse_coo:  # converted on the device, like from_coo
+            A = A.coalesce()
+            idx = A.indices()
+            return cls.from_coo(idx[0], idx[1], A.values(), A.shape,
+                                device or (A.device if A.is_cuda else None))
         if A.layout != torch.sparse_csr:
             A = A.to_sparse_csr()
         return cls(A.crow_indices(), A.col_indices(), A.values(), A.shape,
                    device or (A.device if A.is_cuda else None))
+
+    @classmethod
+    def from_coo(cls, rows, cols, vals, shape, device=None):
+        """Triplets (NumPy arrays or torch tensors, on the host or already on the device) -> CSR,
+        converted ON the device: entries sorted by (row, column), duplicates summed in that order
+        (SciPy's ``coo_matrix.tocsr`` convention), row pointers from the row counts."""
+        require_cuda()
+        dev = torch.device(device) if device is not None else torch.device(
+            "cuda", torch.cuda.current_device())
+        nr, nc = int(shape[0]), int(shape[1])
+        with torch.cuda.device(dev):
+            r = torch.as_tensor(rows).to(device=dev, dtype=torch.int64).reshape(-1)
+            c = torch.as_tensor(cols).to(device=dev, dtype=torch.int64).reshape(-1)
+            v = torch.as_tensor(vals)
+            if v.is_complex():
+                raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
+            v = v.to(device=dev, dtype=torch.float64).reshape(-1)
+            if not (r.numel() == c.numel() == v.numel()):
+                raise ValueError("rows, cols and vals differ in length")
+            if r.numel() and (int(r.min()) < 0 or int(r.max()) >= nr or int(c.min()) < 0
+                              or int(c.max()) >= nc):
+                raise ValueError("index out of range")
+            key = r * nc + c
+            key, perm = torch.sort(key, stable=True)
+            v = v[perm]
+            uniq, counts = torch.unique_consecutive(key, return_counts=True)
+            if uniq.numel() != key.numel():  # duplicates: summed in stored order (no atomics)
+                try:
+                    v = torch.segment_reduce(v, "sum", lengths=counts)
+                except RuntimeError:  # builds without the CUDA segment kernel: atomics (the sum of
+                    # three or more duplicates may then differ in the last bit run to run)
+                    inv = torch.repeat_interleave(
+                        torch.arange(uniq.numel(), device=dev), counts)
+                    v = torch.zeros(uniq.numel(), dtype=torch.float64,
+                                    device=dev).index_add_(0, inv, v)
+            if uniq.numel() >= 2**31:
+                raise ValueError("nnz must fit int32")
+            rp = torch.zeros(nr + 1, dtype=torch.int64, device=dev)
+            rp[1:] = torch.cumsum(torch.bincount(uniq // nc, minlength=nr), 0)
+            return cls(rp.to(torch.int32), (uniq % nc).to(torch.int32), v, (nr, nc), dev)
+
+    @classmethod
+    def from_file(cls, path, device=None):
+        """Matrix Market (``.mtx`` / ``.mtx.gz``, coordinate or array, real / integer / pattern,
+        general or symmetric -- parsed by ``scipy.io.mmread``) or SciPy's ``.npz`` sparse container.
+        The triplets go to the device as they are and are converted there (``from_coo``)."""
+        path = str(path)
+        if path.endswith(".npz"):
+            import scipy.sparse
+
+            return cls.from_scipy(scipy.sparse.load_npz(path), device)
+        import scipy.io
+
+        M = scipy.io.mmread(path)
+        if isinstance(M, np.ndarray):
+            return cls.from_dense(M, device)
+        if np.iscomplexobj(M.data):
+            raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
+        M = M.tocoo()
+        return cls.from_coo(M.row, M.col, M.data, M.shape, device)
 
     @property
     def T(self):

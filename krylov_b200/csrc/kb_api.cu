@@ -10,6 +10,7 @@
 #include "kb_spmv.cuh"
 #include "kb_vec.cuh"
 #include "kb_march.cuh"
+#include "kb_block.cuh"
 
 thread_local char kb_errbuf[512] = {0};
 
@@ -1482,13 +1483,94 @@ int kb_multi_axpy(kb_ws_t ws, int64_t n, int k, int m, const double* h, const do
   return KB_OK;
 }
 
+}  // extern "C"
+
+// ---- tall-skinny block products on the DMMA pipe (kb_block.cuh; utils.py:100-118) ----
+static inline int kb_block_grid(const kb_ws_s* ws, int64_t n) {
+  int64_t need = (n + 127) / 128;
+  int64_t cap = (int64_t)ws->num_sms * 2;  // 2 CTAs of 8 warps per SM: 64 KB of loads in flight
+  if (cap > KB_MAX_BLOCKS) cap = KB_MAX_BLOCKS;
+  if (need > cap) need = cap;
+  if (need < 1) need = 1;
+  return (int)need;
+}
+
+template <int MODE>
+static int kb_block_apply_mode(kb_ws_s* ws, int64_t n, int k, int l, const double* X, int64_t ldx,
+                               const double* C, int64_t ldc, const double* Y, int64_t ldy,
+                               double* Z, int64_t ldz, cudaStream_t st) {
+  const int hk = k > 8 ? 2 : 1, hl = l > 8 ? 2 : 1;
+  const int grid = kb_block_grid(ws, n);
+  KbRed rd = kb_red(ws);
+#define KB_APPLY(HK, HL)                                                                       \
+  kb_block_apply_kernel<HK, HL, MODE><<<grid, KB_BG_WARPS * 32, 0, st>>>(n, k, l, X, ldx, C, ldc, \
+                                                                         Y, ldy, Z, ldz, rd)
+  if (hk == 1 && hl == 1) KB_APPLY(1, 1);
+  else if (hk == 1) KB_APPLY(1, 2);
+  else if (hl == 1) KB_APPLY(2, 1);
+  else KB_APPLY(2, 2);
+#undef KB_APPLY
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" {
+
+int kb_block_gram(kb_ws_t ws, int64_t n, int k, int l, const double* X, int64_t ldx,
+                  const double* Y, int64_t ldy, double* G, int64_t ldg, double* Gacc,
+                  int64_t ldacc, int flags, void* stream) {
+  KB_REQUIRE(ws != nullptr, "null workspace");
+  KB_REQUIRE(n >= 0, "negative length");
+  KB_REQUIRE(k >= 1 && k <= 16 && l >= 1 && l <= 16, "1 <= k, l <= 16 columns per call");
+  KB_REQUIRE(X && Y && G, "null argument");
+  KB_REQUIRE(ldx >= k && ldy >= l && ldg >= l && (Gacc == nullptr || ldacc >= l),
+             "leading dimension smaller than the column count");
+  const int hx = k > 8 ? 2 : 1, hy = l > 8 ? 2 : 1;
+  KB_REQUIRE(ws->max_k >= hx * hy * 64, "workspace too narrow: create it with max_k >= 256");
+  KbRed rd = kb_red(ws);
+  KB_REQUIRE(!rd.collective || ws->comm->max_k >= hx * hy * 64, "communicator too narrow");
+  const int grid = kb_block_grid(ws, n);
+  cudaStream_t st = S(stream);
+#define KB_GRAM(HX, HY)                                                                      \
+  kb_block_gram_kernel<HX, HY><<<grid, KB_BG_WARPS * 32, 0, st>>>(n, k, l, X, ldx, Y, ldy, G, \
+                                                                  ldg, Gacc, ldacc, flags, rd)
+  if (hx == 1 && hy == 1) KB_GRAM(1, 1);
+  else if (hx == 1) KB_GRAM(1, 2);
+  else if (hy == 1) KB_GRAM(2, 1);
+  else KB_GRAM(2, 2);
+#undef KB_GRAM
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_block_apply(kb_ws_t ws, int64_t n, int k, int l, const double* X, int64_t ldx,
+                   const double* C, int64_t ldc, const double* Y, int64_t ldy, double* Z,
+                   int64_t ldz, int mode, void* stream) {
+  KB_REQUIRE(ws != nullptr, "null workspace");
+  KB_REQUIRE(n >= 0, "negative length");
+  KB_REQUIRE(k >= 1 && k <= 16 && l >= 1 && l <= 16, "1 <= k, l <= 16 columns per call");
+  KB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+  KB_REQUIRE(X && C && Z && (mode == 0 || Y), "null argument");
+  KB_REQUIRE(ldx >= k && ldc >= l && ldz >= l && (mode == 0 || ldy >= l),
+             "leading dimension smaller than the column count");
+  if (mode == 0) return kb_block_apply_mode<0>(ws, n, k, l, X, ldx, C, ldc, Y, ldy, Z, ldz, S(stream));
+  if (mode == 1) return kb_block_apply_mode<1>(ws, n, k, l, X, ldx, C, ldc, Y, ldy, Z, ldz, S(stream));
+  return kb_block_apply_mode<2>(ws, n, k, l, X, ldx, C, ldc, Y, ldy, Z, ldz, S(stream));
+}
+
 int kb_house_make(kb_ws_t ws, int64_t n, int64_t off, const double* x, double* v, double* params,
                   double* scratch, void* stream) {
+  return kb_house_make2(ws, n, off, x, v, params, scratch, 0, stream);
+}
+
+int kb_house_make2(kb_ws_t ws, int64_t n, int64_t off, const double* x, double* v, double* params,
+                   double* scratch, int lapack_sign, void* stream) {
   KB_REQUIRE(ws && x && v && params && scratch, "null argument");
   KB_REQUIRE(off >= 0 && off < n, "offset out of range");
   int rc = kb_dot(ws, n - off - 1, 1, x + off + 1, x + off + 1, scratch, stream);
   if (rc != KB_OK) return rc;
-  kb_house_params_kernel<<<1, 32, 0, S(stream)>>>(x, off, scratch, params, kb_red(ws));
+  kb_house_params_kernel<<<1, 32, 0, S(stream)>>>(x, off, scratch, params, lapack_sign ? 1 : 0,
+                                                  kb_red(ws));
   KB_LAUNCH_CHECK();
   const int grid = kb_grid_for(ws, n, KB_BLOCK, 2);
   kb_house_fill_kernel<<<grid, KB_BLOCK, 0, S(stream)>>>(n, off, x, params, v, kb_red(ws));

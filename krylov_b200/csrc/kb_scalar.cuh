@@ -197,8 +197,10 @@ __global__ void kb_gmres_solve_y_kernel(int k, int m, int maxiter, const double*
 // householder.py:26-51 for the tail x[off:], k == 1.
 // scratch[0] = sigma2 = <x[off+1:], x[off+1:]> must already be reduced.
 // params: [0] alpha, [1] beta, [2] xnorm, [3] v0 (unnormalised), [4] 1/||v||-divisor
+// lapack_sign: a zero pivot with a nonzero tail counts as positive (Fortran SIGN(a, 0) = +|a| in
+// dlarfg), i.e. H x = -||x|| e_1; the reference's Householder maps it to +||x|| e_1.
 __global__ void kb_house_params_kernel(const double* x, int64_t off, const double* scratch,
-                                       double* params, KbRed rd) {
+                                       double* params, int lapack_sign, KbRed rd) {
   if (kb_gated(rd)) return;
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double gamma = x[off];
@@ -211,8 +213,8 @@ __global__ void kb_house_params_kernel(const double* x, int64_t off, const doubl
   } else {
     beta = 2.0;
     if (gamma == 0.0) {
-      v0 = -sqrt(sigma2);
-      alpha = 1.0;
+      v0 = lapack_sign ? sqrt(sigma2) : -sqrt(sigma2);
+      alpha = lapack_sign ? -1.0 : 1.0;
     } else {
       v0 = __dadd_rn(gamma, __dmul_rn(gamma / fabs(gamma), xnorm));
       alpha = -gamma / fabs(gamma);

@@ -270,12 +270,12 @@ class Ops:
                                    ptr(x0), ptr(out), cur_stream()))
 
     # -- Householder
-    def house_make(self, off, x, v, params, scratch):
+    def house_make(self, off, x, v, params, scratch, lapack_sign=False):
         if self.comm is not None:
             raise NotImplementedError("Householder orthogonalisation is single-GPU in this round")
         self.launches += 3
-        check(lib.kb_house_make(self.ws.handle, self.n, int(off), ptr(x), ptr(v), ptr(params),
-                                ptr(scratch), cur_stream()))
+        check(lib.kb_house_make2(self.ws.handle, self.n, int(off), ptr(x), ptr(v), ptr(params),
+                                 ptr(scratch), 1 if lapack_sign else 0, cur_stream()))
 
     def house_hlast(self, w, off, v, params, tau, h_out):
         self.launches += 1
@@ -286,3 +286,94 @@ class Ops:
         self.launches += 1
         check(lib.kb_poke(self.ws.handle, int(op), ptr(x), int(idx), ptr(s), float(val), ptr(dst),
                           cur_stream()))
+
+
+class BlockOps:
+    """Tall-skinny block products on the FP64 tensor cores (``kb_block_gram`` /
+    ``kb_block_apply``) for row-major 2-D CUDA tensors whose rows may be strided (column
+    sub-blocks are valid operands).  More than 16 columns: 16-column panels."""
+
+    _KEY = 256  # workspace width: one 16 x 16 block of sums per CTA
+
+    def __init__(self, device=None):
+        require_cuda()
+        self.device = torch.device(device) if device is not None else torch.device(
+            "cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            self.ws = _borrow_workspace(self.device, self._KEY)
+        self.launches = 0
+
+    def __del__(self):
+        ws = getattr(self, "ws", None)
+        if ws is not None:
+            self.ws = None
+            _return_workspace(self.device, self._KEY, ws)
+
+    @staticmethod
+    def _ld(t):
+        if t.dim() != 2 or t.dtype != torch.float64 or not t.is_cuda:
+            raise ValueError("block operands are 2-D fp64 CUDA tensors")
+        if t.shape[1] > 1 and t.stride(1) != 1:
+            raise ValueError("block operands need unit stride along the columns")
+        return max(int(t.stride(0)), int(t.shape[1])) if t.shape[0] > 1 else int(t.shape[1])
+
+    def gram(self, X, Y, out=None, acc=None, sqrt_abs=False):
+        """out[i, j] = sum_r X[r, i] Y[r, j] (a (k, l) device tensor); ``acc`` (k, l): += too."""
+        n, k = X.shape
+        l = Y.shape[1]
+        if Y.shape[0] != n:
+            raise ValueError(f"row counts differ: {tuple(X.shape)} vs {tuple(Y.shape)}")
+        G = out if out is not None else torch.zeros((k, l), dtype=torch.float64, device=self.device)
+        if k == 0 or l == 0:
+            return G
+        ldx, ldy = self._ld(X), self._ld(Y)
+        for i0 in range(0, k, 16):
+            for j0 in range(0, l, 16):
+                kk, ll = min(16, k - i0), min(16, l - j0)
+                Xp, Yp, Gp = X[:, i0:], Y[:, j0:], G[i0:, j0:]
+                Ap = None if acc is None else acc[i0:, j0:]
+                self.launches += 1
+                check(lib.kb_block_gram(self.ws.handle, n, kk, ll, ptr(Xp), ldx, ptr(Yp), ldy,
+                                        ptr(Gp), G.stride(0), ptr(Ap),
+                                        0 if acc is None else acc.stride(0),
+                                        1 if sqrt_abs else 0, cur_stream()))
+        return G
+
+    def apply(self, X, C, Y=None, sign=0, out=None):
+        """sign 0: X C;  sign -1: Y - X C;  sign +1: Y + X C   (X (n, k), C (k, l) on the device)."""
+        n, k = X.shape
+        l = C.shape[1]
+        if C.shape[0] != k:
+            raise ValueError(f"inner dimensions differ: {tuple(X.shape)} @ {tuple(C.shape)}")
+        if sign != 0 and (Y is None or tuple(Y.shape) != (n, l)):
+            raise ValueError("Y must have shape (n, l)")
+        Z = out if out is not None else torch.empty((n, l), dtype=torch.float64, device=self.device)
+        if n == 0 or l == 0:
+            return Z
+        if k == 0:
+            if sign == 0:
+                Z.zero_()
+            elif Z.data_ptr() != Y.data_ptr():
+                Z.copy_(Y)
+            return Z
+        if out is not None and out.data_ptr() == X.data_ptr() and (k > 16 or l > 16):
+            raise ValueError("in-place X <- X C needs k, l <= 16")
+        C = C.contiguous()
+        ldx, ldz = self._ld(X), self._ld(Z)
+        ldy = self._ld(Y) if Y is not None else 0
+        for j0 in range(0, l, 16):
+            ll = min(16, l - j0)
+            for i0 in range(0, k, 16):
+                kk = min(16, k - i0)
+                if i0 == 0:
+                    mode = {0: 0, -1: 1, 1: 2}[sign]
+                    Ysrc = None if Y is None else Y[:, j0:]
+                    ldsrc = ldy
+                else:  # further panels of the contraction accumulate onto the result
+                    mode = 1 if sign == -1 else 2
+                    Ysrc, ldsrc = Z[:, j0:], ldz
+                self.launches += 1
+                check(lib.kb_block_apply(self.ws.handle, n, kk, ll, ptr(X[:, i0:]), ldx,
+                                         ptr(C[i0:, j0:]), C.stride(0), ptr(Ysrc), ldsrc,
+                                         ptr(Z[:, j0:]), ldz, mode, cur_stream()))
+        return Z

@@ -128,3 +128,142 @@ def host_logic():
         yield sr
     finally:
         sr.Problem, sr.Alg = saved
+
+
+# ------------------------------------------------------------------------------------------------
+# krylov_b200.utils: the same idea for qr / angles / hegedus (host logic on CPU tensors)
+# ------------------------------------------------------------------------------------------------
+class _FakeCsr:
+    def __init__(self, M):
+        import scipy.sparse
+
+        self.M = scipy.sparse.csr_matrix(M)
+        self.shape = self.M.shape
+
+    def matvec_device(self, x):
+        return torch.from_numpy(np.ascontiguousarray(self.M @ x.numpy()))
+
+
+class FakeOps:
+    """Stand-in for krylov_b200.device.Ops on CPU tensors: one method per kernel, evaluated in the
+    kernels' rounding order (products rounded before sums; reductions as plain sums)."""
+
+    def __init__(self, n, k, device=None, comm=None):
+        self.n, self.k, self.launches = n, k, 0
+
+    def vec(self, zero=True):
+        return torch.zeros((self.n, self.k), dtype=torch.float64)
+
+    def slots(self, m=1):
+        return torch.zeros((m, self.k), dtype=torch.float64)
+
+    def dot(self, x, y, out, n=None):
+        out.copy_((x * y).sum(dim=0))
+
+    def axpy(self, y, coef, x, sign=1.0):
+        y += (sign * coef) * x
+
+    def div_scale(self, out, x, coef):
+        out.copy_(x / torch.where(coef != 0, coef, torch.ones_like(coef)))
+
+    def lincomb(self, out, ca, x, cb=None, y=None):
+        t = x if ca is None else ca * x
+        if y is not None:
+            t = t + cb * y
+        out.copy_(t)
+
+    def axpy_dot(self, coef, u, w, dot=0, z=None, out=None, scale=None):
+        a = coef if scale is None else scale[0] * coef
+        w -= a * u
+        if dot == 1:
+            out.copy_((z * w).sum(dim=0))
+        elif dot == 2:
+            out.copy_((w * w).sum(dim=0))
+
+    def spmv(self, A, x, y, mode=0, z=None, coef=None, dot=0, w=None, out=None):
+        assert mode == 0
+        y.copy_(A.matvec_device(x))
+        if dot == 1:
+            out.copy_((w * y).sum(dim=0))
+
+    def house_make(self, off, x, v, params, scratch, lapack_sign=False):
+        """kb_house_make2: csrc/kb_scalar.cuh kb_house_params_kernel + kb_house_fill_kernel"""
+        xs = x.reshape(-1)
+        gamma = float(xs[off])
+        sigma2 = float((xs[off + 1:] * xs[off + 1:]).sum())
+        v0, xnorm = 1.0, float(np.sqrt(gamma * gamma + sigma2))
+        if sigma2 == 0.0:
+            beta, xnorm = 0.0, abs(gamma)
+            alpha = 1.0 if gamma == 0.0 else gamma / xnorm
+        else:
+            beta = 2.0
+            if gamma == 0.0:
+                v0 = np.sqrt(sigma2) if lapack_sign else -np.sqrt(sigma2)
+                alpha = -1.0 if lapack_sign else 1.0
+            else:
+                v0 = gamma + gamma / abs(gamma) * xnorm
+                alpha = -gamma / abs(gamma)
+        d = float(np.sqrt(v0 * v0 + sigma2))
+        params.copy_(torch.tensor([alpha, beta, xnorm, v0, d], dtype=torch.float64))
+        vv = v.reshape(-1)
+        vv[:off] = 0.0
+        vv[off] = v0 / d
+        vv[off + 1:] = xs[off + 1:] / d
+
+
+class FakeBlockOps:
+    def __init__(self, device=None):
+        self.launches = 0
+
+    def gram(self, X, Y, out=None, acc=None, sqrt_abs=False):
+        G = X.t() @ Y
+        if sqrt_abs:
+            G = torch.sqrt(torch.abs(G))
+        if acc is not None:
+            acc += G
+        if out is not None:
+            out.copy_(G)
+            return out
+        return G
+
+    def apply(self, X, C, Y=None, sign=0, out=None):
+        Z = X @ C
+        if sign != 0:
+            Z = Y + sign * Z
+        if out is not None:
+            out.copy_(Z)
+            return out
+        return Z
+
+
+def _host_matrix(v, device=None):
+    if isinstance(v, torch.Tensor):
+        return v.to(dtype=torch.float64).contiguous()
+    a = np.asarray(v)
+    if np.iscomplexobj(a):
+        raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).copy())
+
+
+class _UtilsProblem(FakeProblem):
+    def __init__(self, A, b, x0=None):
+        super().__init__(A, b, x0)
+        self.device = torch.device("cpu")
+
+
+@contextlib.contextmanager
+def utils_host_logic():
+    import krylov_b200.utils as ku
+
+    names = ("Ops", "BlockOps", "Problem", "require_cuda", "as_device_matrix", "to_csr_or_none", "_on")
+    saved = {n: getattr(ku, n) for n in names}
+    ku.Ops, ku.BlockOps, ku.Problem = FakeOps, FakeBlockOps, _UtilsProblem
+    ku.require_cuda = lambda: None
+    ku.as_device_matrix = _host_matrix
+    ku.to_csr_or_none = lambda A, device=None: _FakeCsr(A)
+    ku._on = lambda device: contextlib.nullcontext()
+    try:
+        yield ku
+    finally:
+        for n, v in saved.items():
+            setattr(ku, n, v)
