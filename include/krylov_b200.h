@@ -111,6 +111,11 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y,
             int mode, const double* z, const double* coef,
             int dot, const double* w, double* out, void* stream);
 
+/* *yes = 1 if kb_spmv with this block width and operand runs the line-marching SpMM
+ * (csrc/kb_lines.cuh: k a power of two in [2, 32], 3-D 7-point pattern with constant diagonals,
+ * x 16-byte aligned; kb_tune key 16: 0 off, 1 default, 2 wherever valid), else the row-wise kernel. */
+int kb_spmm_is_lines(kb_csr_t A, int k, const double* x, int* yes);
+
 /* boundary rows of a row-partitioned matrix, after the halo
  * entries xh have arrived: for i < n_brows, row = rows[i]:
  *   h = sum_j hval[j] * xh[hcol[j], c];  y[row, c] += sign * h

@@ -76,6 +76,7 @@ SIGNATURES = {
     "kb_csr_get_info": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32),
                         C.POINTER(i32)],
     "kb_spmv": [vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp],
+    "kb_spmm_is_lines": [vp, i32, vp, C.POINTER(i32)],
     "kb_spmv_halo_add": [vp, i32, i64, f64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp],
     "kb_halo_create": [C.POINTER(vp), i32, i32, i64],
     "kb_halo_get_handle": [vp, vp],

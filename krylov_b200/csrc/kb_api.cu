@@ -10,6 +10,7 @@
 #include "kb_spmv.cuh"
 #include "kb_vec.cuh"
 #include "kb_march.cuh"
+#include "kb_lines.cuh"
 #include "kb_block.cuh"
 
 thread_local char kb_errbuf[512] = {0};
@@ -53,6 +54,10 @@ static int g_stencil_l2pol = 0; // kb_tune key 12: L2 hint of the x windows (0 e
 static int g_march_ch = 0;     // kb_tune key 13: planes per work item of the marching kernel (0 auto)
 static int g_march_cfg = 0;    // kb_tune key 14: tile / ring shape of the marching kernel
 static int g_cg_fuse = 1;      // kb_tune key 15: fused marching CG kernels in kb_cg_run (0 off)
+static int g_spmm_lines = 1;    // kb_tune key 16: line-marching SpMM (k > 1, constant 3-D stencils):
+                                // 0 off, 1 where a line fills >= half of its chunks, 2 wherever valid
+static int g_lines_ch = 0;      // kb_tune key 17: lines per work item of it (0 = 32)
+static int g_lines_cfg = 0;     // kb_tune key 18: 0 = 1024-entry chunks, 2 CTAs/SM; 1 = 512, 4 CTAs/SM
 static int g_stencil_ctas = 0;  // kb_tune key 11: CTAs/SM cap of it (0 = occupancy limit)
 static int g_cgs_jc = 8;  // kb_tune key 9: basis vectors per multi-dot launch (8 or 16)
 static int g_rowwise_contig = -1;  // kb_tune key 5: -1 auto, 0 strided, 1 contiguous rows per block
@@ -204,6 +209,9 @@ int kb_tune(int key, int value) {
     case 13: g_march_ch = value; return KB_OK;
     case 14: g_march_cfg = value; return KB_OK;
     case 15: g_cg_fuse = value; return KB_OK;
+    case 16: g_spmm_lines = value; return KB_OK;
+    case 17: g_lines_ch = value; return KB_OK;
+    case 18: g_lines_cfg = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -837,6 +845,85 @@ static int kb_launch_stencil(kb_csr_s* A, kb_ws_s* ws, const double* x, double* 
   }
 }
 
+// Geometry of kb_spmm_lines_kernel; false if the matrix / block width / operand do not qualify:
+// constant diagonals {-P, -n, -i, 0, +i, +n, +P}, k a power of two in [2, 32] (a thread keeps one
+// column; 288 % k == 0 for the block reduction), x 16-byte aligned (TMA).
+static bool kb_lines_geom(const kb_csr_s* A, int k, const double* x, KbLines* g) {
+  const int TR = g_lines_cfg == 1 ? 512 : 1024;
+  g->TR = TR;
+  if (g_spmm_lines <= 0 || !A->constv || A->pat.nd != 7 || A->masks == nullptr) return false;
+  if (k < 2 || k > 32 || (k & (k - 1)) != 0) return false;
+  if (((uintptr_t)x & 15u) != 0) return false;
+  const int* off = A->pat.off;
+  if (off[3] != 0) return false;
+  for (int d = 0; d < 3; ++d)
+    if (off[d] != -off[6 - d]) return false;
+  if (!(off[4] > 0 && off[5] > off[4] && off[6] > off[5])) return false;
+  const long long inner = (long long)off[4] * k;
+  if (inner > 64) return false;
+  int ks = 0;
+  while ((1 << ks) < k) ++ks;
+  g->k = k;
+  g->kshift = ks;
+  g->inner = (int)inner;
+  g->H = (int)((inner + 1) & ~1ll);
+  g->L = (long long)off[5] * k;
+  g->Pz = (long long)off[6] * k;
+  g->N = (long long)A->n_rows * k;
+  g->Nx = (long long)A->n_cols * k;
+  g->nlines = (g->N + g->L - 1) / g->L;
+  g->ncol = (int)((g->L + TR - 1) / TR);
+  if (g_spmm_lines == 1 && 2 * g->L < (long long)g->ncol * TR) return false;  // chunks mostly empty
+  g->slotlen = 3 * TR + 2 * g->H;
+  long long ch = g_lines_ch > 0 ? g_lines_ch : 32;
+  if (ch > g->nlines) ch = g->nlines;
+  if (ch < 1) ch = 1;
+  g->ch = (int)ch;
+  g->nitems = (long long)g->ncol * ((g->nlines + ch - 1) / ch);
+  return true;
+}
+
+template <int RPT, int MINB, int DOT, bool WX>
+static int kb_launch_lines_t(kb_csr_s* A, kb_ws_s* ws, const KbLines& g, const double* x, double* y,
+                             int mode, const double* z, const double* coef, const double* w,
+                             double* out, cudaStream_t st) {
+  static int max_smem[64] = {0};
+  constexpr int NS = 4;
+  auto kern = kb_spmm_lines_kernel<RPT, NS, MINB, DOT, WX>;
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  const size_t smem = (size_t)NS * g.slotlen * 8 + 2 * NS * 8;
+  if (dev < 0 || dev >= 64 || max_smem[dev] == 0) {
+    int lim = 0;
+    KB_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lim - 8 * 1024));
+    if (dev >= 0 && dev < 64) max_smem[dev] = lim - 8 * 1024;
+  }
+  int ctas = 0;
+  KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 288, smem));
+  if (ctas < 1) return KB_EUNSUPPORTED;
+  long long grid = (long long)ws->num_sms * ctas;
+  if (grid > g.nitems) grid = g.nitems;
+  if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
+  kern<<<(int)grid, 288, smem, st>>>(g, A->masks, A->cv, x, y, mode, z, coef, w, out, kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+template <int DOT>
+static int kb_launch_lines(kb_csr_s* A, kb_ws_s* ws, const KbLines& g, const double* x, double* y,
+                           int mode, const double* z, const double* coef, const double* w,
+                           double* out, cudaStream_t st) {
+  const bool wx = DOT == 1 && w == x;  // <x, A x>: the operand is the middle diagonal's entry, on chip
+  if (g.TR == 512) {
+    if (wx) return kb_launch_lines_t<2, 4, DOT, (DOT == 1)>(A, ws, g, x, y, mode, z, coef, w, out, st);
+    return kb_launch_lines_t<2, 4, DOT, false>(A, ws, g, x, y, mode, z, coef, w, out, st);
+  }
+  if (wx) return kb_launch_lines_t<4, 2, DOT, (DOT == 1)>(A, ws, g, x, y, mode, z, coef, w, out, st);
+  return kb_launch_lines_t<4, 2, DOT, false>(A, ws, g, x, y, mode, z, coef, w, out, st);
+}
+
 template <int STAGES, int RPT, int MINB, int DOT>
 static int kb_launch_spmm_window_cfg(kb_csr_s* A, kb_ws_s* ws, int k, const double* x, double* y,
                                      int mode, const double* z, const double* coef,
@@ -928,6 +1015,17 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
     if (dot == 1) return kb_launch_stream<1>(A, ws, x, y, mode, z, coef, w, out, st);
     return kb_launch_stream<2>(A, ws, x, y, mode, z, coef, w, out, st);
   }
+  // blocked right-hand sides on a constant-coefficient 3-D stencil: line-marching SpMM
+  if (k > 1 && A->schedule == 4 && A->forced != 1) {
+    KbLines g;
+    if (kb_lines_geom(A, k, x, &g)) {
+      int rc;
+      if (dot == 0) rc = kb_launch_lines<0>(A, ws, g, x, y, mode, z, coef, w, out, st);
+      else if (dot == 1) rc = kb_launch_lines<1>(A, ws, g, x, y, mode, z, coef, w, out, st);
+      else rc = kb_launch_lines<2>(A, ws, g, x, y, mode, z, coef, w, out, st);
+      if (rc != KB_EUNSUPPORTED) return rc;
+    }
+  }
   // blocked right-hand sides on a stencil-like matrix: windowed SpMM
   if (k > 1 && 256 % k == 0 && A->pattern_ok && A->pat.nw > 0 && g_spmm_cfg >= 0 &&
       A->forced != 1 && ((uintptr_t)x % 16 == 0)) {
@@ -956,6 +1054,13 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
     kb_spmv_rowwise_kernel<2><<<grid, block, 0, st>>>(A->n_rows, k, A->rowptr, A->colidx, A->vals,
                                                       x, y, mode, z, coef, w, out, contiguous, rd);
   KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+int kb_spmm_is_lines(kb_csr_t A, int k, const double* x, int* yes) {
+  KB_REQUIRE(A != nullptr && yes != nullptr, "null argument");
+  KbLines g;
+  *yes = (k > 1 && A->schedule == 4 && A->forced != 1 && kb_lines_geom(A, k, x, &g)) ? 1 : 0;
   return KB_OK;
 }
 

@@ -1,0 +1,205 @@
+// Line-marching SpMM for constant-coefficient 3-D stencils and blocked right-hand sides (sm_100a).
+//
+// Y = A X with X of shape (n, k), row-major, is the banded product of A (x) I_k with the flattened
+// vector: row e = i k + c has the diagonals e + k off[d].  For the 7-point stencil these are
+//   {-Pz, -L, -kI, 0, +kI, +L, +Pz},   L = nx k (one grid line),  Pz = nx ny k (one plane).
+// The row-wise SpMM gathers seven 8 k-byte rows of X per row through L1/L2: 7 x 128 B at k = 16,
+// and runs into the L2 -> SM limit at 0.36 of the HBM roofline (profiles/r1_c4_tune.txt: 2.50 ms
+// at 256^3, k = 16).  The plane-marching kernel of k = 1 does not carry over: its ring would hold
+// windows of 2 L + tile entries, 72 KB each at k = 16.
+//
+// Here a CTA owns a chunk of TR = 1024 (or 512) consecutive entries of a line and *marches over the
+// lines*.  One ring slot holds everything the flattened vector contributes at line r:
+//     [ x[r L + c TR - H, ... + TR + H) | x[. - Pz, TR entries) | x[. + Pz, TR entries) ]
+// (H >= k |off of the innermost pair|: the +-kI neighbours; three 1-D TMA bulk copies, one
+// mbarrier).  Computing line r reads the -L diagonal from the previous slot, 0 / +-kI / +-Pz from
+// the current one and +L from the next: (TR + 2H) / TR + 2 = 3.03 entries per row cross the
+// L2 -> SM boundary instead of 7, DRAM sees X once (the +-Pz chunks were brought in by the CTAs
+// one plane away and are L2 hits: 126 MB of L2 against 8 MB planes).
+// Products, their order and rounding are those of every other schedule (kb_march_rows): results
+// are bit-identical to the row-wise kernel.  Rows next to a boundary skip absent diagonals through
+// the per-row masks, so any matrix with this offset pattern and constant diagonals qualifies
+// (Dirichlet gaps, truncated last plane, row slabs of a partitioned matrix).
+#pragma once
+#include "kb_march.cuh"
+
+struct KbLines {
+  long long L;       // line stride in flattened entries
+  long long Pz;      // plane stride in flattened entries
+  long long N;       // n_rows * k
+  long long Nx;      // n_cols * k (length of the flattened x)
+  long long nlines;  // ceil(N / L)
+  long long nitems;  // ncol * ceil(nlines / ch)
+  int k, kshift;     // block width (power of two), log2
+  int H;             // halo entries on each side of a chunk's window (even, >= k * off[4])
+  int inner;         // k * off[4]
+  int slotlen;       // 3 TR + 2 H doubles
+  int ncol;          // chunks per line
+  int ch;            // lines per work item
+  int TR;            // entries per chunk (256 x entries per thread)
+};
+
+template <int RPT, int NS, int MINB, int DOT, bool WX>
+__global__ void __launch_bounds__(256 + 32, MINB)
+kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals cv,
+                     const double* __restrict__ x, double* __restrict__ y, int mode,
+                     const double* __restrict__ z, const double* __restrict__ coef,
+                     const double* __restrict__ w, double* __restrict__ out, KbRed rd) {
+  static_assert(RPT == 2 || RPT == 4, "kb_march_rows works on pairs of entries");
+  static_assert(NS >= 4, "ring: previous, current, next line + one in flight");
+  if (kb_gated(rd)) return;
+  constexpr int TR = 256 * RPT;
+  extern __shared__ __align__(128) unsigned char kb_dyn_smem[];
+  double* const s_win = reinterpret_cast<double*>(kb_dyn_smem);
+  uint64_t* const s_full = reinterpret_cast<uint64_t*>(s_win + (size_t)NS * g.slotlen);
+  uint64_t* const s_empty = s_full + NS;
+  __shared__ double red_sm[256 + 32];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      kb_mbar_init(&s_full[s], 1);
+      kb_mbar_init(&s_empty[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc = 0.0;
+  if (warp == 8) {
+    // ---------------------------------------------- producer: one slot per line ---
+    if ((tid & 31) == 0) {
+      const uint64_t pol = kb_policy_evict_last();
+      unsigned cnt = 0;
+      for (long long item = blockIdx.x; item < g.nitems; item += gridDim.x) {
+        const int c = (int)(item % g.ncol);
+        const long long r0 = (item / g.ncol) * g.ch;
+        const long long r1 = (r0 + g.ch < g.nlines) ? r0 + g.ch : g.nlines;
+        const int nload = (int)(r1 - r0) + 2;
+        for (int l = 0; l < nload; ++l, ++cnt) {
+          const int slot = (int)(cnt % NS);
+          const unsigned use = cnt / NS;
+          if (use > 0) kb_mbar_wait(&s_empty[slot], (use - 1u) & 1u);
+          double* const sl = s_win + (size_t)slot * g.slotlen;
+          const long long e0 = (r0 - 1 + l) * g.L + (long long)c * TR;  // first own entry
+          // pieces: the window with its halo; the -Pz and +Pz chunks (lines inside the item only)
+          long long lo[3], hi[3];
+          double* dst[3];
+          const bool inside = l >= 1 && l <= nload - 2;
+          const long long s0[3] = {e0 - g.H, e0 - g.Pz, e0 + g.Pz};
+          const long long len[3] = {(long long)TR + 2 * g.H, inside ? TR : 0, inside ? TR : 0};
+          double* const base[3] = {sl, sl + TR + 2 * g.H, sl + 2 * TR + 2 * g.H};
+          uint32_t total = 0;
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            lo[p] = s0[p] > 0 ? s0[p] : 0;
+            hi[p] = (s0[p] + len[p] < g.Nx) ? s0[p] + len[p] : g.Nx;
+            dst[p] = base[p] + (lo[p] - s0[p]);
+            if (hi[p] > lo[p]) total += (uint32_t)(hi[p] - lo[p]) * 8u;
+          }
+          if (total > 0) {
+            kb_mbar_expect_tx(&s_full[slot], total);
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+              if (hi[p] > lo[p])
+                kb_bulk_g2s_hint(dst[p], x + lo[p], (uint32_t)(hi[p] - lo[p]) * 8u, &s_full[slot],
+                                 pol);
+          } else {
+            kb_mbar_arrive(&s_full[slot]);  // nothing of this line exists
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------- consumers: RPT entries per thread ---
+    const uint32_t sbase = kb_smem_u32(s_win);
+    const uint32_t sbytes = (uint32_t)g.slotlen * 8u;
+    const uint32_t own = (uint32_t)(g.H + tid) * 8u;           // entry q = 0 in a slot's window
+    const uint32_t olo = (uint32_t)(TR + 2 * g.H + tid) * 8u;  // ... in its -Pz chunk
+    const uint32_t ohi = olo + (uint32_t)TR * 8u;              // ... in its +Pz chunk
+    const uint32_t oin = (uint32_t)g.inner * 8u;
+    const int col = tid & (g.k - 1);  // 256 % k == 0: the same column for every q
+    double cf = 0.0;
+    if (mode == 1) cf = coef[col];
+    unsigned cnt = 0;
+    for (long long item = blockIdx.x; item < g.nitems; item += gridDim.x) {
+      const int c = (int)(item % g.ncol);
+      const long long r0 = (item / g.ncol) * g.ch;
+      const long long r1 = (r0 + g.ch < g.nlines) ? r0 + g.ch : g.nlines;
+      const int nload = (int)(r1 - r0) + 2;
+      const long long pos0 = (long long)c * TR + tid;  // in-line position of entry q = 0
+      unsigned mn[RPT];
+      double zn[RPT], wn[RPT];
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        mn[q] = 0u;
+        zn[q] = wn[q] = 0.0;
+      }
+      for (int l = 0; l < nload; ++l, ++cnt) {
+        const int slot = (int)(cnt % NS);
+        const long long rc = r0 + l - 2;  // line computed in this pass (l >= 2)
+        unsigned m[RPT];
+        double zv[RPT], wv[RPT];
+        long long ent[RPT];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+          const long long pos = pos0 + q * 256;
+          const long long e64 = rc * g.L + pos;
+          const bool ok = l >= 2 && pos < g.L && e64 < g.N;
+          ent[q] = ok ? e64 : -1;
+          m[q] = mn[q];
+          zv[q] = zn[q];
+          wv[q] = wn[q];
+          // operands of the next pass (line rc + 1) are requested one pass ahead
+          const long long n64 = e64 + g.L;
+          const bool nok = l >= 1 && l + 1 < nload && pos < g.L && n64 < g.N;
+          mn[q] = nok ? (unsigned)masks[n64 >> g.kshift] : 0u;
+          zn[q] = wn[q] = 0.0;
+          if (nok) {
+            if (mode != 0) zn[q] = z[n64];
+            if (DOT == 1 && !WX) wn[q] = w[n64];
+          }
+        }
+        kb_mbar_wait(&s_full[slot], (cnt / NS) & 1u);
+        if (l >= 2) {
+          const uint32_t wprev = sbase + (uint32_t)((cnt - 2u) % NS) * sbytes;
+          const uint32_t wcur = sbase + (uint32_t)((cnt - 1u) % NS) * sbytes;
+          const uint32_t wnext = sbase + (uint32_t)slot * sbytes;
+          uint32_t a[7];
+          a[0] = wcur + olo;
+          a[1] = wprev + own;
+          a[2] = wcur + own - oin;
+          a[3] = wcur + own;
+          a[4] = wcur + own + oin;
+          a[5] = wnext + own;
+          a[6] = wcur + ohi;
+          double sum[RPT], ctr[RPT];
+          kb_march_rows<7, 0, 2>(a, m, cv, sum, ctr);
+          if constexpr (RPT == 4) kb_march_rows<7, 2, 2>(a, m, cv, sum, ctr);
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) {
+            if (ent[q] >= 0) {
+              double yv = sum[q];
+              if (mode == 1) yv = kb_mul_sub(cf, zv[q], sum[q]);
+              if (mode == 2) yv = __dsub_rn(zv[q], sum[q]);
+              __stcs(&y[ent[q]], yv);
+              if (DOT == 1) acc = fma(WX ? ctr[q] : wv[q], yv, acc);
+              if (DOT == 2) acc = fma(yv, yv, acc);
+            }
+          }
+          __syncwarp();
+          if ((tid & 31) == 0) kb_mbar_arrive(&s_empty[(cnt - 2u) % NS]);
+        }
+      }
+      // the last two slots of the item are not needed by a later pass
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        kb_mbar_arrive(&s_empty[(cnt - 2u) % NS]);
+        kb_mbar_arrive(&s_empty[(cnt - 1u) % NS]);
+      }
+    }
+  }
+  if (DOT == 0) return;
+  kb_grid_colsum(acc, g.k, rd, out, red_sm);
+}

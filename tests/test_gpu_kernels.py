@@ -546,3 +546,89 @@ def test_fused_marching_cg_step_by_step_paths():
     sol_o, info_o = orc.cg(A, b, tol=1e-9, maxiter=500)
     assert info_o.numsteps == len(out[1][1]) - 1
     assert np.linalg.norm(out[1][0] - sol_o) <= 1e-10 * np.linalg.norm(sol_o)
+
+
+@pytest.mark.parametrize("chunk", [0, 1])
+@pytest.mark.parametrize("k", [2, 4, 8, 16, 32])
+def test_line_marching_spmm_bit_exact(k, chunk):
+    """kb_spmm_lines_kernel (blocked right-hand sides on constant 3-D stencils): bit-identical to
+    SciPy's csr_matvecs and to the row-wise kernel in every mode, incl. lines shorter / longer than
+    a chunk, a truncated last plane, one line per item, and the <x, A x> operand taken on chip."""
+    import ctypes
+
+    from krylov_b200._lib import check, lib
+
+    def is_lines(Ad, x):
+        yes = ctypes.c_int(0)
+        check(lib.kb_spmm_is_lines(Ad.handle, k, x.data_ptr(), ctypes.byref(yes)))
+        return bool(yes.value)
+
+    lib.kb_tune(16, 2)  # wherever the geometry is valid (default: only where lines fill their chunks)
+    lib.kb_tune(18, chunk)  # 1024- / 512-entry chunks
+    try:
+        for (nx, ny, nz), coeffs, ch in (((70, 5, 4), st.STENCIL_POISSON, 0), ((33, 4, 5), st.convdiff_coeffs(), 3),
+                                        ((130, 3, 3), st.convdiff_coeffs(), 1), ((16, 16, 16), st.STENCIL_POISSON, 0)):
+            lib.kb_tune(17, ch)
+            A = st.to_scipy(st.stencil7_csr(nx, ny, nz, coeffs=coeffs))
+            if (nx, ny, nz) == (33, 4, 5):
+                A = A[:-7, :-7].tocsr()  # truncated last plane
+            n = A.shape[0]
+            Ad = kb.CsrMatrix.from_scipy(A)
+            assert Ad.info()["schedule"] == "stencil"
+            Ar = kb.CsrMatrix.from_scipy(A).set_schedule("rowwise")
+            X, Z, W = (rng.standard_normal((n, k)) for _ in range(3))
+            coef = rng.standard_normal(k)
+            x, z, w = (torch.from_numpy(a).cuda() for a in (X, Z, W))
+            cf = torch.from_numpy(coef).cuda()
+            assert is_lines(Ad, x) and not is_lines(Ar, x)
+            ops = Ops(n, k)
+            y, yr = torch.empty_like(x), torch.empty_like(x)
+            out, outr = ops.slots(1)[0], ops.slots(1)[0]
+            t = A @ X
+            for mode, ref in ((0, t), (1, t - coef * Z), (2, Z - t)):
+                for dot, ww in ((0, w), (1, w), (1, x), (2, w)):
+                    y.fill_(float("nan"))
+                    ops.spmv(Ad, x, y, mode=mode, z=z, coef=cf, dot=dot, w=ww, out=out)
+                    ops.spmv(Ar, x, yr, mode=mode, z=z, coef=cf, dot=dot, w=ww, out=outr)
+                    np.testing.assert_array_equal(y.cpu().numpy(), ref)
+                    assert torch.equal(y, yr)
+                    if dot:
+                        Wn = X if ww is x else W
+                        dref = np.einsum("ij,ij->j", Wn if dot == 1 else ref, ref)
+                        np.testing.assert_allclose(out.cpu().numpy(), dref, rtol=1e-12, atol=1e-11)
+                        np.testing.assert_allclose(out.cpu().numpy(), outr.cpu().numpy(), rtol=1e-12, atol=1e-11)
+            # an unaligned operand falls back to the row-wise kernel, same bits
+            xo = torch.empty(n * k + 1, dtype=torch.float64, device="cuda")[1:].reshape(n, k)
+            xo.copy_(x)
+            assert not is_lines(Ad, xo)
+        # blocked CG end to end: same history as with the row-wise product
+        A = st.poisson3d(20)
+        B = rng.standard_normal((A.shape[0], k))
+        lib.kb_tune(17, 0)
+        s1, i1 = kb.cg(A, B, tol=1e-10, maxiter=300)
+        lib.kb_tune(16, 0)
+        s0, i0 = kb.cg(A, B, tol=1e-10, maxiter=300)
+        assert i1.success and i0.success and abs(i1.numsteps - i0.numsteps) <= 1
+        r1, r0 = np.asarray(i1.resnorms), np.asarray(i0.resnorms)
+        m = min(len(r1), len(r0))
+        live = r0[:m] / r0[0] >= 1e-6
+        np.testing.assert_allclose(r1[:m][live], r0[:m][live], rtol=1e-8)
+        np.testing.assert_allclose(s1, s0, rtol=0, atol=1e-8)
+    finally:
+        lib.kb_tune(16, 1)
+        lib.kb_tune(17, 0)
+        lib.kb_tune(18, 0)
+
+
+def test_line_marching_spmm_default_selection():
+    """default rule: the kernel runs where a line fills at least half of its chunks (C4: 256 x 16)"""
+    import ctypes
+
+    from krylov_b200._lib import check, lib
+
+    for n1, k, want in ((64, 16, True), (64, 8, True), (16, 16, False), (64, 3, False), (40, 16, True)):
+        Ad = device_stencil7(n1, 8, 8)
+        x = torch.zeros((Ad.shape[0], k), dtype=torch.float64, device="cuda")
+        yes = ctypes.c_int(0)
+        check(lib.kb_spmm_is_lines(Ad.handle, k, x.data_ptr(), ctypes.byref(yes)))
+        assert bool(yes.value) == want, (n1, k)
