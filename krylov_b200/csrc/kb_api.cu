@@ -57,6 +57,7 @@ static int g_cg_fuse = 1;      // kb_tune key 15: fused marching CG kernels in k
 static int g_spmm_lines = 1;    // kb_tune key 16: line-marching SpMM (k > 1, constant 3-D stencils):
                                 // 0 off, 1 where a line fills >= half of its chunks, 2 wherever valid
 static int g_lines_ch = 0;      // kb_tune key 17: lines per work item of it (0 = 32)
+static int g_lines_order = 1;   // kb_tune key 19: work-item order, 0 natural, 1 planes fastest
 static int g_lines_cfg = 0;     // kb_tune key 18: 0 = 1024-entry chunks, 2 CTAs/SM; 1 = 512, 4 CTAs/SM
 static int g_stencil_ctas = 0;  // kb_tune key 11: CTAs/SM cap of it (0 = occupancy limit)
 static int g_cgs_jc = 8;  // kb_tune key 9: basis vectors per multi-dot launch (8 or 16)
@@ -212,6 +213,7 @@ int kb_tune(int key, int value) {
     case 16: g_spmm_lines = value; return KB_OK;
     case 17: g_lines_ch = value; return KB_OK;
     case 18: g_lines_cfg = value; return KB_OK;
+    case 19: g_lines_order = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -880,6 +882,16 @@ static bool kb_lines_geom(const kb_csr_s* A, int k, const double* x, KbLines* g)
   if (ch < 1) ch = 1;
   g->ch = (int)ch;
   g->nitems = (long long)g->ncol * ((g->nlines + ch - 1) / ch);
+  if (g->L + TR >= (1ll << 31)) return false;  // in-line positions are 32-bit
+  g->tail = (int)(g->N - (g->nlines - 1) * g->L);
+  g->lpp = 0;
+  g->nplanes = 1;
+  if (g_lines_order == 1 && g->Pz % g->L == 0) {
+    g->lpp = g->Pz / g->L;
+    g->nplanes = (g->nlines + g->lpp - 1) / g->lpp;
+    const long long gpp = (g->lpp + ch - 1) / ch;
+    g->nitems = gpp * g->ncol * g->nplanes;
+  }
   return true;
 }
 

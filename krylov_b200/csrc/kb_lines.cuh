@@ -37,7 +37,34 @@ struct KbLines {
   int ncol;          // chunks per line
   int ch;            // lines per work item
   int TR;            // entries per chunk (256 x entries per thread)
+  // work-item order.  lpp > 0: planes fastest -- item = ((group in plane) * ncol + chunk) * nplanes
+  // + plane, so that CTAs running side by side hold the same chunk of neighbouring planes and the
+  // +-Pz chunks are L2 hits; lpp == 0: natural order (line groups, then chunks).
+  long long lpp;     // lines per plane (Pz / L), 0 = natural order
+  long long nplanes; // ceil(nlines / lpp)
+  int tail;          // entries of the last line (N - (nlines - 1) L)
 };
+
+// lines [r0, r1) and chunk c of a work item; false for an empty item (plane-fastest order only)
+__device__ __forceinline__ bool kb_lines_item(const KbLines& g, long long item, int& c,
+                                              long long& r0, long long& r1) {
+  if (g.lpp == 0) {
+    c = (int)(item % g.ncol);
+    r0 = (item / g.ncol) * g.ch;
+    r1 = (r0 + g.ch < g.nlines) ? r0 + g.ch : g.nlines;
+    return true;
+  }
+  const long long zp = item % g.nplanes;
+  const long long gc = item / g.nplanes;
+  c = (int)(gc % g.ncol);
+  const long long gi = gc / g.ncol;
+  r0 = zp * g.lpp + gi * g.ch;
+  long long e = r0 + g.ch;
+  const long long pe = (zp + 1) * g.lpp;
+  e = e < pe ? e : pe;
+  r1 = e < g.nlines ? e : g.nlines;
+  return r1 > r0;
+}
 
 template <int RPT, int NS, int MINB, int DOT, bool WX>
 __global__ void __launch_bounds__(256 + 32, MINB)
@@ -73,9 +100,9 @@ kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals 
       const uint64_t pol = kb_policy_evict_last();
       unsigned cnt = 0;
       for (long long item = blockIdx.x; item < g.nitems; item += gridDim.x) {
-        const int c = (int)(item % g.ncol);
-        const long long r0 = (item / g.ncol) * g.ch;
-        const long long r1 = (r0 + g.ch < g.nlines) ? r0 + g.ch : g.nlines;
+        int c;
+        long long r0, r1;
+        if (!kb_lines_item(g, item, c, r0, r1)) continue;
         const int nload = (int)(r1 - r0) + 2;
         for (int l = 0; l < nload; ++l, ++cnt) {
           const int slot = (int)(cnt % NS);
@@ -123,12 +150,16 @@ kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals 
     double cf = 0.0;
     if (mode == 1) cf = coef[col];
     unsigned cnt = 0;
+    const int mq = 256 >> g.kshift;  // mask entries between consecutive q (256 % k == 0)
     for (long long item = blockIdx.x; item < g.nitems; item += gridDim.x) {
-      const int c = (int)(item % g.ncol);
-      const long long r0 = (item / g.ncol) * g.ch;
-      const long long r1 = (r0 + g.ch < g.nlines) ? r0 + g.ch : g.nlines;
+      int c;
+      long long r0, r1;
+      if (!kb_lines_item(g, item, c, r0, r1)) continue;
       const int nload = (int)(r1 - r0) + 2;
-      const long long pos0 = (long long)c * TR + tid;  // in-line position of entry q = 0
+      const int pos0 = c * TR + tid;  // in-line position of entry q = 0
+      // Running index of entry q = 0 of the line computed in the current pass; everything per
+      // entry is an immediate offset (q * 256) from it -- no 64-bit arithmetic per entry and pass.
+      long long e = (r0 - 2) * g.L + pos0;
       unsigned mn[RPT];
       double zn[RPT], wn[RPT];
 #pragma unroll
@@ -136,29 +167,31 @@ kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals 
         mn[q] = 0u;
         zn[q] = wn[q] = 0.0;
       }
-      for (int l = 0; l < nload; ++l, ++cnt) {
+      for (int l = 0; l < nload; ++l, ++cnt, e += g.L) {
         const int slot = (int)(cnt % NS);
         const long long rc = r0 + l - 2;  // line computed in this pass (l >= 2)
+        // valid positions of this line and of the next one (the last line may be short)
+        const int limc = l >= 2 ? (rc == g.nlines - 1 ? g.tail : (int)g.L) : 0;
+        const int limn = (l >= 1 && l + 1 < nload) ? (rc + 1 == g.nlines - 1 ? g.tail : (int)g.L) : 0;
         unsigned m[RPT];
         double zv[RPT], wv[RPT];
-        long long ent[RPT];
+        bool okq[RPT];
+        const long long en = e + g.L;
+        const uint16_t* const mp = masks + (en >> g.kshift);
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
-          const long long pos = pos0 + q * 256;
-          const long long e64 = rc * g.L + pos;
-          const bool ok = l >= 2 && pos < g.L && e64 < g.N;
-          ent[q] = ok ? e64 : -1;
+          const int pos = pos0 + q * 256;
+          okq[q] = pos < limc;
           m[q] = mn[q];
           zv[q] = zn[q];
           wv[q] = wn[q];
           // operands of the next pass (line rc + 1) are requested one pass ahead
-          const long long n64 = e64 + g.L;
-          const bool nok = l >= 1 && l + 1 < nload && pos < g.L && n64 < g.N;
-          mn[q] = nok ? (unsigned)masks[n64 >> g.kshift] : 0u;
+          const bool nok = pos < limn;
+          mn[q] = nok ? (unsigned)mp[q * mq] : 0u;
           zn[q] = wn[q] = 0.0;
           if (nok) {
-            if (mode != 0) zn[q] = z[n64];
-            if (DOT == 1 && !WX) wn[q] = w[n64];
+            if (mode != 0) zn[q] = z[en + q * 256];
+            if (DOT == 1 && !WX) wn[q] = w[en + q * 256];
           }
         }
         kb_mbar_wait(&s_full[slot], (cnt / NS) & 1u);
@@ -179,11 +212,11 @@ kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals 
           if constexpr (RPT == 4) kb_march_rows<7, 2, 2>(a, m, cv, sum, ctr);
 #pragma unroll
           for (int q = 0; q < RPT; ++q) {
-            if (ent[q] >= 0) {
+            if (okq[q]) {
               double yv = sum[q];
               if (mode == 1) yv = kb_mul_sub(cf, zv[q], sum[q]);
               if (mode == 2) yv = __dsub_rn(zv[q], sum[q]);
-              __stcs(&y[ent[q]], yv);
+              __stcs(&y[e + q * 256], yv);
               if (DOT == 1) acc = fma(WX ? ctr[q] : wv[q], yv, acc);
               if (DOT == 2) acc = fma(yv, yv, acc);
             }

@@ -548,9 +548,9 @@ def test_fused_marching_cg_step_by_step_paths():
     assert np.linalg.norm(out[1][0] - sol_o) <= 1e-10 * np.linalg.norm(sol_o)
 
 
-@pytest.mark.parametrize("chunk", [0, 1])
+@pytest.mark.parametrize("chunk,order", [(0, 1), (1, 1), (0, 0)])
 @pytest.mark.parametrize("k", [2, 4, 8, 16, 32])
-def test_line_marching_spmm_bit_exact(k, chunk):
+def test_line_marching_spmm_bit_exact(k, chunk, order):
     """kb_spmm_lines_kernel (blocked right-hand sides on constant 3-D stencils): bit-identical to
     SciPy's csr_matvecs and to the row-wise kernel in every mode, incl. lines shorter / longer than
     a chunk, a truncated last plane, one line per item, and the <x, A x> operand taken on chip."""
@@ -565,6 +565,7 @@ def test_line_marching_spmm_bit_exact(k, chunk):
 
     lib.kb_tune(16, 2)  # wherever the geometry is valid (default: only where lines fill their chunks)
     lib.kb_tune(18, chunk)  # 1024- / 512-entry chunks
+    lib.kb_tune(19, order)  # work items: planes fastest (default) / natural order
     try:
         for (nx, ny, nz), coeffs, ch in (((70, 5, 4), st.STENCIL_POISSON, 0), ((33, 4, 5), st.convdiff_coeffs(), 3),
                                         ((130, 3, 3), st.convdiff_coeffs(), 1), ((16, 16, 16), st.STENCIL_POISSON, 0)):
@@ -618,6 +619,7 @@ def test_line_marching_spmm_bit_exact(k, chunk):
         lib.kb_tune(16, 1)
         lib.kb_tune(17, 0)
         lib.kb_tune(18, 0)
+        lib.kb_tune(19, 1)
 
 
 def test_line_marching_spmm_default_selection():

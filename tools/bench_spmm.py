@@ -30,19 +30,21 @@ N = a.n
 A = device_stencil7(N, N, N)
 n = A.shape[0]
 print(f"3-D Poisson {N}^3, peak {peak:.1f} GB/s")
-for k in ((16,) if a.quick else (16, 8, 4, 2, 32)):
+for k in ((16,) if a.quick else (16, 8, 4, 32)):
     ops = Ops(n, k)
     x = torch.randn(n, k, dtype=torch.float64, device="cuda")
     y = torch.empty_like(x)
     out = ops.slots(1)[0]
     res = {}
-    for name, cfg, ch, chunk in (("row-wise", 0, 0, 0), ("lines 1024/32", 1, 0, 0), ("lines 1024/64", 1, 64, 0),
-                                 ("lines 512/32", 1, 0, 1), ("lines 512/64", 1, 64, 1)):
-        if a.quick and (ch or chunk):
+    for name, cfg, ch, chunk, order in (("row-wise", 0, 0, 0, 1), ("lines planes/32", 1, 0, 0, 1),
+                                        ("lines planes/64", 1, 64, 0, 1), ("lines planes/16", 1, 16, 0, 1),
+                                        ("lines natural/32", 1, 0, 0, 0), ("lines 512 pl/32", 1, 0, 1, 1)):
+        if a.quick and (ch or chunk or not order):
             continue
         lib.kb_tune(16, cfg)
         lib.kb_tune(17, ch)
         lib.kb_tune(18, chunk)
+        lib.kb_tune(19, order)
         for _ in range(2):
             ops.spmv(A, x, y, dot=1, w=x, out=out)
         torch.cuda.synchronize()
@@ -55,7 +57,7 @@ for k in ((16,) if a.quick else (16, 8, 4, 2, 32)):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         res[name] = (y.clone(), out.clone())
-        print(f"k={k:2d} {name:13s}: {ms:7.3f} ms  model {A.spmv_bytes(k) / ms / 1e6:6.0f} GB/s = "
+        print(f"k={k:2d} {name:16s}: {ms:7.3f} ms  model {A.spmv_bytes(k) / ms / 1e6:6.0f} GB/s = "
               f"{A.spmv_bytes(k) / ms / 1e6 / peak:5.3f} of peak   (x in + y out only: {16.0 * n * k / ms / 1e6:6.0f} GB/s)",
               flush=True)
     ref = res["row-wise"][0]
@@ -63,6 +65,7 @@ for k in ((16,) if a.quick else (16, 8, 4, 2, 32)):
     del x, y, res, ref
 lib.kb_tune(17, 0)
 lib.kb_tune(18, 0)
+lib.kb_tune(19, 1)
 if not a.quick:
     g = torch.Generator(device="cuda").manual_seed(0)
     B = torch.randn((n, 16), generator=g, dtype=torch.float64, device="cuda")
