@@ -108,3 +108,43 @@ def test_no_cpu_fallback():
         kb.utils.hegedus(np.eye(6), np.ones(6), np.ones(6))
     with pytest.raises(kb.KrylovB200Error):
         kb.utils.EuclideanInner()(X, X)
+
+
+def test_edge_shapes():
+    """empty blocks, square / wide blocks (LAPACK convention vs np.linalg.qr), a wide block under
+    Gram-Schmidt, 1-D vectors, blocks where hegedus is undefined"""
+    from oracle import krylov_oracle_utils as ou
+
+    rng = np.random.default_rng(0)
+    with utils_host_logic() as ku:
+        e = ku.EuclideanInner()
+        X0 = np.zeros((10, 0))
+        for inner in (e, None):
+            Q, R = ku.qr(X0, inner=inner)
+            assert Q.shape == (10, 0) and R.shape == (0, 0)
+        F = rng.standard_normal((10, 3))
+        np.testing.assert_array_equal(ku.angles(F, X0, inner=e), np.full(3, np.pi / 2))
+        th, U, V = ku.angles(X0, F, inner=e, compute_vectors=True)
+        assert U.shape == (10, 0) and V.shape == (10, 3) and np.all(th == np.pi / 2)
+        for shape in ((5, 5), (4, 7), (1, 3), (6, 1)):
+            X = rng.standard_normal(shape)
+            Q, R = ku.qr(X)
+            Qn, Rn = np.linalg.qr(X, mode="reduced")
+            assert Q.shape == Qn.shape and R.shape == Rn.shape
+            np.testing.assert_allclose(Q, Qn, rtol=0, atol=1e-14)
+            np.testing.assert_allclose(R, Rn, rtol=0, atol=1e-14)
+        X = rng.standard_normal((3, 5))
+        Q, R = ku.qr(X, inner=e)
+        Qr, Rr = ou.qr(X, inner=cu.numpy_inner("euclid", 3))
+        np.testing.assert_allclose(Q, Qr, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(R, Rr, rtol=0, atol=1e-14)
+        A, b, x0 = np.diag(np.arange(1.0, 7.0)), np.ones(6), np.linspace(1, 2, 6)
+        ref = ou.hegedus(A, b, x0, inner=cu.numpy_inner("euclid", 6))
+        for inner in (None, e, lambda x, y: np.dot(x.T.conj(), y)):
+            got = ku.hegedus(A, b, x0, inner=inner)
+            assert got.shape == (6,)
+            np.testing.assert_allclose(got, ref, rtol=1e-14)
+        with pytest.raises(ValueError):
+            ku.hegedus(A, np.ones((6, 2)), np.ones((6, 2)))
+        with pytest.raises(TypeError):
+            ku.qr(F, inner=3.0)
