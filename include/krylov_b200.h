@@ -49,7 +49,11 @@ int kb_last_error(char* buf, size_t len);
 int kb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* developer tunables: key 0 stream-kernel configuration (0..5), key 1 stream CTAs/SM
  * (0 = default), key 2 CTAs/SM of the vector and row-wise grids, key 3 CTAs/SM of the
- * pattern kernels, key 4 windowed-kernel configuration (-1 = gather variant) */
+ * pattern kernels, key 4 windowed-kernel configuration (-1 = gather variant); keys 5-15: see
+ * csrc/kb_api.cu (tile shapes and CTAs/SM of the stencil / marching / fused CG kernels);
+ * key 16 line-marching SpMM for blocked right-hand sides (0 off, 1 default rule, 2 wherever valid),
+ * 17 its lines per work item (0 = 32), 18 its chunk size (0 = 1024 entries, 1 = 512),
+ * 19 its work-item order (1 = planes fastest, 0 = natural) */
 int kb_tune(int key, int value);
 
 /* --- workspace -------------------------------------------------------- */

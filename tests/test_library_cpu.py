@@ -41,6 +41,15 @@ def test_argument_validation_without_gpu():
     assert "max_k" in L.last_error()
     assert L.lib.kb_csr_create(ctypes.byref(h), -1, 1, 0, None, None, None, 0, None) == -1
     assert L.lib.kb_tune(99, 0) == -1
+    # entry points added for utils / blocked right-hand sides: null handles are refused, not dereferenced
+    assert L.lib.kb_block_gram(None, 8, 2, 2, None, 2, None, 2, None, 2, None, 0, 0, None) == -1
+    assert "null workspace" in L.last_error()
+    assert L.lib.kb_block_apply(None, 8, 2, 2, None, 2, None, 2, None, 2, None, 2, 0, None) == -1
+    assert L.lib.kb_house_make2(None, 8, 0, None, None, None, None, 1, None) == -1
+    yes = ctypes.c_int(7)
+    assert L.lib.kb_spmm_is_lines(None, 16, None, ctypes.byref(yes)) == -1
+    for key in (16, 17, 18, 19):  # tunables of the line-marching SpMM exist (and are restored)
+        assert L.lib.kb_tune(key, {16: 1, 17: 0, 18: 0, 19: 1}[key]) == 0
     with pytest.raises(L.KrylovB200Error):
         L.check(-1)
 
