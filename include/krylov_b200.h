@@ -100,6 +100,11 @@ int kb_csr_destroy(kb_csr_t h);
 int kb_csr_set_schedule(kb_csr_t h, int schedule);
 int kb_csr_get_info(kb_csr_t h, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
                     int* max_row_len, int* schedule);
+/* The offset pattern found by kb_csr_create: *nd distinct diagonals (0 = none), their offsets
+ * col - row ascending in offsets16[0..nd), the one value of each in coeffs8 when *constv, and the
+ * library-owned per-row masks (bit d set: the row stores diagonal d).  Any output may be NULL. */
+int kb_csr_get_stencil(kb_csr_t h, int* nd, int* offsets16, double* coeffs8, int* constv,
+                       const uint16_t** masks);
 
 /* --- sparse products: `A @ x` (cg.py:86,180; arnoldi.py:73,176,244;
  *     minres.py:111,121; gmres.py:106) fused with what follows it ---------
@@ -144,6 +149,10 @@ int kb_halo_get_handle(kb_halo_t h, void* out64);
 int kb_halo_open(kb_halo_t h, const void* handles);
 int kb_halo_destroy(kb_halo_t h);
 int kb_halo_error(kb_halo_t h, int* err);
+/* Address of rank's data area as seen from this process (own allocation, or the CUDA-IPC mapping
+ * after kb_halo_open): vectors that neighbours write into -- the ghost-extended r of the row-
+ * partitioned CG path -- live there. */
+int kb_halo_data_ptr(kb_halo_t h, int rank, void** out);
 int kb_halo_push(kb_halo_t h, kb_ws_t ws, int k, int n_seg, const int64_t* segs, int64_t n_total,
                  const int32_t* idx, const double* x, void* stream);
 /* gather x[idx[i], :] -> buf[i, :] (halo send buffer) */
@@ -208,6 +217,24 @@ typedef struct {
    * new value from the number of executed steps).  p2 == NULL: three launches, p in place. */
   double* p2;
   int pcur;
+  /* Row-partitioned two-launch path (one process per GPU, z-slab of a 3-D constant-coefficient
+   * stencil; NULL / 0 on one GPU).  masks_ext != NULL: the kernels run on the ghost-extended row
+   * space [one plane of the lower neighbour | the n own rows | one plane of the upper neighbour],
+   * n_ext = n + 2 * plane rows, own_lo = plane: r, p, p2 are then the bases of EXTENDED buffers
+   * (x still of the own rows), masks_ext holds one diagonal mask per extended row (0 on the ghost
+   * planes, the global pattern -- neighbour couplings included -- on the own rows), slots has
+   * 7*k doubles with slot 6 permanently zero.  The r update stores the new r of the first / last
+   * own plane straight into the neighbours' ghost planes (r_push_lo / r_push_hi: peer-mapped
+   * addresses, NULL at the ends of the partition); the peer-memory all-reduce that ends the same
+   * kernel (kb_ws_set_comm, collective = 1) orders them before the next launch of every rank.
+   * The ghost planes of p are maintained locally (p' = r + omega p with the replicated omega), so
+   * r is the only vector that crosses NVLink: 2 planes per iteration, no separate exchange kernel.
+   * Every iteration (i = 0 too: p, p2 zero-filled on entry) moves p to the other buffer. */
+  const uint16_t* masks_ext;
+  int64_t n_ext;
+  int64_t own_lo;
+  double* r_push_lo;
+  double* r_push_hi;
 } kb_cg_state;
 int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending, void* stream);
 /* *fused = 1 if kb_cg_run would take the two-launch path for this state (see p2 above). */

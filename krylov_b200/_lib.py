@@ -42,6 +42,7 @@ class CgState(C.Structure):
     _fields_ = [
         ("A", vp), ("n", i64), ("k", i32), ("x", vp), ("r", vp), ("p", vp), ("Ap", vp),
         ("slots", vp), ("crit", vp), ("hist", vp), ("stop_at", vp), ("p2", vp), ("pcur", i32),
+        ("masks_ext", vp), ("n_ext", i64), ("own_lo", i64), ("r_push_lo", vp), ("r_push_hi", vp),
     ]
 
 
@@ -75,6 +76,8 @@ SIGNATURES = {
     "kb_csr_set_schedule": [vp, i32],
     "kb_csr_get_info": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32),
                         C.POINTER(i32)],
+    "kb_csr_get_stencil": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(f64), C.POINTER(i32),
+                           C.POINTER(vp)],
     "kb_spmv": [vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp],
     "kb_spmm_is_lines": [vp, i32, vp, C.POINTER(i32)],
     "kb_spmv_halo_add": [vp, i32, i64, f64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp],
@@ -83,6 +86,7 @@ SIGNATURES = {
     "kb_halo_open": [vp, vp],
     "kb_halo_destroy": [vp],
     "kb_halo_error": [vp, C.POINTER(i32)],
+    "kb_halo_data_ptr": [vp, i32, C.POINTER(vp)],
     "kb_halo_push": [vp, vp, i32, i32, vp, i64, vp, vp, vp],
     "kb_pack_rows": [vp, i32, i64, vp, vp, vp, vp],
     "kb_dot": [vp, i64, i32, vp, vp, vp, vp],

@@ -121,7 +121,21 @@ class FusedCG:
         self.n, self.k, self.dev = n, k, b.device
         self.comm = getattr(A, "comm", None)
         self.ops = ops = Ops(n, k, self.dev, comm=self.comm)
-        self.r = ops.vec(zero=False)
+        # Row-partitioned two-launch path (csrc/kb_march.cuh on the ghost-extended row space):
+        # r lives in the matrix's IPC-exported area so that the neighbours' r update can store
+        # their boundary planes into its ghost planes
+        self.gplan = None
+        if (self.comm is not None and k == 1 and M is None and Ml is None and ops.fused_allreduce
+                and hasattr(A, "fused_cg_plan")):
+            self.gplan = A.fused_cg_plan()
+        if self.gplan is not None:
+            P = self.gplan["P"]
+            self.r_ext = self.gplan["r_ext"]
+            self.r_ext[:P].zero_()
+            self.r_ext[P + n:].zero_()
+            self.r = self.r_ext[P:P + n].view(n, 1)
+        else:
+            self.r = ops.vec(zero=False)
         self.Ap = ops.vec(zero=False)
         self.yk = ops.vec(zero=True)
         self.z = ops.vec(zero=False) if M is not None else self.r   # M_Ml_rk (== Ml_rk if M = I)
@@ -131,7 +145,7 @@ class FusedCG:
         # sl[2] = alpha of the last iteration.  Landing slots of reductions (these may see
         # un-gated NCCL all-reduces after on-device convergence, so nothing persistent
         # lives there): sl[3] = <p, Ap>, sl[4] = <r, r>, sl[5] = scratch.
-        self.sl = ops.slots(6)
+        self.sl = ops.slots(7)  # sl[6] stays zero (omega of the first partitioned iteration)
         self.stop_at = torch.full((1,), INT_MAX, dtype=torch.int32, device=self.dev)
         self.hist = torch.zeros((_BATCH_MAX, k), dtype=torch.float64, device=self.dev)
         self.spmv_events = None  # bench hook: list of (start, end) CUDA events around A @ p
@@ -144,10 +158,28 @@ class FusedCG:
         # search direction: pbuf[pcur].  The fused marching kernels (single GPU, k = 1, 3-D
         # constant-coefficient stencil: kb_cg_run with a second buffer) read p with its halo
         # and write the new p to the other buffer; every other path updates pbuf[pcur] in place.
-        self.pbuf = [self.z.clone(), None]
         self.pcur = 0
         self.kk = 0
         self._cstate = None
+        if self.gplan is not None:
+            # both search-direction buffers ghost-extended and zero: iteration 0 forms p = r + 0 p
+            # on the own AND the ghost planes (the neighbours' r0 planes are exchanged once here)
+            P, n_ext = self.gplan["P"], self.gplan["n_ext"]
+            A.exchange_ghost_planes(self.r_ext, P)
+            self.p_ext = [torch.zeros(n_ext, dtype=torch.float64, device=self.dev) for _ in (0, 1)]
+            self.pbuf = [pe[P:P + n].view(n, 1) for pe in self.p_ext]
+            self._cstate = CgState(A=A.A_loc.handle, n=n, k=k, x=ptr(self.yk), r=ptr(self.r_ext),
+                                   p=ptr(self.p_ext[0]), Ap=ptr(self.Ap), slots=ptr(self.sl),
+                                   crit=ptr(self.crit_d), hist=ptr(self.hist),
+                                   stop_at=ptr(self.stop_at), p2=ptr(self.p_ext[1]), pcur=0,
+                                   masks_ext=ptr(self.gplan["masks_ext"]), n_ext=n_ext, own_lo=P,
+                                   r_push_lo=self.gplan["push_lo"], r_push_hi=self.gplan["push_hi"])
+            fz = C.c_int(0)
+            check(lib.kb_cg_is_fused(C.byref(self._cstate), C.byref(fz)))
+            if not fz.value:
+                raise RuntimeError("row-partitioned fused CG: the library rejected the plan")
+        else:
+            self.pbuf = [self.z.clone(), None]
         if self.comm is None and hasattr(A, "handle") and M is None and Ml is None:
             if k == 1 and A.info()["schedule"] == "stencil":
                 self.pbuf[1] = ops.vec(zero=False)
@@ -237,17 +269,17 @@ class FusedCG:
         residual norms of the steps that actually ran (the rest were gated)."""
         kk, k = self.kk, self.k
         self.stop_at.fill_(INT_MAX)
-        via_c = self.comm is None and self.spmv_events is None and self._cstate is not None
+        via_c = self.spmv_events is None and self._cstate is not None
         if via_c:
-            # single GPU: the whole batch is enqueued by one C call (kb_cg_run)
+            # the whole batch is enqueued by one C call (kb_cg_run); row-partitioned: the fused
+            # two-launch path with peer-memory pushes and all-reduces inside the kernels
             self._cstate.pcur = self.pcur
             fz = C.c_int(0)
             check(lib.kb_cg_is_fused(C.byref(self._cstate), C.byref(fz)))
             self.fused_march = bool(fz.value)
             check(lib.kb_cg_run(self.ops.ws.handle, C.byref(self._cstate), kk, nb,
                                 1 if self.x_pending else 0, cur_stream()))
-            self.ops.launches += (2 if self.fused_march else 3) * nb - (
-                (0 if self.fused_march else 1) if kk == 0 else 0)
+            self.ops.launches += self._launches_of(kk, nb)
             self.x_pending = True
         else:
             hist_ptr = self.hist.data_ptr() - (kk + 1) * k * 8  # history row kk+1 == hist[0]
@@ -257,11 +289,32 @@ class FusedCG:
         s = int(self.stop_at.item())  # one host read per batch
         done = min(s, kk + nb) - kk
         if via_c and self.fused_march:
-            # every executed iteration i > 0 moved p to the other buffer
-            self.pcur = (self.pcur + done - (1 if kk == 0 and done > 0 else 0)) % 2
+            self.pcur = self._pcur_after(kk, done)
         rows = self.hist[:done].cpu().numpy()
         self.kk += done
+        self._check_peers()
         return [rows[j].copy() for j in range(done)]
+
+    def _launches_of(self, kk, nb):
+        if self.gplan is not None:
+            return 2 * nb
+        return (2 if self.fused_march else 3) * nb - (
+            (0 if self.fused_march else 1) if kk == 0 else 0)
+
+    def _pcur_after(self, kk, done):
+        """Every executed iteration moves p to the other buffer, except iteration 0 on one
+        GPU (p = r0 is used in place there)."""
+        if self.gplan is not None:
+            return (self.pcur + done) % 2
+        return (self.pcur + done - (1 if kk == 0 and done > 0 else 0)) % 2
+
+    def _check_peers(self):
+        """A peer that never arrived (3 s device-side budget) poisons the results with NaN and
+        raises the sticky error word: turn it into an exception at every batch boundary."""
+        if self.comm is not None:
+            chk = getattr(self.A, "check_p2p", None) or getattr(self.comm, "check_p2p", None)
+            if chk is not None:
+                chk()
 
 
     def run_timed(self, nb):
@@ -269,7 +322,7 @@ class FusedCG:
         CUDA events around each one on the launching stream.  Returns (mean ms of the step's
         phases, total ms, fused?).  Phases: fused path {p/x update + A p + <p,Ap>, r update +
         <r,r>}; three-kernel path {p/x update, A p + <p,Ap>, r update + <r,r>}."""
-        assert self.comm is None and self._cstate is not None, "single-GPU C path only"
+        assert self._cstate is not None, "C batch path only"
         kk = self.kk
         self.stop_at.fill_(INT_MAX)
         self._cstate.pcur = self.pcur
@@ -280,14 +333,14 @@ class FusedCG:
         tot = C.c_float(0)
         check(lib.kb_cg_run_timed(self.ops.ws.handle, C.byref(self._cstate), kk, nb,
                                   1 if self.x_pending else 0, cur_stream(), ms, C.byref(tot)))
-        self.ops.launches += (2 if self.fused_march else 3) * nb - (
-            (0 if self.fused_march else 1) if kk == 0 else 0)
+        self.ops.launches += self._launches_of(kk, nb)
         self.x_pending = True
         s = int(self.stop_at.item())
         done = min(s, kk + nb) - kk
         if self.fused_march:
-            self.pcur = (self.pcur + done - (1 if kk == 0 and done > 0 else 0)) % 2
+            self.pcur = self._pcur_after(kk, done)
         self.kk += done
+        self._check_peers()
         n_ph = 2 if self.fused_march else 3
         return [float(ms[i]) for i in range(n_ph)], float(tot.value), self.fused_march
 

@@ -216,6 +216,19 @@ class CsrMatrix:
                 "max_row_len": mx.value,
                 "schedule": {1: "rowwise", 2: "stream", 3: "pattern", 4: "stencil"}[sc.value]}
 
+    def stencil_info(self):
+        """Offset pattern detected at creation: ``{"nd", "offsets", "coeffs", "constv",
+        "masks_ptr"}`` (nd = 0: no pattern; coeffs valid when constv; masks_ptr: device address
+        of the library-owned 16-bit row masks)."""
+        nd, cv = C.c_int(), C.c_int()
+        offs = (C.c_int * 16)()
+        co = (C.c_double * 8)()
+        mp = C.c_void_p()
+        check(lib.kb_csr_get_stencil(self.handle, C.byref(nd), offs, co, C.byref(cv), C.byref(mp)))
+        return {"nd": nd.value, "offsets": [int(o) for o in offs[: nd.value]],
+                "coeffs": [float(c) for c in co[: min(nd.value, 8)]], "constv": bool(cv.value),
+                "masks_ptr": mp.value}
+
     def set_schedule(self, name: str):
         check(lib.kb_csr_set_schedule(self.handle, _SCHEDULES[name]))
         return self

@@ -54,6 +54,7 @@ static int g_stencil_l2pol = 0; // kb_tune key 12: L2 hint of the x windows (0 e
 static int g_march_ch = 0;     // kb_tune key 13: planes per work item of the marching kernel (0 auto)
 static int g_march_cfg = 0;    // kb_tune key 14: tile / ring shape of the marching kernel
 static int g_cg_fuse = 1;      // kb_tune key 15: fused marching CG kernels in kb_cg_run (0 off)
+static int g_march_even = 1;   // kb_tune key 20: marching grids sized for equal items per CTA
 static int g_spmm_lines = 1;    // kb_tune key 16: line-marching SpMM (k > 1, constant 3-D stencils):
                                 // 0 off, 1 where a line fills >= half of its chunks, 2 wherever valid
 static int g_lines_ch = 0;      // kb_tune key 17: lines per work item of it (0 = 32)
@@ -214,6 +215,7 @@ int kb_tune(int key, int value) {
     case 17: g_lines_ch = value; return KB_OK;
     case 18: g_lines_cfg = value; return KB_OK;
     case 19: g_lines_order = value; return KB_OK;
+    case 20: g_march_even = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -477,6 +479,19 @@ int kb_csr_get_info(kb_csr_t h, int64_t* n_rows, int64_t* n_cols, int64_t* nnz, 
   if (nnz) *nnz = h->nnz;
   if (max_row_len) *max_row_len = h->max_row_len;
   if (schedule) *schedule = h->schedule;
+  return KB_OK;
+}
+
+int kb_csr_get_stencil(kb_csr_t h, int* nd, int* offsets16, double* coeffs8, int* constv,
+                       const uint16_t** masks) {
+  KB_REQUIRE(h != nullptr, "null matrix");
+  if (nd) *nd = h->pattern_ok ? h->pat.nd : 0;
+  if (offsets16)
+    for (int i = 0; i < 16; ++i) offsets16[i] = h->pattern_ok ? h->pat.off[i] : 0;
+  if (coeffs8)
+    for (int i = 0; i < 8; ++i) coeffs8[i] = h->constv ? h->cv.c[i] : 0.0;
+  if (constv) *constv = h->constv;
+  if (masks) *masks = h->pattern_ok ? h->masks : nullptr;
   return KB_OK;
 }
 
@@ -785,6 +800,12 @@ static int kb_launch_march_t(kb_csr_s* A, kb_ws_s* ws, const KbMarch& g, const d
   int grid = ws->num_sms * ctas;
   if (grid > g.nitems) grid = g.nitems;
   if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
+  if (g_march_even && grid > 0) {
+    // the work items cost the same: the smallest grid that needs the same number of rounds ends
+    // with every CTA busy instead of a last round that fills a fraction of the machine
+    const int rounds = (g.nitems + grid - 1) / grid;
+    grid = (g.nitems + rounds - 1) / rounds;
+  }
   kern<<<grid, 288, smem, st>>>((int)A->n_rows, (int)A->n_cols, g, A->masks, A->pat, A->cv, x, y,
                                 mode, z, coef, w, cg, g_stencil_l2pol, out, kb_red(ws));
   KB_LAUNCH_CHECK();
@@ -1174,6 +1195,16 @@ int kb_halo_destroy(kb_halo_t h) {
   return KB_OK;
 }
 
+int kb_halo_data_ptr(kb_halo_t h, int rank, void** out) {
+  KB_REQUIRE(h != nullptr && out != nullptr, "null argument");
+  KB_REQUIRE(h->opened || rank == h->dev.rank, "halo not opened");
+  KB_REQUIRE(rank >= 0 && rank < h->dev.size, "bad rank");
+  unsigned char* b = rank == h->dev.rank ? h->base : (unsigned char*)h->peer_base[rank];
+  KB_REQUIRE(b != nullptr, "peer not mapped");
+  *out = b + KB_HALO_DATA;
+  return KB_OK;
+}
+
 int kb_halo_error(kb_halo_t h, int* err) {
   KB_REQUIRE(h != nullptr && err != nullptr, "null argument");
   KB_CUDA(cudaMemcpy(err, h->base + KB_HALO_ERROR, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1283,17 +1314,29 @@ int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new
 // Fused CG iteration on a 3-D constant-coefficient stencil (kb_march.cuh): p/x update fused with
 // A p and <p, A p> (reads p_in with halo, writes the other p buffer), r update with A p
 // recomputed from the ring.  Two launches and 64 n + masks bytes per iteration.
-static bool kb_cg_fusable(const kb_cg_state* s, KbMarch* g) {
+// Row-partitioned variant (s->masks_ext != NULL): the same two kernels on the ghost-extended row
+// space [ghost plane | own planes | ghost plane]; r, p, p2 are bases of extended buffers, x of the
+// own rows.  *ext receives a copy of the local matrix handle re-dimensioned to that space.
+static bool kb_cg_fusable(const kb_cg_state* s, KbMarch* g, kb_csr_s* ext) {
   if (!g_cg_fuse || s->k != 1 || s->p2 == nullptr || s->A->schedule != 4) return false;
-  if (!kb_march_geom(s->A, kb_march_rpt(), g) || s->A->pat.off[3] != 0) return false;
+  *ext = *s->A;
+  if (s->masks_ext != nullptr) {
+    ext->n_rows = ext->n_cols = s->n_ext;
+    ext->masks = const_cast<uint16_t*>(s->masks_ext);
+  }
+  if (!kb_march_geom(ext, kb_march_rpt(), g) || s->A->pat.off[3] != 0) return false;
   if (s->A->n_rows != s->n || s->A->n_cols != s->n) return false;
+  if (s->masks_ext != nullptr &&
+      (s->own_lo != g->P || s->n_ext != s->n + 2 * (int64_t)g->P || s->n % g->P != 0))
+    return false;
   return ((uintptr_t)s->p % 16 == 0) && ((uintptr_t)s->p2 % 16 == 0) && ((uintptr_t)s->r % 16 == 0);
 }
 
 int kb_cg_is_fused(const kb_cg_state* s, int* fused) {
   KB_REQUIRE(s != nullptr && fused != nullptr && s->A != nullptr, "null argument");
   KbMarch geo;
-  *fused = kb_cg_fusable(s, &geo) ? 1 : 0;
+  kb_csr_s ext;
+  *fused = kb_cg_fusable(s, &geo, &ext) ? 1 : 0;
   return KB_OK;
 }
 
@@ -1310,7 +1353,12 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
   const int saved_tag = ws->gate_tag;
   int rc = KB_OK;
   KbMarch geo;
-  const bool fused = kb_cg_fusable(s, &geo);
+  kb_csr_s ext;
+  const bool fused = kb_cg_fusable(s, &geo, &ext);
+  const bool parted = s->masks_ext != nullptr;  // row-partitioned: ghost-extended row space
+  KB_REQUIRE(!parted || fused, "row-partitioned kb_cg_run needs the fused marching path");
+  const int own_lo = parted ? (int)s->own_lo : 0;
+  const int own_hi = own_lo + (int)s->n;
   double* pb[2] = {s->p, s->p2};
   int pc = s->pcur;
   cudaStream_t st = S(stream);
@@ -1327,14 +1375,18 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
       KbMarchCg cg;
       memset(&cg, 0, sizeof(cg));
       cg.rec.step = -1;
-      if (i > 0) {  // [x += alpha p;] p' = r + omega p (into the other buffer); <p', A p'>
-        cg.rho_a = cur;
-        cg.rho_b = nxt;
+      cg.own_lo = own_lo;
+      cg.own_hi = own_hi;
+      if (i > 0 || parted) {  // [x += alpha p;] p' = r + omega p (into the other buffer); <p', A p'>
+        // row-partitioned, i == 0: omega = 0 / nz(0) from the permanently zero slot 6 and a
+        // zero-filled p, so that p' = r on the ghost planes as well
+        cg.rho_a = i > 0 ? cur : sl + 6 * (size_t)k;
+        cg.rho_b = i > 0 ? nxt : sl + 6 * (size_t)k;
         cg.alpha_in = alpha;
         cg.r_in = s->r;
-        cg.xv = x_pending ? s->x : nullptr;
+        cg.xv = (x_pending && i > 0) ? s->x - own_lo : nullptr;
         cg.p_out = pb[pc ^ 1];
-        rc = kb_launch_march<1, 1, false>(s->A, ws, geo, pb[pc], nullptr, 0, nullptr, nullptr,
+        rc = kb_launch_march<1, 1, false>(&ext, ws, geo, pb[pc], nullptr, 0, nullptr, nullptr,
                                           nullptr, cg, pAp, st);
         pc ^= 1;
       } else {
@@ -1343,6 +1395,10 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
       if (ev) cudaEventRecord(ev[3 * (i - i0) + 1], st);
       if (rc == KB_OK) {  // alpha; r -= alpha (A p); <r, r>; record step i+1, rho_{i+1} -> nxt
         memset(&cg, 0, sizeof(cg));
+        cg.own_lo = own_lo;
+        cg.own_hi = own_hi;
+        cg.push_lo = parted ? s->r_push_lo : nullptr;
+        cg.push_hi = parted ? s->r_push_hi : nullptr;
         cg.rho_a = cur;
         cg.rho_b = pAp;
         cg.alpha_out = alpha;
@@ -1352,7 +1408,7 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
         cg.rec.hist = s->hist - (size_t)(i0 + 1) * k;
         cg.rec.stop_at = s->stop_at;
         cg.rec.rho_keep = nxt;
-        rc = kb_launch_march<2, 2, false>(s->A, ws, geo, pb[pc], nullptr, 0, nullptr, nullptr,
+        rc = kb_launch_march<2, 2, false>(&ext, ws, geo, pb[pc], nullptr, 0, nullptr, nullptr,
                                           nullptr, cg, rr, st);
       }
       if (ev) cudaEventRecord(ev[3 * (i - i0) + 2], st);
@@ -1392,7 +1448,8 @@ int kb_cg_run_timed(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x
   KB_REQUIRE(ms != nullptr && total_ms != nullptr && n_iters >= 1 && n_iters <= 100000,
              "bad argument");
   KbMarch geo;
-  const bool fused = s != nullptr && s->A != nullptr && kb_cg_fusable(s, &geo);
+  kb_csr_s ext;
+  const bool fused = s != nullptr && s->A != nullptr && kb_cg_fusable(s, &geo, &ext);
   const int ne = 3 * n_iters + 1;
   cudaEvent_t* ev = new (std::nothrow) cudaEvent_t[ne];
   if (!ev) return kb_fail(KB_ECUDA, "kb_cg_run_timed: out of memory");

@@ -46,6 +46,16 @@ struct KbMarchCg {
   double* xv;              // KIND 1: x (own rows), may be null: no x update
   double* p_out;           // KIND 1: the new search direction (a buffer different from p_in)
   KbCgRecord rec;          // KIND 2
+  // Row-partitioned problems run the same kernels on a ghost-extended row space: one plane of the
+  // lower neighbour, the rank's own planes, one plane of the upper neighbour (masks of the ghost
+  // rows are 0).  Rows [own_lo, own_hi) are this rank's: only they enter the dots and update x
+  // and r; p_out is written for every row (the ghost planes of p are kept up to date locally:
+  // p' = r + omega p with the neighbours' r and the replicated omega).  KIND 2 also stores the
+  // new r of its first / last own plane into the neighbours' ghost planes (NVLink peer stores);
+  // the all-reduce that ends the kernel is what tells the neighbours that they have landed.
+  int own_lo, own_hi;
+  double* push_lo;         // KIND 2: the lower neighbour's upper ghost plane of r (peer-mapped) or null
+  double* push_hi;         // KIND 2: the upper neighbour's lower ghost plane of r or null
 };
 
 __device__ __forceinline__ void kb_st_f64_shared(uint32_t addr, double v) {
@@ -221,12 +231,15 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
         unsigned m[RPT];
         double zv[RPT], wv[RPT], xo[RPT];
         int row[RPT], trow[RPT];
+        bool xrow[RPT];
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
           const int pos = pos0 + q * 256;
           const long long r64 = (long long)jc * g.P + pos;
-          const bool ok = l >= 2 && pos < g.P && r64 < (long long)n_rows;
+          bool ok = l >= 2 && pos < g.P && r64 < (long long)n_rows;
+          if (KIND != 0) ok = ok && r64 >= (long long)cg.own_lo && r64 < (long long)cg.own_hi;
           row[q] = ok ? (int)r64 : -1;
+          xrow[q] = false;
           m[q] = mn[q];
           zv[q] = zn[q];
           wv[q] = wn[q];
@@ -239,16 +252,19 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
           if (nok) {
             if (KIND == 0 && mode != 0) zn[q] = z[n64];
             if (KIND == 0 && DOT == 1 && !WX) wn[q] = w[n64];
-            if (KIND == 2) zn[q] = cg.r[n64];
+            if (KIND == 2 && n64 >= (long long)cg.own_lo && n64 < (long long)cg.own_hi)
+              zn[q] = cg.r[n64];
           }
           if (KIND == 1) {
             // own rows of the arriving plane j0 - 1 + l (inside the item for 1 <= l <= nload - 2)
             const long long t64 = r64 + g.P;
             const bool tok = l >= 1 && l <= nload - 2 && pos < g.P && t64 < (long long)n_rows;
             trow[q] = tok ? (int)t64 : -1;
+            xrow[q] = tok && t64 >= (long long)cg.own_lo && t64 < (long long)cg.own_hi;
             // x of the own rows of the plane arriving in the next pass
             const long long u64 = t64 + g.P;
-            const bool uok = l + 1 <= nload - 2 && pos < g.P && u64 < (long long)n_rows;
+            const bool uok = l + 1 <= nload - 2 && pos < g.P && u64 >= (long long)cg.own_lo &&
+                             u64 < (long long)cg.own_hi;
             xn[q] = (uok && cg.xv != nullptr) ? cg.xv[u64] : 0.0;
           }
         }
@@ -271,7 +287,8 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
               const double pn = kb_mul_add(omega, po[q], ro[q]);
               kb_st_f64_shared(pw + own + (uint32_t)q * 2048u, pn);
               if (trow[q] >= 0) {
-                if (cg.xv != nullptr) __stcs(&cg.xv[trow[q]], kb_mul_add(alpha, po[q], xo[q]));
+                if (cg.xv != nullptr && xrow[q])
+                  __stcs(&cg.xv[trow[q]], kb_mul_add(alpha, po[q], xo[q]));
                 __stcs(&cg.p_out[trow[q]], pn);
               }
             }
@@ -326,6 +343,10 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
               } else {
                 const double rn = kb_mul_sub(alpha, sum[q], zv[q]);  // r - alpha (A p)
                 cg.r[row[q]] = rn;
+                if (cg.push_lo != nullptr && row[q] < cg.own_lo + g.P)
+                  cg.push_lo[row[q] - cg.own_lo] = rn;
+                if (cg.push_hi != nullptr && row[q] >= cg.own_hi - g.P)
+                  cg.push_hi[row[q] - (cg.own_hi - g.P)] = rn;
                 acc = fma(rn, rn, acc);
               }
             }
@@ -343,6 +364,9 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
     }
   }
   if (KIND == 0 && DOT == 0) return;
+  // peer stores of r must be visible system-wide before this block's arrival is counted: the
+  // finishing block's all-reduce flag is the neighbours' "ghost planes landed" signal
+  if (KIND == 2 && (cg.push_lo != nullptr || cg.push_hi != nullptr)) __threadfence_system();
   const bool last = kb_grid_colsum(acc, 1, rd, out, red_sm);
   if (KIND == 2 && last && cg.rec.step >= 0) {  // cg.py:156,214-217 in the finishing block
     __syncthreads();

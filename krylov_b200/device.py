@@ -28,6 +28,23 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+class _DeviceMemory:
+    """Raw device memory owned by the library (or a peer process) as a CUDA-array-interface
+    object, so that torch can view it without a copy."""
+
+    def __init__(self, address, count, typestr, owner=None):
+        self.owner = owner  # keeps the allocation alive as long as the tensor lives
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr,
+                                         "data": (int(address), False), "version": 2}
+
+
+def view_device_memory(address, count, dtype, device, owner=None) -> torch.Tensor:
+    """1-D tensor over `count` elements at a raw device address (no copy, no ownership)."""
+    typestr = {torch.float64: "<f8", torch.int16: "<i2", torch.int32: "<i4"}[dtype]
+    with torch.cuda.device(device):
+        return torch.as_tensor(_DeviceMemory(address, count, typestr, owner), device=device)
+
+
 def as_device_matrix(v, device=None) -> torch.Tensor:
     """Any real array-like -> contiguous fp64 CUDA tensor."""
     if isinstance(v, torch.Tensor):

@@ -94,6 +94,22 @@ class Comm:
                 warnings.warn("krylov_b200: CUDA IPC peer mapping unavailable; using NCCL "
                               "all-reduce and send/recv")
 
+    def close(self):
+        if self.p2p_handle is not None:
+            from ._lib import lib
+
+            try:
+                lib.kb_comm_destroy(self.p2p_handle)
+            except Exception:
+                pass
+            self.p2p_handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def check_p2p(self):
         """Raise if a peer ever failed to arrive in a fused all-reduce."""
         if self.p2p_handle is not None:
@@ -305,6 +321,140 @@ class DistCsrMatrix:
             check(lib.kb_halo_error(h, C.byref(e)))
             if e.value:
                 raise KrylovB200Error("peer-memory halo exchange timed out waiting for a rank")
+
+    # ------------------------------------------------ two-launch CG across ranks --
+    def fused_cg_plan(self):
+        """Ghost-plane layout of the fused CG path, or None if this matrix does not qualify.
+
+        Qualifies: z-slab partition of a 3-D constant-coefficient 7-diagonal stencil whose only
+        couplings across ranks are the +-P (plane) diagonals towards the two neighbouring ranks,
+        every slab a whole number (>= 2) of planes, peer memory available.  Then a CG iteration
+        is the two marching kernels of the single-GPU path on the row space
+        ``[ghost plane | own planes | ghost plane]`` (csrc/kb_march.cuh): the r update stores its
+        first / last plane straight into the neighbours' ghost planes, the ghost planes of p are
+        recomputed locally, nothing else crosses NVLink.  Collective on first use (all ranks
+        must agree; the extended r lives in an IPC-exported allocation that is kept and reused
+        by later solves with this matrix)."""
+        if hasattr(self, "_fused_plan"):
+            return self._fused_plan
+        self._fused_plan = None
+        import ctypes as C
+
+        from ._lib import lib
+        from .device import view_device_memory
+
+        comm, plan, dev = self.comm, self.plan, self.device
+        n = self.shape[0]
+        ok = self.halo_mode == "p2p" and comm.p2p_handle is not None and comm.size > 1
+        P = 0
+        coeffs = ()
+        rows_lo = rows_hi = None
+        if ok:
+            si = self.A_loc.stencil_info()
+            off = si["offsets"]
+            ok = (si["constv"] and si["nd"] == 7 and self.A_loc.info()["schedule"] == "stencil"
+                  and off[3] == 0 and off[0] == -off[6] and off[6] > 0)
+        if ok:
+            P = off[6]
+            coeffs = tuple(si["coeffs"][:7])
+            r0 = plan.row_start
+            ok = (n % P == 0 and n >= 2 * P and all(int(o) % P == 0 for o in plan.offsets)
+                  and set(plan.peers) <= {comm.rank - 1, comm.rank + 1})
+        if ok and plan.n_brows:
+            # every halo entry must be the -P diagonal of a first-plane row (value c[0]) or the
+            # +P diagonal of a last-plane row (value c[6])
+            cnt = (plan.h_rowptr[1:] - plan.h_rowptr[:-1]).to(torch.int64)
+            rows = torch.repeat_interleave(plan.h_rows.to(torch.int64), cnt)
+            diff = plan.halo_globals[plan.h_col.to(torch.int64)] - (rows + r0)
+            lo, hi = diff == -P, diff == P
+            c_lo = torch.tensor(coeffs[0], dtype=torch.float64, device=dev)
+            c_hi = torch.tensor(coeffs[6], dtype=torch.float64, device=dev)
+            ok = bool(torch.all(lo | hi)) and bool(torch.all(rows[lo] < P)) \
+                and bool(torch.all(rows[hi] >= n - P)) \
+                and bool(torch.all(plan.h_val[lo] == c_lo)) and bool(torch.all(plan.h_val[hi] == c_hi))
+            rows_lo, rows_hi = rows[lo], rows[hi]
+        votes = comm.allgather_object((bool(ok), P, coeffs))
+        if not all(v[0] and v[1] == votes[0][1] and v[2] == votes[0][2] for v in votes):
+            return None
+        n_ext = n + 2 * P
+        with torch.cuda.device(dev):
+            h = C.c_void_p()
+            buf = C.create_string_buffer(64)
+            good = lib.kb_halo_create(C.byref(h), comm.rank, comm.size, n_ext * 8) == 0
+            good = good and lib.kb_halo_get_handle(h, buf) == 0
+            handles = comm.allgather_object(bytes(buf.raw) if good else b"")
+            good = good and all(len(x) == 64 for x in handles)
+            if good:
+                allh = C.create_string_buffer(b"".join(handles), 64 * comm.size)
+                good = lib.kb_halo_open(h, allh) == 0
+            if not comm._all_ok(good):
+                if h:
+                    lib.kb_halo_destroy(h)
+                return None
+            self._fused_halo = h
+
+            def data_ptr(rank):
+                out = C.c_void_p()
+                if lib.kb_halo_data_ptr(h, rank, C.byref(out)) != 0:
+                    raise RuntimeError("kb_halo_data_ptr failed")
+                return out.value
+
+            r_ext = view_device_memory(data_ptr(comm.rank), n_ext, torch.float64, dev)
+            # masks of the extended row space: global pattern on the own rows, 0 on the ghosts
+            m_loc = view_device_memory(si["masks_ptr"], n, torch.int16, dev)
+            masks = torch.zeros(n_ext, dtype=torch.int16, device=dev)
+            masks[P:P + n] = m_loc
+            if rows_lo is not None and rows_lo.numel():
+                masks[P + rows_lo] |= 1
+            if rows_hi is not None and rows_hi.numel():
+                masks[P + rows_hi] |= 1 << 6
+            sizes = [int(plan.offsets[q + 1] - plan.offsets[q]) for q in range(comm.size)]
+            push_lo = push_hi = None
+            if comm.rank > 0 and rows_lo is not None and rows_lo.numel():
+                # the lower neighbour's UPPER ghost plane: extended rows [P + n_prev, P + n_prev + P)
+                push_lo = data_ptr(comm.rank - 1) + 8 * (P + sizes[comm.rank - 1])
+            if comm.rank < comm.size - 1 and rows_hi is not None and rows_hi.numel():
+                push_hi = data_ptr(comm.rank + 1)  # the upper neighbour's LOWER ghost plane
+        self._fused_plan = {"P": P, "n_ext": n_ext, "r_ext": r_ext, "masks_ext": masks,
+                            "push_lo": push_lo, "push_hi": push_hi}
+        return self._fused_plan
+
+    def exchange_ghost_planes(self, v_ext, P):
+        """One-off (set-up) exchange: first / last own plane of the extended vector -> the
+        neighbours' ghost planes, by NCCL send/recv.  Inside the iteration the r update does
+        this itself with peer stores."""
+        n = self.shape[0]
+        r, size = self.comm.rank, self.comm.size
+        ops = []
+        if r > 0:
+            ops.append(dist.P2POp(dist.isend, v_ext[P:2 * P], r - 1, group=self.comm.group))
+            ops.append(dist.P2POp(dist.irecv, v_ext[:P], r - 1, group=self.comm.group))
+        if r < size - 1:
+            ops.append(dist.P2POp(dist.isend, v_ext[n:n + P], r + 1, group=self.comm.group))
+            ops.append(dist.P2POp(dist.irecv, v_ext[n + P:], r + 1, group=self.comm.group))
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+
+    def close(self):
+        """Unmaps / frees the peer-memory areas of this matrix (halo receive areas, the extended
+        r of the fused CG path).  Collective in spirit: call it on every rank."""
+        from ._lib import lib
+
+        self._fused_plan = None
+        for h in list(self._halos.values()) + [getattr(self, "_fused_halo", None)]:
+            if h:
+                try:
+                    lib.kb_halo_destroy(h)
+                except Exception:
+                    pass
+        self._halos = {}
+        self._fused_halo = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _buffers(self, k):
         b = self._bufs.get(k)

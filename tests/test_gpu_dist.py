@@ -27,3 +27,6 @@ def test_two_rank_solvers_match_single_gpu(tmp_path):
         assert d["steps_equal"], (name, d)
         assert d["hist_rel"] <= 1e-9, (name, d)
         assert d["sol_rel"] <= 1e-10, (name, d)
+        if name.startswith("fused_cg_"):
+            assert d["fused_path_used"], (name, d)
+            assert all(d["solve_success"]) and d["solve_final_rel"] <= 1e-10, (name, d)

@@ -145,3 +145,40 @@ def test_c5_cg_poisson3d_512_properties():
     for sched in ("rowwise", "stream", "pattern"):
         Ad.set_schedule(sched)
         assert torch.equal(Ad.matvec_device(x), y1)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE-scale parity against the REAL reference: tests/golden/scale.npz holds the residual
+# history and the final iterate (norms + 256 sampled entries) of the unmodified reference after a
+# fixed number of steps on the seeded systems of tests/scale_cases.py
+# (generated by tests/golden/make_golden_scale.py in the authoring container).
+import os
+
+import scale_cases as sc
+
+_SCALE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale.npz")
+
+
+@pytest.mark.parametrize("name", list(sc.CASES))
+def test_scale_fixture_vs_reference(name):
+    solver, steps, kw, N, kind, k = sc.CASES[name]
+    g = np.load(_SCALE)
+    coeffs, shift = sc.matrix_params(kind, N)
+    Ad = device_stencil7(N, N, N, coeffs=coeffs, shift=shift)
+    xs = torch.from_numpy(sc.xstar(name)).cuda()
+    b = Ad.matvec_device(xs)  # bit-identical to SciPy's csr_matvec(s) (tests/test_gpu_kernels.py)
+    del xs
+    _, info = getattr(kb, solver)(Ad, b, tol=0.0, atol=0.0, maxiter=steps, **kw)
+    assert info.numsteps == steps
+    res = np.asarray(info.resnorms, dtype=float)
+    ref = g[name + "_resnorms"]
+    assert res.shape == ref.shape
+    # north-star tolerances: residual history 1e-8 relative, solution 1e-10 relative
+    assert np.max(np.abs(res - ref) / ref) <= 1e-8, np.max(np.abs(res - ref) / ref)
+    x = info.xk
+    xn = torch.sqrt(torch.sum(x * x, dim=0)).cpu().numpy()
+    assert np.all(np.abs(xn - g[name + "_xnorm2"]) <= 1e-10 * g[name + "_xnorm2"])
+    idx = torch.from_numpy(sc.sample_index(N ** 3)).cuda()
+    samp = x[idx].cpu().numpy()
+    sref = g[name + "_xsample"]
+    assert np.max(np.abs(samp - sref)) <= 1e-10 * np.max(np.abs(sref))
