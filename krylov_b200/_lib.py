@@ -126,6 +126,12 @@ for _name, _args in SIGNATURES.items():
     _fn.restype = i32
 
 
+# experiments: KRYLOV_B200_TUNE="key=value,key=value" applies kb_tune settings at import
+for _kv in filter(None, os.environ.get("KRYLOV_B200_TUNE", "").split(",")):
+    _k, _v = _kv.split("=")
+    lib.kb_tune(int(_k), int(_v))
+
+
 def last_error() -> str:
     buf = C.create_string_buffer(512)
     lib.kb_last_error(buf, 512)

@@ -131,6 +131,8 @@ class FusedCG:
         if self.gplan is not None:
             P = self.gplan["P"]
             self.r_ext = self.gplan["r_ext"]
+            if getattr(FusedCG, "_debug_local_r", False):  # measurement only (tools/dist_slab.py)
+                self.r_ext = torch.zeros_like(self.r_ext)
             self.r_ext[:P].zero_()
             self.r_ext[P + n:].zero_()
             self.r = self.r_ext[P:P + n].view(n, 1)

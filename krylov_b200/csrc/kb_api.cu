@@ -54,7 +54,12 @@ static int g_stencil_l2pol = 0; // kb_tune key 12: L2 hint of the x windows (0 e
 static int g_march_ch = 0;     // kb_tune key 13: planes per work item of the marching kernel (0 auto)
 static int g_march_cfg = 0;    // kb_tune key 14: tile / ring shape of the marching kernel
 static int g_cg_fuse = 1;      // kb_tune key 15: fused marching CG kernels in kb_cg_run (0 off)
-static int g_march_even = 1;   // kb_tune key 20: marching grids sized for equal items per CTA
+static int g_part_dbg = 0;     // kb_tune key 21 (measurement only, results become wrong): bit 0 no
+                               // peer pushes of r, bit 1 no all-reduce in the partitioned CG kernels
+static int g_cg_cfg[2] = {-1, -1};  // kb_tune keys 22 / 23: shape of the fused CG kernels KIND 1 / 2 (-1 auto)
+static int g_march_depth = 96;  // kb_tune key 24: deepest grid marched top to bottom by one CTA per column
+static int g_march_even = 0;   // kb_tune key 20: marching grids sized for equal items per CTA (measured
+                               // no gain at 512^3 on one GPU: profiles/r2_march_even.txt)
 static int g_spmm_lines = 1;    // kb_tune key 16: line-marching SpMM (k > 1, constant 3-D stencils):
                                 // 0 off, 1 where a line fills >= half of its chunks, 2 wherever valid
 static int g_lines_ch = 0;      // kb_tune key 17: lines per work item of it (0 = 32)
@@ -216,6 +221,10 @@ int kb_tune(int key, int value) {
     case 18: g_lines_cfg = value; return KB_OK;
     case 19: g_lines_order = value; return KB_OK;
     case 20: g_march_even = value; return KB_OK;
+    case 21: g_part_dbg = value; return KB_OK;
+    case 22: g_cg_cfg[0] = value; return KB_OK;
+    case 23: g_cg_cfg[1] = value; return KB_OK;
+    case 24: g_march_depth = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -287,7 +296,7 @@ int kb_comm_create(kb_comm_t* out, int rank, int size, int max_k) {
   c->max_k = max_k;
   c->dev.rank = rank;
   c->dev.size = size;
-  c->dev.stride = ((1 + max_k + 15) / 16) * 16;  // 128-byte multiples
+  c->dev.stride = ((2 * max_k + 15) / 16) * 16;  // 16 bytes per value; 128-byte multiples
   // mailbox | counter | error live in one IPC-exported allocation
   const size_t mbox_doubles = (size_t)2 * size * c->dev.stride;
   const size_t bytes = (mbox_doubles + 16) * sizeof(double);
@@ -750,18 +759,18 @@ static int kb_launch_stencil2(kb_csr_s* A, kb_ws_s* ws, const double* x, double*
 // ------------------------------------------------ plane-marching stencil kernel ---
 // Geometry of kb_stencil_march_kernel for this matrix and tile height; false if the pattern is
 // not {-P, inner diagonals within +-1024, +P} with constant coefficients.
-static bool kb_march_geom(const kb_csr_s* A, int RPT, KbMarch* g) {
+static bool kb_march_geom(const kb_csr_s* A, int RPT, KbMarch* g, int CT = 256, int slots = 0) {
   if (!A->constv || A->pat.nd != 7 || A->masks == nullptr) return false;
   const int* off = A->pat.off;
   const int P = off[6];
-  if (P <= 0 || off[0] != -P || (P & 1)) return false;
+  if (P <= 0 || off[0] != -P || (P & 1) || A->n_rows % P != 0) return false;
   int L = 1;
   for (int d = 1; d < 6; ++d) {
     const int a = off[d] < 0 ? -off[d] : off[d];
     L = a > L ? a : L;
   }
-  const int LP = ((L + 255) / 256) * 256;
-  const int TR = 256 * RPT;
+  const int LP = ((L + CT - 1) / CT) * CT;
+  const int TR = CT * RPT;
   if (LP > 1024 || L >= P || P < TR) return false;
   if ((A->n_cols & 1) || A->n_rows >= (1ll << 31) - 4096 || A->n_cols >= (1ll << 31) - 4096)
     return false;
@@ -770,19 +779,26 @@ static bool kb_march_geom(const kb_csr_s* A, int RPT, KbMarch* g) {
   g->wlen = TR + 2 * LP;
   g->ncol = (P + TR - 1) / TR;
   g->nplanes = (int)((A->n_rows + P - 1) / P);
+  // planes per work item: 32 / 16 measured best on deep grids (profiles/r1_march_bench_512.txt);
+  // a thin slab with at least one column tile per SM (the per-rank share of a row-partitioned
+  // problem) is marched top to bottom by one CTA per column: no quantisation of the work over
+  // the grid, all columns in lock-step (profiles/r2_slab_tune.txt: 0.75 -> 0.80 of peak at 64 planes)
   int ch = g_march_ch > 0 ? g_march_ch : (g->nplanes >= 256 ? 32 : 16);
+  if (g_march_ch == 0 && g->nplanes <= g_march_depth &&
+      (slots > 0 ? (g->ncol <= slots && g->ncol * 100 >= slots * 85) : g->ncol >= 148))
+    ch = g->nplanes;
   if (ch > g->nplanes) ch = g->nplanes;
   g->ch = ch;
   g->nitems = g->ncol * ((g->nplanes + ch - 1) / ch);
   return true;
 }
 
-template <int RPT, int NS, int MINB, int KIND, int DOT, bool WX>
+template <int RPT, int NS, int MINB, int KIND, int DOT, bool WX, bool PART = false, int CT = 256>
 static int kb_launch_march_t(kb_csr_s* A, kb_ws_s* ws, const KbMarch& g, const double* x, double* y,
                              int mode, const double* z, const double* coef, const double* w,
                              const KbMarchCg& cg, double* out, cudaStream_t st) {
   static int max_smem[64] = {0};
-  auto kern = kb_stencil_march_kernel<7, RPT, NS, MINB, KIND, DOT, WX>;
+  auto kern = kb_stencil_march_kernel<7, RPT, NS, MINB, KIND, DOT, WX, PART, CT>;
   int dev = 0;
   KB_CUDA(cudaGetDevice(&dev));
   const size_t smem = (size_t)(NS + (KIND == 1 ? 2 : 0)) * g.wlen * 8 + (2 * NS + 2) * 8;
@@ -794,7 +810,7 @@ static int kb_launch_march_t(kb_csr_s* A, kb_ws_s* ws, const KbMarch& g, const d
     if (dev >= 0 && dev < 64) max_smem[dev] = lim - 8 * 1024;
   }
   int ctas = 0;
-  KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 288, smem));
+  KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, CT + 32, smem));
   if (ctas < 1) return kb_fail(KB_EUNSUPPORTED, "marching stencil kernel: ring does not fit");
   if (g_stencil_ctas > 0 && g_stencil_ctas < ctas) ctas = g_stencil_ctas;
   int grid = ws->num_sms * ctas;
@@ -806,15 +822,26 @@ static int kb_launch_march_t(kb_csr_s* A, kb_ws_s* ws, const KbMarch& g, const d
     const int rounds = (g.nitems + grid - 1) / grid;
     grid = (g.nitems + rounds - 1) / rounds;
   }
-  kern<<<grid, 288, smem, st>>>((int)A->n_rows, (int)A->n_cols, g, A->masks, A->pat, A->cv, x, y,
+  kern<<<grid, CT + 32, smem, st>>>((int)A->n_rows, (int)A->n_cols, g, A->masks, A->pat, A->cv, x, y,
                                 mode, z, coef, w, cg, g_stencil_l2pol, out, kb_red(ws));
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
 
 // kb_tune 14: 0 = 1024-row tiles, ring of 4; 1 = 1024 rows, ring of 5; 2 = 512 rows, ring of 4;
-// 3 = 512 rows, ring of 5
+// 3 = 512 rows, ring of 5; (fused CG kernels only) 4 = 896-row tiles (224 consumer threads x 4),
+// 5 = 768-row tiles (256 x 3)
 static int kb_march_rpt() { return (g_march_cfg == 2 || g_march_cfg == 3) ? 2 : 4; }
+
+// Tile shapes of the fused CG kernels: {rows per thread, consumer threads, resident CTAs per SM}
+struct KbShape { int cfg, rpt, ct, ctas1, ctas2; };  // ctas1 / ctas2: KIND 1 / KIND 2
+static const KbShape kb_shapes[] = {{0, 4, 256, 2, 3}, {1, 4, 256, 2, 2}, {2, 2, 256, 3, 4},
+                                    {3, 2, 256, 3, 3}, {4, 4, 224, 2, 3}, {5, 3, 256, 2, 3}};
+static const KbShape& kb_shape_of(int cfg) {
+  for (const KbShape& sh : kb_shapes)
+    if (sh.cfg == cfg) return sh;
+  return kb_shapes[0];
+}
 
 template <int KIND, int DOT, bool WX>
 static int kb_launch_march(kb_csr_s* A, kb_ws_s* ws, const KbMarch& g, const double* x, double* y,
@@ -827,6 +854,64 @@ static int kb_launch_march(kb_csr_s* A, kb_ws_s* ws, const KbMarch& g, const dou
     case 3: return kb_launch_march_t<2, 5, 3, KIND, DOT, WX>(A, ws, g, x, y, mode, z, coef, w, cg, out, st);
     default: return kb_launch_march_t<4, 4, (KIND == 1 ? 2 : 3), KIND, DOT, WX>(A, ws, g, x, y, mode, z, coef, w, cg, out, st);
   }
+}
+
+// The fused CG kernels (KIND 1 / 2) in any tile shape
+template <int KIND, int DOT, bool PART>
+static int kb_launch_march_cg(int cfg, kb_csr_s* A, kb_ws_s* ws, const KbMarch& g, const double* x,
+                              const KbMarchCg& cg, double* out, cudaStream_t st) {
+#define KB_MCG(RPT, NS, MINB, CT)                                                                  \
+  return kb_launch_march_t<RPT, NS, MINB, KIND, DOT, false, PART, CT>(A, ws, g, x, nullptr, 0,     \
+                                                                      nullptr, nullptr, nullptr,  \
+                                                                      cg, out, st)
+  switch (cfg) {
+    case 1: KB_MCG(4, 5, 2, 256);
+    case 2: KB_MCG(2, 4, (KIND == 1 ? 3 : 4), 256);
+    case 3: KB_MCG(2, 5, 3, 256);
+    case 4: KB_MCG(4, 4, (KIND == 1 ? 2 : 3), 224);
+    case 5: KB_MCG(3, 4, (KIND == 1 ? 2 : 3), 256);
+    default: KB_MCG(4, 4, (KIND == 1 ? 2 : 3), 256);
+  }
+#undef KB_MCG
+}
+
+// Tile shape + geometry of a fused CG kernel.  kb_tune 14 != 0 forces one shape; otherwise the
+// default 1024-row tiles unless another shape needs >= 5 % fewer tile-row-steps per CTA: the
+// per-CTA critical path is what bounds these kernels on thin slabs (profiles/r2_slab_tune.txt),
+// so a shape whose column count fills the machine's CTA slots in ONE round wins there
+// (512 x 512 planes: 293 tiles of 896 rows on 296 slots, 342 of 768 on 444).
+static bool kb_cg_pick_shape(const kb_csr_s* A, int num_sms, int kind, int* cfg, KbMarch* g) {
+  const int forced =
+      g_cg_cfg[kind - 1] >= 0 ? g_cg_cfg[kind - 1] : (g_march_cfg != 0 ? g_march_cfg : -1);
+  if (forced >= 0) {
+    const KbShape& sh = kb_shape_of(forced);
+    *cfg = sh.cfg;
+    return kb_march_geom(A, sh.rpt, g, sh.ct, num_sms * (kind == 1 ? sh.ctas1 : sh.ctas2));
+  }
+  static const int cand1[] = {0, 4}, cand2[] = {0, 5, 4};
+  const int* cand = kind == 1 ? cand1 : cand2;
+  const int nc = kind == 1 ? 2 : 3;
+  double cost0 = 0.0, best = 0.0;
+  bool found = false;
+  for (int i = 0; i < nc; ++i) {
+    const KbShape& sh = kb_shape_of(cand[i]);
+    const int slots = num_sms * (kind == 1 ? sh.ctas1 : sh.ctas2);
+    KbMarch gg;
+    if (!kb_march_geom(A, sh.rpt, &gg, sh.ct, slots)) continue;
+    const int rounds = (gg.nitems + slots - 1) / slots;
+    const double cost = (double)rounds * (gg.ch + 2) * sh.rpt * sh.ct;
+    if (!found) {  // the default shape (or the first that applies)
+      cost0 = best = cost;
+      *cfg = sh.cfg;
+      *g = gg;
+      found = true;
+    } else if (cost < 0.95 * cost0 && cost < best) {
+      best = cost;
+      *cfg = sh.cfg;
+      *g = gg;
+    }
+  }
+  return found;
 }
 
 // A x (+ epilogue, dot) by the marching kernel; KB_EUNSUPPORTED if the matrix does not qualify
@@ -1317,26 +1402,31 @@ int kb_cg_update_p(kb_ws_t ws, int64_t n, int k, int step, const double* rho_new
 // Row-partitioned variant (s->masks_ext != NULL): the same two kernels on the ghost-extended row
 // space [ghost plane | own planes | ghost plane]; r, p, p2 are bases of extended buffers, x of the
 // own rows.  *ext receives a copy of the local matrix handle re-dimensioned to that space.
-static bool kb_cg_fusable(const kb_cg_state* s, KbMarch* g, kb_csr_s* ext) {
+static bool kb_cg_fusable(const kb_cg_state* s, kb_csr_s* ext, int num_sms, int cfg[2],
+                          KbMarch geo[2]) {
   if (!g_cg_fuse || s->k != 1 || s->p2 == nullptr || s->A->schedule != 4) return false;
   *ext = *s->A;
   if (s->masks_ext != nullptr) {
     ext->n_rows = ext->n_cols = s->n_ext;
     ext->masks = const_cast<uint16_t*>(s->masks_ext);
   }
-  if (!kb_march_geom(ext, kb_march_rpt(), g) || s->A->pat.off[3] != 0) return false;
+  if (s->A->pat.off[3] != 0) return false;
+  if (!kb_cg_pick_shape(ext, num_sms, 1, &cfg[0], &geo[0])) return false;
+  if (!kb_cg_pick_shape(ext, num_sms, 2, &cfg[1], &geo[1])) return false;
   if (s->A->n_rows != s->n || s->A->n_cols != s->n) return false;
+  const int P = geo[0].P;
   if (s->masks_ext != nullptr &&
-      (s->own_lo != g->P || s->n_ext != s->n + 2 * (int64_t)g->P || s->n % g->P != 0))
+      (s->own_lo != P || s->n_ext != s->n + 2 * (int64_t)P || s->n % P != 0))
     return false;
   return ((uintptr_t)s->p % 16 == 0) && ((uintptr_t)s->p2 % 16 == 0) && ((uintptr_t)s->r % 16 == 0);
 }
 
 int kb_cg_is_fused(const kb_cg_state* s, int* fused) {
   KB_REQUIRE(s != nullptr && fused != nullptr && s->A != nullptr, "null argument");
-  KbMarch geo;
+  KbMarch geo[2];
+  int cfg[2];
   kb_csr_s ext;
-  *fused = kb_cg_fusable(s, &geo, &ext) ? 1 : 0;
+  *fused = kb_cg_fusable(s, &ext, 148, cfg, geo) ? 1 : 0;
   return KB_OK;
 }
 
@@ -1351,10 +1441,13 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
   double* sl = s->slots;
   const int* saved_gate = ws->gate;
   const int saved_tag = ws->gate_tag;
+  const int saved_coll = ws->collective;
+  if (g_part_dbg & 2) ws->collective = 0;
   int rc = KB_OK;
-  KbMarch geo;
+  KbMarch geo[2];
+  int cfg[2] = {0, 0};
   kb_csr_s ext;
-  const bool fused = kb_cg_fusable(s, &geo, &ext);
+  const bool fused = kb_cg_fusable(s, &ext, ws->num_sms, cfg, geo);
   const bool parted = s->masks_ext != nullptr;  // row-partitioned: ghost-extended row space
   KB_REQUIRE(!parted || fused, "row-partitioned kb_cg_run needs the fused marching path");
   const int own_lo = parted ? (int)s->own_lo : 0;
@@ -1377,6 +1470,8 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
       cg.rec.step = -1;
       cg.own_lo = own_lo;
       cg.own_hi = own_hi;
+      cg.own_pl0 = own_lo / geo[0].P;
+      cg.own_pl1 = own_hi / geo[0].P;
       if (i > 0 || parted) {  // [x += alpha p;] p' = r + omega p (into the other buffer); <p', A p'>
         // row-partitioned, i == 0: omega = 0 / nz(0) from the permanently zero slot 6 and a
         // zero-filled p, so that p' = r on the ghost planes as well
@@ -1386,8 +1481,8 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
         cg.r_in = s->r;
         cg.xv = (x_pending && i > 0) ? s->x - own_lo : nullptr;
         cg.p_out = pb[pc ^ 1];
-        rc = kb_launch_march<1, 1, false>(&ext, ws, geo, pb[pc], nullptr, 0, nullptr, nullptr,
-                                          nullptr, cg, pAp, st);
+        rc = parted ? kb_launch_march_cg<1, 1, true>(cfg[0], &ext, ws, geo[0], pb[pc], cg, pAp, st)
+                    : kb_launch_march_cg<1, 1, false>(cfg[0], &ext, ws, geo[0], pb[pc], cg, pAp, st);
         pc ^= 1;
       } else {
         rc = kb_spmv(s->A, ws, k, pb[pc], s->Ap, 0, nullptr, nullptr, 1, pb[pc], pAp, stream);
@@ -1397,8 +1492,10 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
         memset(&cg, 0, sizeof(cg));
         cg.own_lo = own_lo;
         cg.own_hi = own_hi;
-        cg.push_lo = parted ? s->r_push_lo : nullptr;
-        cg.push_hi = parted ? s->r_push_hi : nullptr;
+        cg.own_pl0 = own_lo / geo[1].P;
+        cg.own_pl1 = own_hi / geo[1].P;
+        cg.push_lo = (parted && !(g_part_dbg & 1)) ? s->r_push_lo : nullptr;
+        cg.push_hi = (parted && !(g_part_dbg & 1)) ? s->r_push_hi : nullptr;
         cg.rho_a = cur;
         cg.rho_b = pAp;
         cg.alpha_out = alpha;
@@ -1408,8 +1505,8 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
         cg.rec.hist = s->hist - (size_t)(i0 + 1) * k;
         cg.rec.stop_at = s->stop_at;
         cg.rec.rho_keep = nxt;
-        rc = kb_launch_march<2, 2, false>(&ext, ws, geo, pb[pc], nullptr, 0, nullptr, nullptr,
-                                          nullptr, cg, rr, st);
+        rc = parted ? kb_launch_march_cg<2, 2, true>(cfg[1], &ext, ws, geo[1], pb[pc], cg, rr, st)
+                    : kb_launch_march_cg<2, 2, false>(cfg[1], &ext, ws, geo[1], pb[pc], cg, rr, st);
       }
       if (ev) cudaEventRecord(ev[3 * (i - i0) + 2], st);
       x_pending = 1;
@@ -1431,6 +1528,7 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
   }
   ws->gate = saved_gate;
   ws->gate_tag = saved_tag;
+  ws->collective = saved_coll;
   return rc;
 }
 
@@ -1447,9 +1545,11 @@ int kb_cg_run_timed(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x
                     void* stream, float* ms, float* total_ms) {
   KB_REQUIRE(ms != nullptr && total_ms != nullptr && n_iters >= 1 && n_iters <= 100000,
              "bad argument");
-  KbMarch geo;
+  KbMarch geo[2];
+  int cfg[2];
   kb_csr_s ext;
-  const bool fused = s != nullptr && s->A != nullptr && kb_cg_fusable(s, &geo, &ext);
+  const bool fused = s != nullptr && s->A != nullptr && ws != nullptr &&
+                     kb_cg_fusable(s, &ext, ws->num_sms, cfg, geo);
   const int ne = 3 * n_iters + 1;
   cudaEvent_t* ev = new (std::nothrow) cudaEvent_t[ne];
   if (!ev) return kb_fail(KB_ECUDA, "kb_cg_run_timed: out of memory");

@@ -40,11 +40,11 @@ int kb_fail(int code, const char* fmt, ...);
 // One-shot all-reduce over NVLink peer memory, fused into the last block of a
 // reduction kernel ("custom one-shot P2P allreduce fused into the
 // reduction kernel's last-block epilogue").  Every rank owns a mailbox
-//   mbox[parity][src_rank][stride]   (u64 flag, then k doubles)
+//   mbox[parity][src_rank][stride]   (k entries of 16 bytes: value + sequence flag, kb_ll_store)
 // mapped into every peer with CUDA IPC.  A collective with sequence number q
 // writes this rank's k partial sums into slot [q & 1][rank] of EVERY rank's
-// mailbox (plain stores over NVLink), fences, stores the flag q, then waits until
-// all `size` flags of its own mailbox show q and adds the contributions in rank
+// mailbox (one self-validating 16-byte NVLink store per value and destination), then waits
+// until all `size` entries of its own mailbox carry q and adds the contributions in rank
 // order (deterministic, identical on all ranks).  q is a device-resident counter,
 // so launches skipped by the gate do not consume a number and parities alternate:
 // a rank can only overwrite slot [q & 1] after every peer has finished reading
@@ -106,7 +106,9 @@ __device__ __forceinline__ volatile unsigned long long* kb_halo_u64(unsigned cha
 #define KB_HALO_PUSH_TICKET 1048  // u32 arrival counter of the push kernel (it may run on a side
                                   // stream next to a reduction that uses the workspace ticket)
 
-// spin until *p >= want (3 s budget, then raise the error flag and go on)
+// spin until *p >= want (3 s budget, then raise the STICKY error word and go on: the callers
+// test it, stop pushing and poison their results with NaN; hosts turn it into an exception at
+// the next batch boundary, Comm.check_p2p / DistCsrMatrix.check_p2p)
 __device__ __forceinline__ void kb_halo_wait(volatile unsigned long long* p,
                                              unsigned long long want, unsigned char* own) {
   const long long t0 = clock64();
@@ -227,41 +229,67 @@ __device__ __forceinline__ double kb_block_colsum(double acc, int k, double* sm)
   return tot;
 }
 
+// One 16-byte store carries a double and its sequence flag twice: {lo, flag, hi, flag}.  Each
+// 8-byte half validates itself (the scheme of NCCL's LL protocol), so data and "it has arrived"
+// travel in ONE NVLink store -- no fence and no second round trip for a separate flag.
+__device__ __forceinline__ void kb_ll_store(double* dst16, double v, unsigned flag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst16), "r"(lo), "r"(flag),
+               "r"(hi), "r"(flag)
+               : "memory");
+}
+__device__ __forceinline__ bool kb_ll_load(const double* src16, unsigned flag, double* v) {
+  unsigned a, b, c, d;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+               : "l"(src16)
+               : "memory");
+  if (b != flag || d != flag) return false;
+  *v = __hiloint2double((int)c, (int)a);
+  return true;
+}
+
 // All-reduce of k values held by threads t < k of ONE block (see KbComm).  Must be
 // called by every thread of that block.  Returns the global sum in threads t < k.
+// Mailbox entry (parity, source rank, value t) = 16 bytes written by kb_ll_store; the flag is the
+// low word of the collective's sequence number (it differs from what the entry held two
+// collectives earlier).  The system fences make the all-reduce a release / acquire point: what
+// the blocks of this grid stored to peer memory (and fenced) before arriving is visible to a
+// peer once that peer's all-reduce returns.
 __device__ __forceinline__ double kb_p2p_allreduce(double v, int k, const KbComm& cm) {
   __shared__ unsigned long long s_seq;
   const int t = threadIdx.x;
   if (t == 0) s_seq = ++(*cm.counter);
+  __threadfence_system();
   __syncthreads();
   const unsigned long long q = s_seq;
-  const size_t slot = ((size_t)(q & 1ull) * cm.size + cm.rank) * cm.stride;
-  if (t < k)
-    for (int p = 0; p < cm.size; ++p) cm.peers[p][slot + 1 + t] = v;
-  __threadfence_system();
-  __syncthreads();
-  if (t < cm.size)  // one thread per destination publishes the flag
-    *reinterpret_cast<volatile unsigned long long*>(cm.peers[t] + slot) = q;
-  // wait for every source's flag in the own mailbox
-  const double* mine = cm.peers[cm.rank];
-  if (t < cm.size) {
-    const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(
-        mine + ((size_t)(q & 1ull) * cm.size + t) * cm.stride);
-    const long long t0 = clock64();
-    while (*f != q) {
-      if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer is gone; fail loudly, do not hang
-        *cm.error = 1;
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  __threadfence_system();
+  const unsigned flag = (unsigned)q;
+  const size_t par = (size_t)(q & 1ull) * cm.size;
   double tot = 0.0;
-  if (t < k)
-    for (int p = 0; p < cm.size; ++p)
-      tot += *reinterpret_cast<const volatile double*>(
-          mine + ((size_t)(q & 1ull) * cm.size + p) * cm.stride + 1 + t);
+  if (t < k) {
+    const size_t slot = (par + cm.rank) * cm.stride + 2 * (size_t)t;
+    for (int i = 1; i <= cm.size; ++i) {  // own mailbox last
+      const int p = (cm.rank + i) % cm.size;
+      kb_ll_store(cm.peers[p] + slot, v, flag);
+    }
+    const double* mine = cm.peers[cm.rank];
+    const long long t0 = clock64();
+    bool dead = false;
+    for (int p = 0; p < cm.size; ++p) {  // rank order: identical bits on every rank
+      const double* e = mine + (par + p) * cm.stride + 2 * (size_t)t;
+      double x = 0.0;
+      while (!dead && !kb_ll_load(e, flag, &x)) {
+        if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer is gone; fail loudly, do not hang
+          *cm.error = 1;
+          dead = true;
+        }
+      }
+      tot += x;
+    }
+    if (dead) tot = nan("");
+  }
+  __threadfence_system();
+  __syncthreads();
   return tot;
 }
 

@@ -54,9 +54,29 @@ struct KbMarchCg {
   // new r of its first / last own plane into the neighbours' ghost planes (NVLink peer stores);
   // the all-reduce that ends the kernel is what tells the neighbours that they have landed.
   int own_lo, own_hi;
+  int own_pl0, own_pl1;    // the same range in planes: own_lo / P, own_hi / P
   double* push_lo;         // KIND 2: the lower neighbour's upper ghost plane of r (peer-mapped) or null
   double* push_hi;         // KIND 2: the upper neighbour's lower ghost plane of r or null
 };
+
+// mbarrier operations on a precomputed shared-window address (no generic -> shared conversion in
+// the marching loop)
+__device__ __forceinline__ void kb_mbar_arrive_u32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void kb_mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "KB_WAITU_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra KB_DONEU_%=;\n"
+      "bra KB_WAITU_%=;\n"
+      "KB_DONEU_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
 
 __device__ __forceinline__ void kb_st_f64_shared(uint32_t addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
@@ -69,7 +89,7 @@ __device__ __forceinline__ double kb_ld_f64_shared(uint32_t addr) {
 
 // row sums of NQ (1 or 2) rows: q = Q0, Q0 + 1 of this thread.  a[d]: shared address of
 // diagonal d for row q = 0 in the current ring position.
-template <int ND, int Q0, int NQ>
+template <int ND, int Q0, int NQ, int CT = 256>
 __device__ __forceinline__ void kb_march_rows(const uint32_t (&a)[ND], const unsigned* m,
                                               const KbConstVals& cv, double* sum, double* ctr) {
   constexpr unsigned full = (1u << ND) - 1u;
@@ -77,8 +97,12 @@ __device__ __forceinline__ void kb_march_rows(const uint32_t (&a)[ND], const uns
   if constexpr (NQ == 2) allfull = allfull && m[Q0 + 1] == full;
   if (__all_sync(0xffffffffu, allfull)) {
     double xa[ND], xb[ND];
-    kb_st2_load<ND, Q0>(a, xa);
-    if constexpr (NQ == 2) kb_st2_load<ND, Q0 + 1>(a, xb);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) xa[d] = kb_lds_f64<Q0 * CT * 8>(a[d]);
+    if constexpr (NQ == 2) {
+#pragma unroll
+      for (int d = 0; d < ND; ++d) xb[d] = kb_lds_f64<(Q0 + 1) * CT * 8>(a[d]);
+    }
     sum[Q0] = kb_st2_sum<ND>(xa, cv);
     ctr[Q0] = xa[ND / 2];
     if constexpr (NQ == 2) {
@@ -88,17 +112,17 @@ __device__ __forceinline__ void kb_march_rows(const uint32_t (&a)[ND], const uns
   } else {  // rows next to a boundary: the absent diagonals are skipped, never loaded
     // the middle entry is the row's own x (dot operand when w aliases x): always inside the window
     double s0 = 0.0, s1 = 0.0, c1 = 0.0;
-    const double c0 = kb_lds_f64<Q0 * 2048>(a[ND / 2]);
-    if constexpr (NQ == 2) c1 = kb_lds_f64<(Q0 + 1) * 2048>(a[ND / 2]);
+    const double c0 = kb_lds_f64<Q0 * CT * 8>(a[ND / 2]);
+    if constexpr (NQ == 2) c1 = kb_lds_f64<(Q0 + 1) * CT * 8>(a[ND / 2]);
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       if ((m[Q0] >> d) & 1u) {
-        const double v = kb_lds_f64<Q0 * 2048>(a[d]);
+        const double v = kb_lds_f64<Q0 * CT * 8>(a[d]);
         s0 = __dadd_rn(s0, __dmul_rn(cv.c[d], v));
       }
       if constexpr (NQ == 2) {
         if ((m[Q0 + 1] >> d) & 1u) {
-          const double v = kb_lds_f64<(Q0 + 1) * 2048>(a[d]);
+          const double v = kb_lds_f64<(Q0 + 1) * CT * 8>(a[d]);
           s1 = __dadd_rn(s1, __dmul_rn(cv.c[d], v));
         }
       }
@@ -114,17 +138,24 @@ __device__ __forceinline__ void kb_march_rows(const uint32_t (&a)[ND], const uns
 
 // KIND 0: y = epilogue(A x) (+ dot), 1: CG p/x update + <p, A p>, 2: CG r update + <r, r> + record
 // WX (KIND 0): the dot operand w is x itself and the middle diagonal is the main diagonal.
-template <int ND, int RPT, int NS, int MINB, int KIND, int DOT, bool WX>
-__global__ void __launch_bounds__(256 + 32, MINB)
+// PART (KIND 1 / 2): row-partitioned, ghost-extended row space (see KbMarchCg); false compiles the
+// ownership tests and the peer stores out.
+// CT: consumer threads (a multiple of 32; + one producer warp).  A tile is CT * RPT rows wide, so
+// the number of column tiles of a plane can be matched to the CTA slots of the machine
+// (512 x 512 planes: 256 tiles of 1024 rows, 293 of 896, 342 of 768).
+template <int ND, int RPT, int NS, int MINB, int KIND, int DOT, bool WX, bool PART = false,
+          int CT = 256>
+__global__ void __launch_bounds__(CT + 32, MINB)
 kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __restrict__ masks,
                         KbPattern pat, KbConstVals cv, const double* __restrict__ x,
                         double* __restrict__ y, int mode, const double* __restrict__ z,
                         const double* __restrict__ coef, const double* __restrict__ w,
                         KbMarchCg cg, int l2pol, double* __restrict__ out, KbRed rd) {
-  static_assert(RPT == 2 || RPT == 4, "rows per thread");
+  static_assert(RPT >= 2 && RPT <= 4, "rows per thread");
+  static_assert(CT % 32 == 0 && CT >= 128 && CT <= 256, "consumer threads");
   static_assert(NS >= 4, "ring: previous, current, next plane + one in flight");
   if (kb_gated(rd)) return;
-  constexpr int TR = 256 * RPT;
+  constexpr int TR = CT * RPT;
   constexpr int NR = KIND == 1 ? 2 : 0;  // staging windows of r (KIND 1)
   extern __shared__ __align__(128) unsigned char kb_dyn_smem[];
   double* const s_win = reinterpret_cast<double*>(kb_dyn_smem);
@@ -132,25 +163,25 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
   uint64_t* const s_full = reinterpret_cast<uint64_t*>(s_rwin + (size_t)NR * g.wlen);
   uint64_t* const s_empty = s_full + NS;
   uint64_t* const s_rempty = s_empty + NS;  // [2], KIND 1
-  __shared__ double red_sm[256 + 32];
+  __shared__ double red_sm[CT + 32];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       kb_mbar_init(&s_full[s], 1);
-      kb_mbar_init(&s_empty[s], 8);
+      kb_mbar_init(&s_empty[s], CT / 32);
     }
     if (KIND == 1) {
-      kb_mbar_init(&s_rempty[0], 8);
-      kb_mbar_init(&s_rempty[1], 8);
+      kb_mbar_init(&s_rempty[0], CT / 32);
+      kb_mbar_init(&s_rempty[1], CT / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   double acc = 0.0;
-  if (warp == 8) {
+  if (warp == CT / 32) {
     // ------------------------------------------------ producer: one window per plane ---
     if ((tid & 31) == 0) {
       const uint64_t pol = l2pol == 2 ? kb_policy_evict_first() : kb_policy_evict_last();
@@ -208,6 +239,13 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
       alpha = cg.rho_a[0] / kb_nz(cg.rho_b[0]);
       if (cg.alpha_out != nullptr && blockIdx.x == 0 && tid == 0) cg.alpha_out[0] = alpha;
     }
+    // Row bookkeeping is per pass, not per row (ncu: it was most of the instructions): the rows
+    // of a thread are pos0 + q * 256 of ONE plane, the first nq of them exist (n_rows is a whole
+    // number of planes: kb_march_geom), whether a plane is computed / written / owned is uniform
+    // over the CTA, and row indices are 32-bit with q * 256 folded into the address offsets.
+    const uint32_t fullb = kb_smem_u32(s_full), emptyb = kb_smem_u32(s_empty);
+    const uint32_t rempb = kb_smem_u32(s_rempty);
+    const bool have_x = KIND == 1 && cg.xv != nullptr;
     unsigned cnt = 0;
     for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
       const int c = item % g.ncol;
@@ -215,6 +253,7 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
       const int j1 = min(j0 + g.ch, g.nplanes);
       const int nload = j1 - j0 + 2;
       const int pos0 = c * TR + tid;  // in-plane position of row q = 0
+      const int nq = min(RPT, max(0, (g.P - pos0 + CT - 1) / CT));  // rows of this thread in a plane
       // Operands that come from global memory (masks, z / r, w, x of the own rows) are requested
       // one pass ahead: the windows are usually there when a pass starts, so a load issued at
       // the top of the pass that needs it would be waited for in full (ncu: the top stall).
@@ -225,50 +264,43 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
         mn[q] = 0u;
         zn[q] = wn[q] = xn[q] = 0.0;
       }
-      for (int l = 0; l < nload; ++l, ++cnt) {
+      int rowc = (j0 - 2) * g.P + pos0;  // row q = 0 of plane jc (meaningful from l = 2 on)
+      for (int l = 0; l < nload; ++l, ++cnt, rowc += g.P) {
         const int slot = (int)(cnt % NS);
         const int jc = j0 + l - 2;  // plane whose rows are computed in this pass (l >= 2)
+        // uniform flags of this pass; PART: only planes [own_pl0, own_pl1) are this rank's
+        bool comp = l >= 2;                    // rows of plane jc are computed now
+        const bool pre = l >= 1 && l + 1 < nload;  // rows of plane jc + 1 are computed next
+        bool pre_own = pre;
+        const bool arr = KIND == 1 && l >= 1 && l <= nload - 2;  // own rows of the arriving plane
+        bool arr_x = arr && have_x;                              // jc + 1 are written now
+        bool pre_x = have_x && l + 1 <= nload - 2;               // x of plane jc + 2, for the next pass
+        if (PART) {
+          comp = comp && jc >= cg.own_pl0 && jc < cg.own_pl1;
+          pre_own = pre_own && jc + 1 >= cg.own_pl0 && jc + 1 < cg.own_pl1;
+          arr_x = arr_x && jc + 1 >= cg.own_pl0 && jc + 1 < cg.own_pl1;
+          pre_x = pre_x && jc + 2 >= cg.own_pl0 && jc + 2 < cg.own_pl1;
+        }
         unsigned m[RPT];
         double zv[RPT], wv[RPT], xo[RPT];
-        int row[RPT], trow[RPT];
-        bool xrow[RPT];
+        const int rown = rowc + g.P;  // plane jc + 1: computed next (KIND 0 / 2), arriving now (KIND 1)
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
-          const int pos = pos0 + q * 256;
-          const long long r64 = (long long)jc * g.P + pos;
-          bool ok = l >= 2 && pos < g.P && r64 < (long long)n_rows;
-          if (KIND != 0) ok = ok && r64 >= (long long)cg.own_lo && r64 < (long long)cg.own_hi;
-          row[q] = ok ? (int)r64 : -1;
-          xrow[q] = false;
           m[q] = mn[q];
           zv[q] = zn[q];
           wv[q] = wn[q];
           xo[q] = xn[q];
-          // rows computed in the next pass (plane jc + 1)
-          const long long n64 = r64 + g.P;
-          const bool nok = l >= 1 && l + 1 < nload && pos < g.P && n64 < (long long)n_rows;
-          mn[q] = nok ? (unsigned)masks[n64] : 0u;
+          mn[q] = 0u;
           zn[q] = wn[q] = 0.0;
-          if (nok) {
-            if (KIND == 0 && mode != 0) zn[q] = z[n64];
-            if (KIND == 0 && DOT == 1 && !WX) wn[q] = w[n64];
-            if (KIND == 2 && n64 >= (long long)cg.own_lo && n64 < (long long)cg.own_hi)
-              zn[q] = cg.r[n64];
+          if (pre && q < nq) {
+            mn[q] = (unsigned)masks[rown + q * CT];
+            if (KIND == 0 && mode != 0) zn[q] = z[rown + q * CT];
+            if (KIND == 0 && DOT == 1 && !WX) wn[q] = w[rown + q * CT];
+            if (KIND == 2 && pre_own) zn[q] = cg.r[rown + q * CT];
           }
-          if (KIND == 1) {
-            // own rows of the arriving plane j0 - 1 + l (inside the item for 1 <= l <= nload - 2)
-            const long long t64 = r64 + g.P;
-            const bool tok = l >= 1 && l <= nload - 2 && pos < g.P && t64 < (long long)n_rows;
-            trow[q] = tok ? (int)t64 : -1;
-            xrow[q] = tok && t64 >= (long long)cg.own_lo && t64 < (long long)cg.own_hi;
-            // x of the own rows of the plane arriving in the next pass
-            const long long u64 = t64 + g.P;
-            const bool uok = l + 1 <= nload - 2 && pos < g.P && u64 >= (long long)cg.own_lo &&
-                             u64 < (long long)cg.own_hi;
-            xn[q] = (uok && cg.xv != nullptr) ? cg.xv[u64] : 0.0;
-          }
+          if (KIND == 1) xn[q] = (pre_x && q < nq) ? cg.xv[rown + g.P + q * CT] : 0.0;
         }
-        kb_mbar_wait(&s_full[slot], (cnt / NS) & 1u);
+        kb_mbar_wait_u32(fullb + (uint32_t)slot * 8u, (cnt / NS) & 1u);
         if (KIND == 1) {
           // p <- r + omega p on the whole arriving window (halo included), in place; the own
           // rows also go to global memory together with x += alpha p_old  (cg.py:178,196)
@@ -279,94 +311,103 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
             double po[RPT], ro[RPT];
 #pragma unroll
             for (int q = 0; q < RPT; ++q) {
-              po[q] = kb_ld_f64_shared(pw + own + (uint32_t)q * 2048u);
-              ro[q] = kb_ld_f64_shared(rw + own + (uint32_t)q * 2048u);
+              po[q] = kb_ld_f64_shared(pw + own + (uint32_t)(q * CT * 8));
+              ro[q] = kb_ld_f64_shared(rw + own + (uint32_t)(q * CT * 8));
             }
 #pragma unroll
             for (int q = 0; q < RPT; ++q) {
               const double pn = kb_mul_add(omega, po[q], ro[q]);
-              kb_st_f64_shared(pw + own + (uint32_t)q * 2048u, pn);
-              if (trow[q] >= 0) {
-                if (cg.xv != nullptr && xrow[q])
-                  __stcs(&cg.xv[trow[q]], kb_mul_add(alpha, po[q], xo[q]));
-                __stcs(&cg.p_out[trow[q]], pn);
+              kb_st_f64_shared(pw + own + (uint32_t)(q * CT * 8), pn);
+              if (arr && q < nq) {
+                if (arr_x) __stcs(&cg.xv[rown + q * CT], kb_mul_add(alpha, po[q], xo[q]));
+                __stcs(&cg.p_out[rown + q * CT], pn);
               }
             }
           }
           // halo entries on both sides: LP / 256 per side and thread, two at a time
-          const int nh = g.LP >> 8;
+          const int nh = g.LP / CT;  // LP is a multiple of CT (kb_march_geom)
           for (int side = 0; side < 2; ++side) {
-            const uint32_t hb = side == 0 ? 0u : own + (uint32_t)RPT * 2048u;
+            const uint32_t hb = side == 0 ? 0u : own + (uint32_t)(RPT * CT * 8);
             int u = 0;
             for (; u + 1 < nh; u += 2) {
-              const uint32_t o0 = hb + (uint32_t)u * 2048u, o1 = o0 + 2048u;
+              const uint32_t o0 = hb + (uint32_t)u * (CT * 8u), o1 = o0 + CT * 8u;
               const double p0 = kb_ld_f64_shared(pw + o0), p1 = kb_ld_f64_shared(pw + o1);
               const double r0 = kb_ld_f64_shared(rw + o0), r1 = kb_ld_f64_shared(rw + o1);
               kb_st_f64_shared(pw + o0, kb_mul_add(omega, p0, r0));
               kb_st_f64_shared(pw + o1, kb_mul_add(omega, p1, r1));
             }
             if (u < nh) {
-              const uint32_t o0 = hb + (uint32_t)u * 2048u;
+              const uint32_t o0 = hb + (uint32_t)u * (CT * 8u);
               const double p0 = kb_ld_f64_shared(pw + o0);
               const double r0 = kb_ld_f64_shared(rw + o0);
               kb_st_f64_shared(pw + o0, kb_mul_add(omega, p0, r0));
             }
           }
           __syncwarp();
-          if ((tid & 31) == 0) kb_mbar_arrive(&s_rempty[cnt & 1u]);
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // the window is complete for everyone
+          if ((tid & 31) == 0) kb_mbar_arrive_u32(rempb + (cnt & 1u) * 8u);
+          asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");  // the window is complete for everyone
         }
         if (l >= 2) {
-          const uint32_t wprev = sbase + (uint32_t)((cnt - 2u) % NS) * wbytes;
-          const uint32_t wcur = sbase + (uint32_t)((cnt - 1u) % NS) * wbytes;
-          const uint32_t wnext = sbase + (uint32_t)slot * wbytes;
-          uint32_t a[ND];
-          a[0] = wprev + od[0];
+          if (comp) {
+            const uint32_t wprev = sbase + (uint32_t)((cnt - 2u) % NS) * wbytes;
+            const uint32_t wcur = sbase + (uint32_t)((cnt - 1u) % NS) * wbytes;
+            const uint32_t wnext = sbase + (uint32_t)slot * wbytes;
+            uint32_t a[ND];
+            a[0] = wprev + od[0];
 #pragma unroll
-          for (int d = 1; d < ND - 1; ++d) a[d] = wcur + od[d];
-          a[ND - 1] = wnext + od[ND - 1];
-          double sum[RPT], ctr[RPT];
-          kb_march_rows<ND, 0, 2>(a, m, cv, sum, ctr);
-          if constexpr (RPT == 4) kb_march_rows<ND, 2, 2>(a, m, cv, sum, ctr);
+            for (int d = 1; d < ND - 1; ++d) a[d] = wcur + od[d];
+            a[ND - 1] = wnext + od[ND - 1];
+            double sum[RPT], ctr[RPT];
+            kb_march_rows<ND, 0, 2, CT>(a, m, cv, sum, ctr);
+            if constexpr (RPT == 4) kb_march_rows<ND, 2, 2, CT>(a, m, cv, sum, ctr);
+            if constexpr (RPT == 3) kb_march_rows<ND, 2, 1, CT>(a, m, cv, sum, ctr);
+            // PART, KIND 2: the first / last own plane also goes to the neighbours' ghost planes
+            double* plo = nullptr;
+            double* phi = nullptr;
+            if (PART && KIND == 2) {
+              if (cg.push_lo != nullptr && jc == cg.own_pl0) plo = cg.push_lo + pos0;
+              if (cg.push_hi != nullptr && jc == cg.own_pl1 - 1) phi = cg.push_hi + pos0;
+            }
 #pragma unroll
-          for (int q = 0; q < RPT; ++q) {
-            if (row[q] >= 0) {
-              if (KIND == 0) {
-                double yv = sum[q];
-                if (mode == 1) yv = kb_mul_sub(cf, zv[q], sum[q]);
-                if (mode == 2) yv = __dsub_rn(zv[q], sum[q]);
-                __stcs(&y[row[q]], yv);
-                if (DOT == 1) acc = fma(WX ? ctr[q] : wv[q], yv, acc);
-                if (DOT == 2) acc = fma(yv, yv, acc);
-              } else if (KIND == 1) {
-                acc = fma(ctr[q], sum[q], acc);  // <p, A p>
-              } else {
-                const double rn = kb_mul_sub(alpha, sum[q], zv[q]);  // r - alpha (A p)
-                cg.r[row[q]] = rn;
-                if (cg.push_lo != nullptr && row[q] < cg.own_lo + g.P)
-                  cg.push_lo[row[q] - cg.own_lo] = rn;
-                if (cg.push_hi != nullptr && row[q] >= cg.own_hi - g.P)
-                  cg.push_hi[row[q] - (cg.own_hi - g.P)] = rn;
-                acc = fma(rn, rn, acc);
+            for (int q = 0; q < RPT; ++q) {
+              if (q < nq) {
+                if (KIND == 0) {
+                  double yv = sum[q];
+                  if (mode == 1) yv = kb_mul_sub(cf, zv[q], sum[q]);
+                  if (mode == 2) yv = __dsub_rn(zv[q], sum[q]);
+                  __stcs(&y[rowc + q * CT], yv);
+                  if (DOT == 1) acc = fma(WX ? ctr[q] : wv[q], yv, acc);
+                  if (DOT == 2) acc = fma(yv, yv, acc);
+                } else if (KIND == 1) {
+                  acc = fma(ctr[q], sum[q], acc);  // <p, A p>
+                } else {
+                  const double rn = kb_mul_sub(alpha, sum[q], zv[q]);  // r - alpha (A p)
+                  cg.r[rowc + q * CT] = rn;
+                  if (PART) {
+                    if (plo != nullptr) plo[q * CT] = rn;
+                    if (phi != nullptr) phi[q * CT] = rn;
+                  }
+                  acc = fma(rn, rn, acc);
+                }
               }
             }
           }
           __syncwarp();
-          if ((tid & 31) == 0) kb_mbar_arrive(&s_empty[(cnt - 2u) % NS]);
+          if ((tid & 31) == 0) kb_mbar_arrive_u32(emptyb + ((cnt - 2u) % NS) * 8u);
         }
       }
       // the last two windows of the item are not needed by a later pass
       __syncwarp();
       if ((tid & 31) == 0) {
-        kb_mbar_arrive(&s_empty[(cnt - 2u) % NS]);
-        kb_mbar_arrive(&s_empty[(cnt - 1u) % NS]);
+        kb_mbar_arrive_u32(emptyb + ((cnt - 2u) % NS) * 8u);
+        kb_mbar_arrive_u32(emptyb + ((cnt - 1u) % NS) * 8u);
       }
     }
   }
   if (KIND == 0 && DOT == 0) return;
   // peer stores of r must be visible system-wide before this block's arrival is counted: the
   // finishing block's all-reduce flag is the neighbours' "ghost planes landed" signal
-  if (KIND == 2 && (cg.push_lo != nullptr || cg.push_hi != nullptr)) __threadfence_system();
+  if (PART && KIND == 2 && (cg.push_lo != nullptr || cg.push_hi != nullptr)) __threadfence_system();
   const bool last = kb_grid_colsum(acc, 1, rd, out, red_sm);
   if (KIND == 2 && last && cg.rec.step >= 0) {  // cg.py:156,214-217 in the finishing block
     __syncthreads();

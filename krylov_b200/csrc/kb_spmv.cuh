@@ -1316,6 +1316,7 @@ kb_spmv_halo_add_kernel(int64_t n_brows, int k, double sign, const int32_t* __re
   __shared__ double sm[KB_BLOCK];
   unsigned char* own = nullptr;
   unsigned long long q = 0;
+  bool dead = false;  // a source never delivered: the receive area is stale -> poison y and the dot
   if (hd.peers != nullptr) {
     // peer-memory halo: the entries were pushed into this rank's data area; wait for the
     // flag of every source of product q (the push of this product already counted it)
@@ -1325,6 +1326,7 @@ kb_spmv_halo_add_kernel(int64_t n_brows, int k, double sign, const int32_t* __re
       kb_halo_wait(kb_halo_u64(own, KB_HALO_FLAGS + 8 * (size_t)srcs[threadIdx.x]), q, own);
     __syncthreads();
     __threadfence_system();
+    dead = *reinterpret_cast<volatile int*>(own + KB_HALO_ERROR) != 0;  // sticky
     xh = reinterpret_cast<const double*>(own + KB_HALO_DATA);
   }
   const int c = threadIdx.x % k;
@@ -1338,6 +1340,7 @@ kb_spmv_halo_add_kernel(int64_t n_brows, int k, double sign, const int32_t* __re
     for (int j = lo; j < hi; ++j)
       h = __dadd_rn(h, __dmul_rn(hval[j], __ldcv(xh + (size_t)hcol[j] * k + c)));
     h *= sign;
+    if (dead) h = nan("");
     const size_t idx = (size_t)rows[i] * k + c;
     y[idx] = __dadd_rn(y[idx], h);
     if (DOT == 1) acc = fma(w[idx], h, acc);

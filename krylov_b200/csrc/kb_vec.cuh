@@ -612,7 +612,11 @@ kb_halo_push_kernel(int k, int n_seg, const int64_t* __restrict__ segs, int64_t 
   if ((int)threadIdx.x < n_seg)
     kb_halo_wait(kb_halo_u64(own, KB_HALO_ACKS + 8 * (size_t)segs[4 * threadIdx.x]), q - 1ull, own);
   __syncthreads();
-  const int64_t total = n_total * k;
+  // A destination that never acknowledged (sticky error word) may still be reading its buffer:
+  // nothing is pushed and no flag is raised any more -- the destinations time out in turn and
+  // poison their products with NaN, so the failure surfaces on every rank.
+  const bool dead = *reinterpret_cast<volatile int*>(own + KB_HALO_ERROR) != 0;
+  const int64_t total = dead ? 0 : n_total * k;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int64_t i = e / k;
@@ -633,7 +637,7 @@ kb_halo_push_kernel(int k, int n_seg, const int64_t* __restrict__ segs, int64_t 
   __syncthreads();
   if (s_last) {
     __threadfence_system();
-    if ((int)threadIdx.x < n_seg)
+    if ((int)threadIdx.x < n_seg && !dead)
       *kb_halo_u64(hd.peers[segs[4 * threadIdx.x]], KB_HALO_FLAGS + 8 * (size_t)hd.rank) = q;
     if (threadIdx.x == 0) {
       *kb_halo_u64(own, KB_HALO_COUNTER) = q;

@@ -27,6 +27,7 @@ from .operators import Identity, Info, Problem
 
 INT_MAX = 2**31 - 1
 _BATCH_MIN, _BATCH_MAX = 4, 64
+_BASIS_CHUNK = 64  # Arnoldi vectors allocated up front; doubled on demand
 _INVARIANT_MSG = "Krylov subspace was found to be invariant in the previous iteration."
 
 
@@ -81,6 +82,13 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
         assert ortho == "householder"
         assert inner is None
         assert M_is_identity
+        if prob.comm is not None:
+            # reflector j pivots on GLOBAL row j (arnoldi.py:75-96, householder.py:26-62): the
+            # device kernels index rank-local rows, so a row-partitioned matrix would silently
+            # pivot on the wrong entries -- refuse instead
+            raise NotImplementedError(
+                'gmres(ortho="householder") is single-GPU; on a row-partitioned matrix use '
+                'ortho="mgs2" (or "cgs2"), which reach the same orthogonality')
         nre = 1
         householder = True
     # everything device-resident <=> default inner product (no host callable in the loop)
@@ -102,15 +110,30 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
         callback(prob.to_user(x0), prob.to_user(r0))
 
     m = maxiter
-    # Arnoldi bases: V (and P = M^-1-dual basis when M is given; arnoldi.py:131-150)
-    Vbuf = torch.empty((m + 1, n, k), dtype=torch.float64, device=dev)
-    Pbuf = Vbuf if M is None else torch.empty((m + 1, n, k), dtype=torch.float64, device=dev)
-    R = torch.zeros((m + 1, max(m, 1), k), dtype=torch.float64, device=dev)
-    Gc = torch.zeros((max(m, 1), k), dtype=torch.float64, device=dev)
-    Gs = torch.zeros((max(m, 1), k), dtype=torch.float64, device=dev)
-    y = torch.zeros((m + 1, k), dtype=torch.float64, device=dev)
-    yy = torch.zeros((m + 1, k), dtype=torch.float64, device=dev)
-    dots = torch.zeros((nre * (m + 1) + 2, k), dtype=torch.float64, device=dev)
+    # Arnoldi bases V (and P = M^-1-dual basis when M is given; arnoldi.py:131-150), Hessenberg
+    # factor R, rotations and projected right-hand side.  maxiter defaults to n like the
+    # reference's (gmres.py:127), but the reference grows V as a Python list: allocate for
+    # _BASIS_CHUNK steps and grow geometrically between batches (the loop synchronises there),
+    # so that a default-argument call on a large system costs what its iteration count needs.
+    cap = max(1, min(m, _BASIS_CHUNK))
+
+    def _alloc(c):
+        try:
+            Vb = None if householder else torch.empty((c + 1, n, k), dtype=torch.float64, device=dev)
+            Pb = Vb if (M is None or householder) else torch.empty((c + 1, n, k),
+                                                                    dtype=torch.float64, device=dev)
+        except torch.OutOfMemoryError as e:
+            raise MemoryError(
+                f"gmres: no device memory for an Arnoldi basis of {c + 1} vectors of length {n} "
+                f"(x {k} columns); bound it with restart= or maxiter=") from e
+        return (Vb, Pb, torch.zeros((c + 1, c, k), dtype=torch.float64, device=dev),
+                torch.zeros((c, k), dtype=torch.float64, device=dev),
+                torch.zeros((c, k), dtype=torch.float64, device=dev),
+                torch.zeros((c + 1, k), dtype=torch.float64, device=dev),
+                torch.zeros((c + 1, k), dtype=torch.float64, device=dev),
+                torch.zeros((nre * (c + 1) + 2, k), dtype=torch.float64, device=dev))
+
+    Vbuf, Pbuf, R, Gc, Gs, y, yy, dots = _alloc(cap)
     ww = ops.slots(1)[0]
     hlast = ops.slots(1)[0]
     ctl = torch.tensor([INT_MAX, 0], dtype=torch.int32, device=dev)  # stop_at, flags
@@ -128,7 +151,7 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
         if M is not None:
             ops.div_scale(Vbuf[0], z0, nrm0_d)
 
-    st = GmresState(dots=ptr(dots), ww=ptr(ww), num_reorthos=nre, maxiter=max(m, 1), R=ptr(R),
+    st = GmresState(dots=ptr(dots), ww=ptr(ww), num_reorthos=nre, maxiter=cap, R=ptr(R),
                     Gc=ptr(Gc), Gs=ptr(Gs), y=ptr(y), hlast=ptr(hlast), crit=ptr(crit_d), hist=0,
                     stop_at=ctl.data_ptr(), flags=ctl.data_ptr() + 4, have_h=1 if householder else 0)
     stop_at = ctl[0:1]
@@ -139,7 +162,7 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
     def solution(kk):  # gmres.py:89-99
         if kk == 0:
             return x0.clone()
-        ops.gmres_solve_y(kk, max(m, 1), R, y, yy)
+        ops.gmres_solve_y(kk, cap, R, y, yy)
         out = torch.empty_like(x0)
         if householder:
             comb = torch.zeros_like(x0)
@@ -243,6 +266,20 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
         if c[1] & 1:
             raise ArgumentError(_INVARIANT_MSG)  # arnoldi.py:67-70, 168-171
         nb = min(batch, maxiter - kk)
+        if kk + nb > cap:  # grow the basis and the Hessenberg storage (contents kept)
+            new = min(m, max(2 * cap, kk + nb))
+            Vn, Pn, Rn, Gcn, Gsn, yn, yyn, dots = _alloc(new)
+            if Vn is not None:
+                Vn[: cap + 1].copy_(Vbuf)
+                if Pn is not Vn:
+                    Pn[: cap + 1].copy_(Pbuf)
+            Rn[: cap + 1, :cap].copy_(R)
+            Gcn[:cap].copy_(Gc)
+            Gsn[:cap].copy_(Gs)
+            yn[: cap + 1].copy_(y)
+            Vbuf, Pbuf, R, Gc, Gs, y, yy, cap = Vn, Pn, Rn, Gcn, Gsn, yn, yyn, new
+            st.dots, st.R, st.Gc, st.Gs, st.y, st.maxiter = (ptr(dots), ptr(R), ptr(Gc), ptr(Gs),
+                                                            ptr(y), cap)
         stop_at.fill_(INT_MAX)
         st.hist = hist.data_ptr() - (kk + 1) * k * 8
         for i in range(kk, kk + nb):
@@ -256,6 +293,7 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
             resn.append(rows[j].copy())
         kk += done
         xk = None
+        prob.check_peers()
         if callback is not None:
             xk = solution(kk)
             resn[-1] = _callback_resnorm(prob, callback, xk, resn[-1])

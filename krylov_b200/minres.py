@@ -177,6 +177,7 @@ def _minres_fused(prob, tol, atol, maxiter, callback, M=None, Ml=None, Mr=None):
             resn.append(rows[j].copy())
         kk += done
         xk = None
+        prob.check_peers()
         if callback is not None:
             xk = get_x()
             resn[-1] = _callback_resnorm(prob, callback, xk, resn[-1])

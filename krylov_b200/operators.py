@@ -176,6 +176,15 @@ class Problem:
         # row-partitioned matrix: b, x0 and every vector are this rank's rows
         self.comm = getattr(self.A_csr, "comm", None)
 
+    def check_peers(self):
+        """Row-partitioned problems: raise if a peer-memory exchange or all-reduce ever timed
+        out (the kernels poison their results with NaN and set a sticky error word; called at
+        every batch boundary of the solver loops)."""
+        if self.comm is not None:
+            chk = getattr(self.A_csr, "check_p2p", None) or getattr(self.comm, "check_p2p", None)
+            if chk is not None:
+                chk()
+
     def on_device(self):
         """Context manager: this problem's GPU is the current device."""
         return torch.cuda.device(self.device)

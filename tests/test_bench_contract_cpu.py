@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
-                        "--steps", "3", "--warmup", "1", "--size", "64", "--cpu-size", "24"],
+                        "--steps", "3", "--warmup", "1", "--size", "48"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
@@ -24,6 +24,26 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and d["value"] > 0
+    # the arm runs the workload it names (no extrapolation from a smaller grid) ...
+    assert d["config"]["extrapolated"] is False and "48^3" in d["config"]["sample"]
+    assert d["steps"] == 3
+
+
+def test_reference_arm_does_not_map_the_cuda_library():
+    """... and touches nothing of the product: krylov_b200 (whose import loads
+    libkrylov_b200.so) must not be imported by the CPU arm."""
+    code = (
+        "import sys, runpy\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--size', '24', '--steps', '2', '--warmup', '1']\n"
+        "try:\n"
+        f"    runpy.run_path({os.path.join(ROOT, 'bench.py')!r}, run_name='__main__')\n"
+        "except SystemExit:\n"
+        "    pass\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "print('MAPPED' if 'libkrylov_b200' in maps else 'CLEAN', 'krylov_b200' in sys.modules)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().splitlines()[-1] == "CLEAN False"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -634,3 +634,40 @@ def test_line_marching_spmm_default_selection():
         yes = ctypes.c_int(0)
         check(lib.kb_spmm_is_lines(Ad.handle, k, x.data_ptr(), ctypes.byref(yes)))
         assert bool(yes.value) == want, (n1, k)
+
+
+@pytest.mark.parametrize("shape", [(512, 512, 6), (200, 160, 9), (96, 64, 20)])
+def test_fused_cg_tile_shapes_agree(shape):
+    """The fused CG kernels in every tile shape (kb_tune 22 / 23: 1024-, 896-, 768-, 512-row
+    tiles, ring of 4 / 5) run the same arithmetic: identical row sums, dots that differ only in
+    the order of the block partials."""
+    import torch
+
+    from krylov_b200._lib import lib
+    from krylov_b200.cg import FusedCG
+    from krylov_b200.generate import device_stencil7
+
+    nx, ny, nz = shape
+    A = device_stencil7(nx, ny, nz)
+    n = A.shape[0]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    b = A.matvec_device(torch.randn(n, 1, generator=g, dtype=torch.float64, device="cuda"))
+    x0 = torch.zeros_like(b)
+    ref = None
+    try:
+        for c1, c2 in ((0, 0), (4, 5), (4, 4), (5, 5), (2, 2), (1, 1), (-1, -1)):
+            lib.kb_tune(22, c1)
+            lib.kb_tune(23, c2)
+            st = FusedCG(A, b, x0, 0.0, 0.0)
+            hist = np.asarray(st.run(8) + st.run(17)).reshape(-1)
+            x = st.current_x()
+            if not st.fused_march:
+                pytest.skip("grid too small for the marching kernels")
+            if ref is None:
+                ref = (hist, x)
+            else:
+                assert np.max(np.abs(hist - ref[0]) / ref[0]) <= 1e-12, (c1, c2)
+                assert float(torch.linalg.norm(x - ref[1]) / torch.linalg.norm(ref[1])) <= 1e-12
+    finally:
+        lib.kb_tune(22, -1)
+        lib.kb_tune(23, -1)

@@ -78,6 +78,14 @@ for name, coeffs, shift, fn in cases:
     }
     Ad.check_p2p()
     del Ad, Afull
+# Householder GMRES is refused on a row-partitioned matrix (pivot rows are global)
+Ad = dist_stencil7(N, N, N, st.convdiff_coeffs(), 0.0, comm)
+try:
+    kb.gmres(Ad, torch.ones(Ad.shape[0], dtype=torch.float64, device=dev), maxiter=5, ortho="householder")
+    raise SystemExit("householder on a DistCsrMatrix did not raise")
+except NotImplementedError:
+    pass
+del Ad
 # --- the two-launch fused CG path across ranks (ghost planes, peer pushes of r): fixed step
 #     counts, histories against the single-GPU fused path on the same global problem
 from krylov_b200.cg import FusedCG
