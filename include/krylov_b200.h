@@ -95,8 +95,14 @@ int kb_csr_destroy(kb_csr_t h);
  * 4 = "stencil": schedule 3 with constant diagonals (k == 1; <= 8 diagonals whose stored values
  * are all bitwise equal, tested exactly by kb_csr_create): the <= 8 coefficients travel as kernel
  * parameters and neither indices nor values are streamed.  Bit-identical to the other schedules.
+ * 5 = "merge" (k == 1): tiles of equal NONZERO count instead of rows, several lanes per row,
+ * long rows finished by a second small launch (csrc/kb_merge.cuh) -- what auto picks for long
+ * (mean > 32) or skewed (max > 8 (mean + 8)) rows.  Rows summed by one lane keep csr_matvec's
+ * left-to-right order; rows summed by several lanes follow a fixed tree (1e-13 |A||x| of SciPy,
+ * bitwise repeatable); kb_tune keys 25 (tile shape), 26 (CTAs per SM), 27 (tile -> CTA order).
  * Schedules 3 and 4 snapshot structure (3) and values (4) at creation: a caller that rewrites
- * colidx / vals in place must create a new handle. */
+ * colidx / vals in place must create a new handle; schedule 5 snapshots the row pointers at its first product.  One
+ * matrix handle must not run products on two streams at once (schedule 5 owns scratch). */
 int kb_csr_set_schedule(kb_csr_t h, int schedule);
 int kb_csr_get_info(kb_csr_t h, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
                     int* max_row_len, int* schedule);

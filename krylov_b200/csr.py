@@ -15,7 +15,8 @@ from . import _trace
 from ._lib import check, lib
 from .device import Ops, as_device_matrix, cur_stream, ptr, require_cuda
 
-_SCHEDULES = {"auto": 0, "rowwise": 1, "stream": 2, "pattern": 3, "stencil": 4}
+_SCHEDULES = {"auto": 0, "rowwise": 1, "stream": 2, "pattern": 3, "stencil": 4,
+              "merge": 5}
 _PAD = 4  # elements readable past nnz (TMA tiles are 4-aligned windows)
 
 
@@ -214,7 +215,8 @@ class CsrMatrix:
                                   C.byref(sc)))
         return {"n_rows": nr.value, "n_cols": nc.value, "nnz": nz.value,
                 "max_row_len": mx.value,
-                "schedule": {1: "rowwise", 2: "stream", 3: "pattern", 4: "stencil"}[sc.value]}
+                "schedule": {1: "rowwise", 2: "stream", 3: "pattern", 4: "stencil",
+                             5: "merge"}[sc.value]}
 
     def stencil_info(self):
         """Offset pattern detected at creation: ``{"nd", "offsets", "coeffs", "constv",

@@ -23,23 +23,6 @@ int kb_fail(int code, const char* fmt, ...) {
   return code;
 }
 
-struct kb_csr_s {
-  int64_t n_rows, n_cols, nnz;
-  const int32_t* rowptr;
-  const int32_t* colidx;
-  const double* vals;
-  int padded;
-  int max_row_len;
-  int schedule;  // 1 row-wise, 2 TMA stream, 3 offset-pattern compressed TMA stream,
-                 // 4 stencil (offset pattern + constant diagonals: no value stream either)
-  int forced;    // user override (0 = auto)
-  // offset-pattern compression (library-owned): one 16-bit mask per row
-  uint16_t* masks;
-  KbPattern pat;
-  int pattern_ok;
-  KbConstVals cv;  // one value per diagonal when constv
-  int constv;
-};
 
 
 static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
@@ -225,6 +208,9 @@ int kb_tune(int key, int value) {
     case 22: g_cg_cfg[0] = value; return KB_OK;
     case 23: g_cg_cfg[1] = value; return KB_OK;
     case 24: g_march_depth = value; return KB_OK;
+    case 25: g_merge_cfg = value; return KB_OK;  // tile shape of the merge kernel
+    case 26: g_merge_ctas = value; return KB_OK; // its CTAs per SM (0 = all that fit)
+    case 27: g_merge_order = value; return KB_OK; // tile -> CTA order (kb_merge.cuh)
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -385,16 +371,18 @@ int kb_allreduce(kb_ws_t ws, int k, double* slot, void* stream) {
 static void kb_csr_pick(kb_csr_s* h) {
   // Row-length statistics -> schedule (SURVEY.md 7 "short rows").  The stream
   // kernel gives one thread one row: right for stencil-like matrices whose
-  // rows are short and even.  Long or very skewed rows go to the row-wise
-  // kernel.
+  // rows are short and even.  Long or very skewed rows go to the merge kernel
+  // (tiles of equal nonzero count, several lanes per row); k > 1 and unpadded
+  // arrays to the row-wise kernel.
   const double mean = h->n_rows > 0 ? (double)h->nnz / (double)h->n_rows : 0.0;
+  const bool tma_ok = h->padded && h->n_rows >= 1 && h->n_rows < (1ll << 31) - 512;
   int sched = 1;
-  if (h->padded && h->n_rows >= 1 && h->n_rows < (1ll << 31) - 512 && mean <= 32.0 &&
-      h->max_row_len <= 8 * (mean + 8.0))
-    sched = 2;
+  if (tma_ok && h->nnz > 0) sched = 5;
+  if (tma_ok && mean <= 32.0 && h->max_row_len <= 8 * (mean + 8.0)) sched = 2;
   if (sched == 2 && h->pattern_ok) sched = h->constv ? 4 : 3;
   if (h->forced == 1) sched = 1;
   if (h->forced == 2 && h->padded) sched = 2;
+  if (h->forced == 5 && tma_ok && h->nnz > 0) sched = 5;
   if (h->forced == 3 && h->pattern_ok) sched = 3;
   if (h->forced == 4 && h->constv) sched = 4;
   h->schedule = sched;
@@ -443,6 +431,12 @@ int kb_csr_create(kb_csr_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz,
   h->pattern_ok = 0;
   h->constv = 0;
   h->pat.nd = 0;
+  h->merge_meta = nullptr;
+  h->carry = nullptr;
+  h->merge_fix = nullptr;
+  h->n_fix = 0;
+  h->merge_T = 0;
+  h->n_mtiles = 0;
   if (padded && n_rows > 0 && n_rows < (1ll << 31) - 1024 && n_cols < (1ll << 31) &&
       h->max_row_len >= 1 && h->max_row_len <= 16) {
     int rc = kb_detect_pattern(h, S(stream));
@@ -458,15 +452,19 @@ int kb_csr_create(kb_csr_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz,
   return KB_OK;
 }
 
+
 int kb_csr_destroy(kb_csr_t h) {
   if (h && h->masks) cudaFree(h->masks);
+  if (h) kb_merge_release(h);
   delete h;
   return KB_OK;
 }
 
 int kb_csr_set_schedule(kb_csr_t h, int schedule) {
   KB_REQUIRE(h != nullptr, "null matrix");
-  KB_REQUIRE(schedule >= 0 && schedule <= 4, "schedule must be 0 ... 4");
+  KB_REQUIRE(schedule >= 0 && schedule <= 5, "schedule must be 0 ... 5");
+  if (schedule == 5 && !(h->padded && h->nnz > 0 && h->n_rows < (1ll << 31) - 512))
+    return kb_fail(KB_EUNSUPPORTED, "merge schedule needs padded, 16-byte aligned CSR arrays");
   if (schedule == 4 && !h->constv)
     return kb_fail(KB_EUNSUPPORTED,
                    "stencil schedule needs <= 8 diagonals with one constant value each");
@@ -1118,15 +1116,18 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
     if (dot == 1) return kb_launch_stencil<1>(A, ws, x, y, mode, z, coef, w, out, st);
     return kb_launch_stencil<2>(A, ws, x, y, mode, z, coef, w, out, st);
   }
-  if (k == 1 && A->schedule >= 3 && g_window_cfg >= 0 && kb_window_ok(A, x)) {
+  if (k == 1 && (A->schedule == 3 || A->schedule == 4) && g_window_cfg >= 0 && kb_window_ok(A, x)) {
     if (dot == 0) return kb_launch_window<0>(A, ws, x, y, mode, z, coef, w, out, st);
     if (dot == 1) return kb_launch_window<1>(A, ws, x, y, mode, z, coef, w, out, st);
     return kb_launch_window<2>(A, ws, x, y, mode, z, coef, w, out, st);
   }
-  if (k == 1 && A->schedule >= 3) {
+  if (k == 1 && (A->schedule == 3 || A->schedule == 4)) {
     if (dot == 0) return kb_launch_pattern<0>(A, ws, x, y, mode, z, coef, w, out, st);
     if (dot == 1) return kb_launch_pattern<1>(A, ws, x, y, mode, z, coef, w, out, st);
     return kb_launch_pattern<2>(A, ws, x, y, mode, z, coef, w, out, st);
+  }
+  if (k == 1 && A->schedule == 5) {
+    return kb_launch_merge(A, ws, dot, x, y, mode, z, coef, w, out, st);
   }
   if (k == 1 && A->schedule >= 2) {
     if (dot == 0) return kb_launch_stream<0>(A, ws, x, y, mode, z, coef, w, out, st);

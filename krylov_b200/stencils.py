@@ -110,3 +110,30 @@ def shifted_laplace3d(n, sigma=None):
 
 def convection_diffusion3d(n, gamma=(0.5, 0.25, 0.125)):
     return to_scipy(stencil7_csr(n, n, n, coeffs=convdiff_coeffs(gamma)))
+
+
+def fem27_var(n, seed=0):
+    """27-point pattern on an n^3 grid with VARIABLE coefficients (a trilinear finite-element
+    stiffness matrix of a heterogeneous medium has this shape): symmetric, strictly diagonally
+    dominant, so SPD.  Not a BASELINE matrix -- a test / bench case for the CSR-streaming
+    schedules (no constant diagonals, 27 entries per interior row)."""
+    import scipy.sparse
+
+    rng = np.random.default_rng(seed)
+    idx = np.arange(n ** 3).reshape(n, n, n)
+    rows, cols, vals = [], [], []
+    offs = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)
+            if (a, b, c) > (0, 0, 0)]
+    for a, b, c in offs:
+        src = idx[max(0, -a):n - max(0, a), max(0, -b):n - max(0, b), max(0, -c):n - max(0, c)]
+        dst = idx[max(0, a):n - max(0, -a), max(0, b):n - max(0, -b), max(0, c):n - max(0, -c)]
+        w = -rng.uniform(0.1, 1.0, size=src.size)
+        rows += [src.ravel(), dst.ravel()]
+        cols += [dst.ravel(), src.ravel()]
+        vals += [w, w]
+    rows, cols, vals = (np.concatenate(v) for v in (rows, cols, vals))
+    off = scipy.sparse.csr_matrix((vals, (rows, cols)), shape=(n ** 3, n ** 3))
+    diag = -np.asarray(off.sum(axis=1)).ravel() + rng.uniform(0.05, 0.5, size=n ** 3)
+    A = (off + scipy.sparse.diags(diag)).tocsr()
+    A.sort_indices()
+    return A

@@ -41,6 +41,11 @@ def test_spmv_bit_exact_vs_scipy(name, A, k):
             # not stencil-like / not constant-coefficient: the library refuses, CSR schedules stay
             assert sched in ("pattern", "stencil")
             continue
+        if Ad.info()["schedule"] == "merge" and k == 1:
+            # long / skewed rows: several lanes per row, a fixed tree instead of SciPy's
+            # left-to-right order (test_merge_schedule_* below)
+            np.testing.assert_allclose(Ad @ x, ref, rtol=0, atol=1e-13 * np.max(abs(A) @ abs(x)))
+            continue
         np.testing.assert_array_equal(Ad @ x, ref)
 
 
@@ -671,3 +676,101 @@ def test_fused_cg_tile_shapes_agree(shape):
     finally:
         lib.kb_tune(22, -1)
         lib.kb_tune(23, -1)
+
+
+# ------------------------------------------------------------------ merge schedule --
+def _skewed_mats():
+    r = np.random.default_rng(7)
+    yield "random_100", scipy.sparse.random(20000, 20000, density=0.005, random_state=4, format="csr")
+    lens = np.minimum((r.pareto(1.0, 30000) * 4).astype(np.int64) + 1, 25000)
+    rows = np.repeat(np.arange(30000), lens)
+    cols = r.integers(0, 30000, size=rows.size)
+    P = scipy.sparse.csr_matrix((r.standard_normal(rows.size), (rows, cols)), shape=(30000, 30000))
+    P.sum_duplicates()
+    yield "powerlaw", P
+    # one row of 300 000 entries (147 tiles of 2048) between short rows and empty rows
+    M = scipy.sparse.lil_matrix((50, 300000))
+    M[7, :] = r.standard_normal(300000)
+    for i in (0, 1, 9, 30, 31):
+        M[i, r.choice(300000, 5, replace=False)] = 2.5
+    yield "one_very_long_row", M.tocsr()
+    yield "fem27", st.fem27_var(20)
+    yield "empty_rows", scipy.sparse.csr_matrix(
+        (np.array([1.0, 2.0]), np.array([0, 3]), np.array([0, 0, 1, 1, 2, 2])), shape=(5, 5))
+    yield "poisson3d_20", st.poisson3d(20)
+
+
+@pytest.mark.parametrize("name,A", list(_skewed_mats()))
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7])
+def test_merge_schedule_vs_scipy(name, A, cfg):
+    """Nonzero-balanced tiles (csrc/kb_merge.cuh): every row finished exactly once whatever
+    its length, 1e-13 of |A||x| against SciPy (bit-exact where one lane sums a row), fused
+    epilogues and dots, bitwise repeatable."""
+    from krylov_b200._lib import lib
+
+    A = A.tocsr()
+    A.sort_indices()
+    lib.kb_tune(25, cfg)
+    lib.kb_tune(27, cfg % 3)  # tile -> CTA order
+    try:
+        n, m = A.shape
+        Ad = kb.CsrMatrix.from_scipy(A).set_schedule("merge")
+        assert Ad.info()["schedule"] == "merge"
+        X, Z, W = r_(m), r_(n), r_(n)
+        x, z, w = (torch.from_numpy(a).cuda() for a in (X, Z, W))
+        ops = Ops(n, 1)
+        coef = np.array([0.7])
+        cf = torch.from_numpy(coef).cuda()
+        y = torch.empty(n, dtype=torch.float64, device="cuda")
+        out = ops.slots(1)[0]
+        t = A @ X
+        bound = 1e-13 * (abs(A) @ abs(X)) + 1e-300
+        first = None
+        for mode, ref in ((0, t), (1, t - coef[0] * Z), (2, Z - t)):
+            for dot, dref in ((0, None), (1, W @ ref), (2, ref @ ref)):
+                y.fill_(float("nan"))
+                ops.spmv(Ad, x, y, mode=mode, z=z, coef=cf, dot=dot, w=w, out=out)
+                got = y.cpu().numpy()
+                assert np.all(np.abs(got - ref) <= bound + 1e-15 * np.abs(ref)), (mode, dot)
+                if dot:
+                    sc = (np.abs(W) @ np.abs(ref)) if dot == 1 else dref
+                    assert abs(out.item() - dref) <= 1e-12 * sc + 1e-300
+                if mode == 0 and dot == 0:
+                    first = got.copy()
+        ops.spmv(Ad, x, y, mode=0, dot=0)
+        np.testing.assert_array_equal(y.cpu().numpy(), first)  # timing-independent
+    finally:
+        lib.kb_tune(25, 0)
+        lib.kb_tune(27, 2)
+
+
+def r_(n):
+    return np.random.default_rng(n).standard_normal(n)
+
+
+def test_merge_schedule_is_bit_exact_on_short_rows():
+    """Tiles whose rows get one lane each (more than 128 rows per 2048 nonzeros) sum left to
+    right: the 7-point stencil through the merge kernel equals SciPy bit for bit, except the
+    rows that straddle more than two tiles (none here)."""
+    A = st.poisson3d(24)
+    Ad = kb.CsrMatrix.from_scipy(A).set_schedule("merge")
+    x = r_(A.shape[0])
+    np.testing.assert_array_equal(Ad @ x, A @ x)
+
+
+def test_merge_schedule_selection_and_solvers():
+    A = scipy.sparse.random(4000, 4000, density=0.02, random_state=3, format="csr")  # 80 / row
+    A = (A + A.T + 200 * scipy.sparse.identity(4000)).tocsr()
+    Ad = kb.CsrMatrix.from_scipy(A)
+    assert Ad.info()["schedule"] == "merge"
+    b = A @ r_(4000)
+    from oracle import krylov_oracle as orc
+    for name in ("cg", "minres", "gmres"):
+        sol, info = getattr(kb, name)(Ad, b, tol=1e-10)
+        sol_o, info_o = getattr(orc, name)(A, b, tol=1e-10)
+        assert info.success and abs(info.numsteps - info_o.numsteps) <= 1
+        assert np.linalg.norm(sol - sol_o) <= 1e-10 * np.linalg.norm(sol_o)
+        ro, rr = np.asarray(info_o.resnorms), np.asarray(info.resnorms)
+        m = min(len(ro), len(rr))
+        live = ro[:m] / ro[0] >= 1e-6
+        assert np.all(np.abs(rr[:m] - ro[:m])[live] <= 1e-8 * ro[:m][live])
