@@ -245,6 +245,11 @@ typedef struct {
 int kb_cg_run(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending, void* stream);
 /* *fused = 1 if kb_cg_run would take the two-launch path for this state (see p2 above). */
 int kb_cg_is_fused(const kb_cg_state* s, int* fused);
+/* *yes = 1 if kb_cg_run runs the batch as ONE persistent launch (csrc/kb_small.cu: k == 1, one
+ * GPU, p2 given, n <= kb_tune key 28 [262144]; two grid-wide barriers per iteration instead of
+ * launches).  p moves to the other buffer with every executed iteration i > 0, as on the fused
+ * path.  The stopping test breaks the loop on the device; stop_at / hist / slots as above. */
+int kb_cg_is_persistent(kb_ws_t ws, const kb_cg_state* s, int* yes);
 /* kb_cg_run with CUDA events around every launch (measurement only; synchronises the stream).
  * ms[3]: mean duration of the phases of a step -- fused path: {p/x update + A p + <p,Ap>,
  * r update + <r,r>, 0}; three-kernel path: {p/x update, A p + <p,Ap>, r update + <r,r>}. */

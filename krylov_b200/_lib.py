@@ -95,6 +95,7 @@ SIGNATURES = {
     "kb_cg_update_p": [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "kb_cg_run": [vp, C.POINTER(CgState), i32, i32, i32, vp],
     "kb_cg_is_fused": [C.POINTER(CgState), C.POINTER(i32)],
+    "kb_cg_is_persistent": [vp, C.POINTER(CgState), C.POINTER(i32)],
     "kb_cg_run_timed": [vp, C.POINTER(CgState), i32, i32, i32, vp, C.POINTER(C.c_float),
                         C.POINTER(C.c_float)],
     "kb_axpy": [vp, i64, i32, f64, vp, vp, vp, vp],

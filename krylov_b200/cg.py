@@ -30,6 +30,7 @@ from .operators import Info, Problem
 
 INT_MAX = 2**31 - 1
 _BATCH_MIN, _BATCH_MAX = 8, 256
+_PERSISTENT_MAX_N = 262144  # kb_tune key 28: persistent one-launch batches up to this n
 
 
 def cg(A, b, M=None, Ml=None, inner=None, x0=None, tol=1e-5, atol=1.0e-15, maxiter=None,
@@ -183,7 +184,9 @@ class FusedCG:
         else:
             self.pbuf = [self.z.clone(), None]
         if self.comm is None and hasattr(A, "handle") and M is None and Ml is None:
-            if k == 1 and A.info()["schedule"] == "stencil":
+            # a second search-direction buffer: the fused marching kernels (3-D stencils) and
+            # the persistent small-problem kernel (csrc/kb_small.cu) ping-pong p
+            if k == 1 and (A.info()["schedule"] == "stencil" or n <= _PERSISTENT_MAX_N):
                 self.pbuf[1] = ops.vec(zero=False)
             self._cstate = CgState(A=A.handle, n=n, k=k, x=ptr(self.yk), r=ptr(self.r),
                                    p=ptr(self.pbuf[0]), Ap=ptr(self.Ap), slots=ptr(self.sl),
@@ -196,6 +199,7 @@ class FusedCG:
         # vector kernels of a step); current_x() flushes it
         self.x_pending = False
         self.fused_march = False
+        self.persistent = False
 
     @property
     def p(self):
@@ -276,9 +280,12 @@ class FusedCG:
             # the whole batch is enqueued by one C call (kb_cg_run); row-partitioned: the fused
             # two-launch path with peer-memory pushes and all-reduces inside the kernels
             self._cstate.pcur = self.pcur
-            fz = C.c_int(0)
+            fz, pz = C.c_int(0), C.c_int(0)
             check(lib.kb_cg_is_fused(C.byref(self._cstate), C.byref(fz)))
-            self.fused_march = bool(fz.value)
+            check(lib.kb_cg_is_persistent(self.ops.ws.handle, C.byref(self._cstate), C.byref(pz)))
+            self.persistent = bool(pz.value)
+            # both paths move p to the other buffer with every executed iteration i > 0
+            self.fused_march = bool(fz.value) or self.persistent
             check(lib.kb_cg_run(self.ops.ws.handle, C.byref(self._cstate), kk, nb,
                                 1 if self.x_pending else 0, cur_stream()))
             self.ops.launches += self._launches_of(kk, nb)
@@ -298,6 +305,8 @@ class FusedCG:
         return [rows[j].copy() for j in range(done)]
 
     def _launches_of(self, kk, nb):
+        if self.persistent:
+            return 1  # the whole batch is one persistent launch
         if self.gplan is not None:
             return 2 * nb
         return (2 if self.fused_march else 3) * nb - (
@@ -331,6 +340,7 @@ class FusedCG:
         fz = C.c_int(0)
         check(lib.kb_cg_is_fused(C.byref(self._cstate), C.byref(fz)))
         self.fused_march = bool(fz.value)
+        self.persistent = False  # the timed twin always launches per phase
         ms = (C.c_float * 3)()
         tot = C.c_float(0)
         check(lib.kb_cg_run_timed(self.ops.ws.handle, C.byref(self._cstate), kk, nb,
@@ -383,7 +393,9 @@ def _cg_fused(prob, tol, atol, maxiter, return_arnoldi, callback, M=None, Ml=Non
             xk = st.current_x()
             callback(prob.to_user(xk), prob.to_user(st.r))
         if not step_by_step:
-            batch = min(2 * batch, _BATCH_MAX)
+            # launched paths ramp up (iterations enqueued behind the converged one are wasted
+            # launches); the persistent kernel leaves its loop on the device: full batches
+            batch = _BATCH_MAX if st.persistent else min(2 * batch, _BATCH_MAX)
 
     if xk is None:
         xk = st.current_x()

@@ -211,6 +211,7 @@ int kb_tune(int key, int value) {
     case 25: g_merge_cfg = value; return KB_OK;  // tile shape of the merge kernel
     case 26: g_merge_ctas = value; return KB_OK; // its CTAs per SM (0 = all that fit)
     case 27: g_merge_order = value; return KB_OK; // tile -> CTA order (kb_merge.cuh)
+    case 28: g_small_n = value; return KB_OK;     // largest n of the persistent CG kernel (0 off)
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -246,8 +247,10 @@ int kb_ws_create(kb_ws_t* out, int max_k) {
   ws->comm = nullptr;
   ws->collective = 0;
   cudaError_t e = cudaMalloc(&ws->partials, sizeof(double) * KB_MAX_BLOCKS * (size_t)max_k);
-  if (e == cudaSuccess) e = cudaMalloc(&ws->ticket, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(ws->ticket, 0, sizeof(unsigned int));
+  // ticket[0]: arrival counter of the reductions; ticket[2]: barrier counter of kb_cg_small
+  if (e == cudaSuccess) e = cudaMalloc(&ws->ticket, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(ws->ticket, 0, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&ws->barbuf, KB_BAR_BYTES);
   if (e != cudaSuccess) {
     delete ws;
     return kb_fail(KB_ECUDA, "workspace allocation failed: %s", cudaGetErrorString(e));
@@ -260,6 +263,7 @@ int kb_ws_destroy(kb_ws_t ws) {
   if (!ws) return KB_OK;
   cudaFree(ws->partials);
   cudaFree(ws->ticket);
+  cudaFree(ws->barbuf);
   delete ws;
   return KB_OK;
 }
@@ -1431,6 +1435,12 @@ int kb_cg_is_fused(const kb_cg_state* s, int* fused) {
   return KB_OK;
 }
 
+int kb_cg_is_persistent(kb_ws_t ws, const kb_cg_state* s, int* yes) {
+  KB_REQUIRE(ws != nullptr && s != nullptr && yes != nullptr && s->A != nullptr, "null argument");
+  *yes = kb_cg_small_ok(ws, s) ? 1 : 0;
+  return KB_OK;
+}
+
 static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending,
                           void* stream, cudaEvent_t* ev) {
   KB_REQUIRE(ws != nullptr && s != nullptr, "null argument");
@@ -1438,6 +1448,8 @@ static int kb_cg_run_impl(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters,
              "null field in kb_cg_state");
   KB_REQUIRE(i0 >= 0 && n_iters >= 0, "negative iteration range");
   KB_REQUIRE(s->pcur == 0 || (s->pcur == 1 && s->p2 != nullptr), "pcur must name an existing buffer");
+  if (ev == nullptr && kb_cg_small_ok(ws, s))  // launch-latency-bound sizes: one persistent launch
+    return kb_cg_small_run(ws, s, i0, n_iters, x_pending, S(stream));
   const int k = s->k;
   double* sl = s->slots;
   const int* saved_gate = ws->gate;

@@ -11,6 +11,8 @@
 #define KB_MAX_K 256         // widest block of right-hand sides
 #define KB_CTAS_PER_SM 8     // resident CTAs per SM the vector grids are sized for
 #define KB_MAX_BLOCKS 2048   // upper bound of any reduction grid (partials buffer)
+#define KB_BAR_CTAS 256      // most CTAs of the persistent CG kernel
+#define KB_BAR_BYTES (2 * KB_BAR_CTAS * 128)  // two sets of one 128-byte line per CTA
 
 // ---------------------------------------------------------------- errors --
 extern thread_local char kb_errbuf[512];
@@ -124,6 +126,7 @@ __device__ __forceinline__ void kb_halo_wait(volatile unsigned long long* p,
 struct kb_ws_s {
   double* partials;      // KB_MAX_BLOCKS * max_k doubles
   unsigned int* ticket;  // arrival counter of the single-launch reductions
+  double* barbuf;        // grid-barrier slots of the persistent CG kernel (KB_BAR_BYTES)
   int max_k;
   int num_sms;
   const int* gate;       // device int or nullptr

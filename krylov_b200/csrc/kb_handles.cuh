@@ -49,3 +49,9 @@ void kb_merge_release(kb_csr_s* h);
 int kb_launch_merge(kb_csr_s* A, kb_ws_s* ws, int dot, const double* x, double* y, int mode,
                     const double* z, const double* coef, const double* w, double* out,
                     cudaStream_t st);
+
+// kb_small.cu
+extern int g_small_n;
+bool kb_cg_small_ok(const kb_ws_s* ws, const kb_cg_state* s);
+int kb_cg_small_run(kb_ws_s* ws, const kb_cg_state* s, int i0, int n_iters, int x_pending,
+                    cudaStream_t st);

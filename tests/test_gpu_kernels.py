@@ -501,13 +501,19 @@ def test_fused_marching_cg_is_selected():
     """The two-launch path is what runs for k = 1 on a 3-D constant stencil, and only there."""
     from krylov_b200.cg import FusedCG
 
+    from krylov_b200._lib import lib
+
     def fused(A, k=1):
         n = A.shape[0]
         Ad = kb.CsrMatrix.from_scipy(A)
         b = torch.from_numpy(rng.standard_normal((n, k))).cuda()
-        s = FusedCG(Ad, b, torch.zeros_like(b), 1e-8, 0.0)
-        s.run(4)
-        return s.fused_march
+        lib.kb_tune(28, 0)  # these sizes would otherwise take the persistent kernel
+        try:
+            s = FusedCG(Ad, b, torch.zeros_like(b), 1e-8, 0.0)
+            s.run(4)
+        finally:
+            lib.kb_tune(28, 262144)
+        return s.fused_march and not s.persistent
 
     assert fused(st.poisson3d(32))
     assert not fused(st.poisson3d(32), k=2)
@@ -774,3 +780,61 @@ def test_merge_schedule_selection_and_solvers():
         m = min(len(ro), len(rr))
         live = ro[:m] / ro[0] >= 1e-6
         assert np.all(np.abs(rr[:m] - ro[:m])[live] <= 1e-8 * ro[:m][live])
+
+
+# ------------------------------------------------- persistent small-problem CG kernel --
+def _small_cases():
+    yield "poisson2d_256", st.poisson2d(256), 1e-10          # BASELINE C1
+    yield "poisson2d_37", st.poisson2d(37), 1e-12            # n = 1369: one partial CTA
+    yield "poisson3d_60", st.poisson3d(60), 1e-10            # n = 216000 > 148 x 1024: 2 rows / thread
+    R = scipy.sparse.random(5000, 5000, density=0.004, random_state=5, format="csr")
+    yield "random_spd", (R + R.T + 30 * scipy.sparse.identity(5000)).tocsr(), 1e-12
+    yield "fem27_14", st.fem27_var(14), 1e-11
+
+
+@pytest.mark.parametrize("name,A,tol", list(_small_cases()), ids=[c[0] for c in _small_cases()])
+def test_persistent_cg_matches_launched_cg_and_oracle(name, A, tol):
+    """csrc/kb_small.cu: a whole batch of iterations in one cooperative launch (two grid
+    barriers per step).  Same step count as the launched path and as the oracle, histories
+    within the north-star tolerance of the oracle and 1e-11 of the launched path, same x."""
+    from krylov_b200._lib import lib
+    from oracle import krylov_oracle as orc
+
+    b = A @ r_(A.shape[0])
+    out = {}
+    for mode, key in (("persistent", 262144), ("launched", 0)):
+        lib.kb_tune(28, key)
+        try:
+            Ad = kb.CsrMatrix.from_scipy(A)
+            out[mode] = kb.cg(Ad, b, tol=tol, maxiter=5000)
+        finally:
+            lib.kb_tune(28, 262144)
+    sol_o, info_o = orc.cg(A, b, tol=tol, maxiter=5000)
+    (xp, ip), (xl, il) = out["persistent"], out["launched"]
+    assert ip.success and il.success
+    assert ip.numsteps == il.numsteps == info_o.numsteps
+    rp, rl, ro = (np.asarray(v.resnorms) for v in (ip, il, info_o))
+    live = ro / ro[0] >= 1e-6
+    assert np.all(np.abs(rp - ro)[live] <= 1e-8 * ro[live])
+    assert np.all(np.abs(rp - rl)[live] <= 1e-11 * rl[live])
+    assert np.linalg.norm(xp - sol_o) <= 1e-10 * np.linalg.norm(sol_o)
+    assert np.linalg.norm(xp - xl) <= 1e-12 * np.linalg.norm(xl)
+
+
+def test_persistent_cg_is_selected_and_repeatable():
+    import ctypes as C
+    from krylov_b200.cg import FusedCG
+
+    A = st.poisson2d(256)
+    b = A @ r_(A.shape[0])
+    Ad = kb.CsrMatrix.from_scipy(A)
+    bd = torch.from_numpy(b.reshape(-1, 1)).cuda()
+    stt = FusedCG(Ad, bd, torch.zeros_like(bd), 1e-10, 0.0)
+    l0 = stt.ops.launches
+    h1 = np.concatenate(stt.run(64))
+    assert stt.persistent and stt.ops.launches == l0 + 1  # one launch for 64 steps
+    x1, i1 = kb.cg(Ad, b, tol=1e-10, maxiter=5000)
+    x2, i2 = kb.cg(Ad, b, tol=1e-10, maxiter=5000)
+    np.testing.assert_array_equal(np.asarray(i1.resnorms), np.asarray(i2.resnorms))
+    np.testing.assert_array_equal(x1, x2)
+    np.testing.assert_array_equal(np.asarray(i1.resnorms)[1:65].ravel(), h1.ravel())

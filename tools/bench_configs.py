@@ -37,7 +37,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 A = kb.CsrMatrix.from_scipy(st.poisson2d(256)); n = A.shape[0]
 b = A.matvec_device(torch.randn(n, generator=g, dtype=torch.float64, device="cuda"))
 secs, (sol, info) = timed(lambda: kb.cg(A, b, tol=1e-10, maxiter=5000), reps=3)
-report("C1 cg 2D Poisson 256^2 tol 1e-10", info.numsteps, secs, info.numsteps * (12*A.nnz + 4*(n+1) + 92*n), "(L2-resident; launch-latency bound)")
+report("C1 cg 2D Poisson 256^2 tol 1e-10", info.numsteps, secs, info.numsteps * (12*A.nnz + 4*(n+1) + 92*n), "(L2-resident; one persistent launch per batch, two grid barriers per step)")
 # C2: minres, shifted 3-D Laplacian 128^3, mild shift
 N = 128; A = device_stencil7(N, N, N, shift=st.mild_shift(N)); n = A.shape[0]
 b = A.matvec_device(torch.randn(n, generator=g, dtype=torch.float64, device="cuda"))
