@@ -306,6 +306,24 @@ int kb_minres_update(kb_ws_t ws, int64_t n, int k, const double* coefs, const do
                      double* W0, const double* W1, const double* Av, double* yk,
                      double* vnext, const double* MAv, double* pnext, void* stream);
 
+/* Whole-loop entry point (SURVEY.md 8b "kb_minres_solve"): enqueues MINRES iterations
+ * i0 .. i0+n_iters-1 of the unpreconditioned fused path on one GPU -- per iteration kb_spmv
+ * (Lanczos product fused with alpha), kb_axpy_dot (beta^2), kb_minres_scalar, kb_minres_update --
+ * each gated on *st.stop_at <= i.  V[i % 2] holds v_i (V[(i+1) % 2] = v_{i-1}, overwritten with
+ * v_{i+1}), W[i % 2] / W[(i+1) % 2] the two W vectors; st.hist row 0 receives step i0+1 when the
+ * caller offsets the pointer as for kb_minres_scalar.  Replaces the loop minres.py:168-236. */
+typedef struct {
+  kb_csr_t A;
+  int64_t n;
+  int k;
+  double* V[2];
+  double* W[2];
+  double* Av;
+  double* yk;
+  kb_minres_state st;
+} kb_minres_run_state;
+int kb_minres_run(kb_ws_t ws, const kb_minres_run_state* s, int i0, int n_iters, void* stream);
+
 /* --- Arnoldi-MGS / GMRES (arnoldi.py:167-200, gmres.py:179-234) -------- */
 typedef struct {
   const double* dots;  /* (num_reorthos*(j+1)*k) MGS coefficients of this step */
@@ -324,6 +342,26 @@ typedef struct {
   int have_h;          /* 1: Householder path -- `dots` already holds h[0..j+1] */
 } kb_gmres_state;
 int kb_gmres_scalar(kb_ws_t ws, int k, int iter, const kb_gmres_state* st, void* stream);
+/* Whole-loop entry point (SURVEY.md 8b "kb_gmres_cycle"): enqueues Arnoldi steps i0 ..
+ * i0+n_iters-1 of unpreconditioned GMRES with modified Gram-Schmidt (st.num_reorthos sweeps) on
+ * one GPU -- per step kb_spmv (w = A V[i] fused with <V[0], w>), (i+1) x sweeps kb_axpy_dot,
+ * kb_gmres_scalar (Givens update of the Hessenberg column, residual norm, stop flag),
+ * kb_div_scale (V[i+1] = w / h[i+1]) -- each gated on *st.stop_at <= i.  V[j] = Vbuf + j*vstride
+ * must hold i0+n_iters+1 vectors; dots has num_reorthos*(st.maxiter+1)+2 rows of k doubles and
+ * must equal st.dots.  Replaces the loop gmres.py:179-234 with arnoldi.py:153-200. */
+typedef struct {
+  kb_csr_t A;
+  int64_t n;
+  int k;
+  double* Vbuf;
+  int64_t vstride;
+  double* w;
+  double* dots;
+  double* ww;
+  double* hlast;
+  kb_gmres_state st;
+} kb_gmres_cycle_state;
+int kb_gmres_cycle(kb_ws_t ws, const kb_gmres_cycle_state* s, int i0, int n_iters, void* stream);
 /* yy = R[:m,:m]^-1 y[:m] per column (all-zero column -> zeros) (gmres.py:24-38) */
 int kb_gmres_solve_y(kb_ws_t ws, int k, int m, int maxiter, const double* R, const double* y,
                      double* yy, void* stream);

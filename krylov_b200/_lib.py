@@ -54,6 +54,20 @@ class GmresState(C.Structure):
     ]
 
 
+class MinresRunState(C.Structure):
+    _fields_ = [
+        ("A", vp), ("n", i64), ("k", i32), ("V", vp * 2), ("W", vp * 2), ("Av", vp), ("yk", vp),
+        ("st", MinresState),
+    ]
+
+
+class GmresCycleState(C.Structure):
+    _fields_ = [
+        ("A", vp), ("n", i64), ("k", i32), ("Vbuf", vp), ("vstride", i64), ("w", vp), ("dots", vp),
+        ("ww", vp), ("hlast", vp), ("st", GmresState),
+    ]
+
+
 # name -> argtypes (restype is always int).  Kept in one table so the CPU test
 # can check that every symbol declared in the header is exported.
 SIGNATURES = {
@@ -96,6 +110,8 @@ SIGNATURES = {
     "kb_cg_run": [vp, C.POINTER(CgState), i32, i32, i32, vp],
     "kb_cg_is_fused": [C.POINTER(CgState), C.POINTER(i32)],
     "kb_cg_is_persistent": [vp, C.POINTER(CgState), C.POINTER(i32)],
+    "kb_minres_run": [vp, C.POINTER(MinresRunState), i32, i32, vp],
+    "kb_gmres_cycle": [vp, C.POINTER(GmresCycleState), i32, i32, vp],
     "kb_cg_run_timed": [vp, C.POINTER(CgState), i32, i32, i32, vp, C.POINTER(C.c_float),
                         C.POINTER(C.c_float)],
     "kb_axpy": [vp, i64, i32, f64, vp, vp, vp, vp],

@@ -1,0 +1,83 @@
+// Whole-batch entry points of MINRES and GMRES ("kb_minres_solve",
+// "kb_gmres_cycle"): one C call enqueues every launch of iterations i0 .. i0+n-1, each gated on
+// the device-resident stop flag, so the host language is out of the loop between two read-backs
+// (minres.py:168-236, gmres.py:179-234 with arnoldi.py:153-200).  Same kernels, same order and
+// same arguments as the per-launch path of krylov_b200/minres.py and gmres.py.
+#include "kb_handles.cuh"
+
+extern "C" {
+
+int kb_minres_run(kb_ws_t ws, const kb_minres_run_state* s, int i0, int n_iters, void* stream) {
+  KB_REQUIRE(ws != nullptr && s != nullptr, "null argument");
+  KB_REQUIRE(s->A && s->V[0] && s->V[1] && s->W[0] && s->W[1] && s->Av && s->yk,
+             "null field in kb_minres_run_state");
+  KB_REQUIRE(i0 >= 0 && n_iters >= 0, "negative iteration range");
+  const int k = s->k;
+  const kb_minres_state* st = &s->st;
+  const int* saved_gate = ws->gate;
+  const int saved_tag = ws->gate_tag;
+  int rc = KB_OK;
+  for (int i = i0; i < i0 + n_iters && rc == KB_OK; ++i) {
+    double* v = s->V[i % 2];
+    double* vold = s->V[(i + 1) % 2];
+    ws->gate = st->stop_at;
+    ws->gate_tag = i;
+    // Av = A v - beta_{i-1} v_old, alpha = <v, Av>   (arnoldi.py:244-252)
+    if (i == 0)
+      rc = kb_spmv(s->A, ws, k, v, s->Av, 0, nullptr, nullptr, 1, v, (double*)st->alpha, stream);
+    else
+      rc = kb_spmv(s->A, ws, k, v, s->Av, 1, vold, st->h2prev, 1, v, (double*)st->alpha, stream);
+    // Av -= alpha v, beta_i^2 = <Av, Av>             (arnoldi.py:264-267)
+    if (rc == KB_OK)
+      rc = kb_axpy_dot(ws, s->n, k, st->alpha, nullptr, v, s->Av, 2, nullptr, (double*)st->ww,
+                       stream);
+    if (rc == KB_OK) rc = kb_minres_scalar(ws, k, i, st, stream);  // minres.py:190-228
+    if (rc == KB_OK)  // minres.py:219-221, arnoldi.py:274-277
+      rc = kb_minres_update(ws, s->n, k, st->coefs, v, s->W[i % 2], s->W[(i + 1) % 2], s->Av, s->yk,
+                            vold, nullptr, nullptr, stream);
+  }
+  ws->gate = saved_gate;
+  ws->gate_tag = saved_tag;
+  return rc;
+}
+
+int kb_gmres_cycle(kb_ws_t ws, const kb_gmres_cycle_state* s, int i0, int n_iters, void* stream) {
+  KB_REQUIRE(ws != nullptr && s != nullptr, "null argument");
+  KB_REQUIRE(s->A && s->Vbuf && s->w && s->dots && s->ww && s->hlast,
+             "null field in kb_gmres_cycle_state");
+  KB_REQUIRE(i0 >= 0 && n_iters >= 0, "negative iteration range");
+  KB_REQUIRE(i0 + n_iters <= s->st.maxiter, "basis storage too small for this range");
+  const int k = s->k;
+  const int nre = s->st.num_reorthos;
+  const int* saved_gate = ws->gate;
+  const int saved_tag = ws->gate_tag;
+  int rc = KB_OK;
+  for (int i = i0; i < i0 + n_iters && rc == KB_OK; ++i) {
+    ws->gate = s->st.stop_at;
+    ws->gate_tag = i;
+    double* V0 = s->Vbuf;
+    double* Vi = s->Vbuf + (size_t)i * s->vstride;
+    // w = A V[i], first MGS coefficient <V[0], w> in the same pass
+    rc = kb_spmv(s->A, ws, k, Vi, s->w, 0, nullptr, nullptr, 1, V0, s->dots, stream);
+    int idx = 0;
+    for (int sweep = 0; sweep < nre && rc == KB_OK; ++sweep)
+      for (int j = 0; j <= i && rc == KB_OK; ++j, ++idx) {  // arnoldi.py:157-162
+        double* Vj = s->Vbuf + (size_t)j * s->vstride;
+        double* coef = s->dots + (size_t)idx * k;
+        if (sweep == nre - 1 && j == i) {  // last projection + <w, w>   (arnoldi.py:184-185)
+          rc = kb_axpy_dot(ws, s->n, k, coef, nullptr, Vj, s->w, 2, nullptr, s->ww, stream);
+        } else {
+          const double* nxt = j < i ? Vj + s->vstride : V0;
+          rc = kb_axpy_dot(ws, s->n, k, coef, nullptr, Vj, s->w, 1, nxt, coef + k, stream);
+        }
+      }
+    if (rc == KB_OK) rc = kb_gmres_scalar(ws, k, i, &s->st, stream);  // gmres.py:206-221
+    if (rc == KB_OK)  // V[i+1] = w / h[i+1]   (arnoldi.py:191-193)
+      rc = kb_div_scale(ws, s->n, k, s->w, s->hlast, Vi + s->vstride, stream);
+  }
+  ws->gate = saved_gate;
+  ws->gate_tag = saved_tag;
+  return rc;
+}
+
+}  // extern "C"

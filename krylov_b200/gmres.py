@@ -19,15 +19,18 @@ import numpy as np
 import torch
 
 from ._alg import Alg, nz
-from ._lib import GmresState
+import ctypes as C
+
+from ._lib import GmresCycleState, GmresState, check, lib
 from .arnoldi import _DevHouseholder
-from .device import Ops, ptr
+from .device import Ops, cur_stream, ptr
 from .errors import ArgumentError
 from .operators import Identity, Info, Problem
 
 INT_MAX = 2**31 - 1
 _BATCH_MIN, _BATCH_MAX = 4, 64
 _BASIS_CHUNK = 64  # Arnoldi vectors allocated up front; doubled on demand
+USE_C_LOOP = True  # kb_gmres_cycle where it applies (tests compare both ways)
 _INVARIANT_MSG = "Krylov subspace was found to be invariant in the previous iteration."
 
 
@@ -249,6 +252,9 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
     Tbuf = [ops.vec(zero=False) for _ in range(0 if csr_chain is None else len(csr_chain) - 1)]
     MWbuf = ops.vec(zero=False) if M_csr is not None and not householder else None
     step_by_step = callback is not None or not fused_dots
+    cycle_in_c = (USE_C_LOOP and not householder and not cgs and fused_dots and M is None and prob.comm is None
+                  and csr_chain is not None and len(csr_chain) == 1
+                  and hasattr(csr_chain[0], "handle"))
     batch = 1 if step_by_step else _BATCH_MIN
     kk = 0
     success = False
@@ -282,9 +288,16 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
                                                             ptr(y), cap)
         stop_at.fill_(INT_MAX)
         st.hist = hist.data_ptr() - (kk + 1) * k * 8
-        for i in range(kk, kk + nb):
-            ops.gate(stop_at, i)
-            arnoldi_step(i)
+        if cycle_in_c:
+            # one GPU, MGS, no preconditioner: the whole batch is one C call (kb_gmres_cycle)
+            cyc = GmresCycleState(A=csr_chain[0].handle, n=n, k=k, Vbuf=ptr(Vbuf), vstride=n * k,
+                                  w=ptr(Wbuf), dots=ptr(dots), ww=ptr(ww), hlast=ptr(hlast), st=st)
+            check(lib.kb_gmres_cycle(ops.ws.handle, C.byref(cyc), kk, nb, cur_stream()))
+            ops.launches += sum(3 + nre * (i + 1) for i in range(kk, kk + nb))
+        else:
+            for i in range(kk, kk + nb):
+                ops.gate(stop_at, i)
+                arnoldi_step(i)
         ops.gate(None, 0)
         s = int(stop_at.item())
         done = min(s, kk + nb) - kk

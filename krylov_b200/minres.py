@@ -19,15 +19,18 @@ import numpy as np
 import torch
 
 from ._alg import Alg, nz
-from ._lib import MinresState
+import ctypes as C
+
+from ._lib import MinresRunState, MinresState, check, lib
 from .arnoldi import _DevLanczos
-from .device import Ops, ptr
+from .device import Ops, cur_stream, ptr
 from .errors import ArgumentError
 from .givens import givens
 from .operators import Info, Problem
 
 INT_MAX = 2**31 - 1
 _BATCH_MIN, _BATCH_MAX = 8, 256
+USE_C_LOOP = True  # kb_minres_run where it applies (tests compare both ways)
 _INVARIANT_MSG = "Krylov subspace was found to be invariant in the previous iteration."
 
 
@@ -128,6 +131,13 @@ def _minres_fused(prob, tol, atol, maxiter, callback, M=None, Ml=None, Mr=None):
                      y0=ptr(sl[3]), coefs=ptr(coefs), crit=ptr(crit_d), hist=0,
                      stop_at=ptr(stop_at), flags=ptr(flags))
 
+    # one GPU, no preconditioner: the whole batch is enqueued by one C call (kb_minres_run)
+    run_c = None
+    if USE_C_LOOP and len(chain) == 1 and M is None and prob.comm is None and hasattr(A, "handle"):
+        run_c = MinresRunState(A=A.handle, n=n, k=k, Av=ptr(Av), yk=ptr(yk))
+        run_c.V[0], run_c.V[1] = ptr(Vb[0]), ptr(Vb[1])
+        run_c.W[0], run_c.W[1] = ptr(Wb[0]), ptr(Wb[1])
+
     batch = 1 if callback is not None else _BATCH_MIN
     kk = 0
     success = False
@@ -147,7 +157,11 @@ def _minres_fused(prob, tol, atol, maxiter, callback, M=None, Ml=None, Mr=None):
         nb = min(batch, maxiter - kk)
         stop_at.fill_(INT_MAX)
         st.hist = hist.data_ptr() - (kk + 1) * k * 8
-        for i in range(kk, kk + nb):
+        if run_c is not None:
+            run_c.st = st
+            check(lib.kb_minres_run(ops.ws.handle, C.byref(run_c), kk, nb, cur_stream()))
+            ops.launches += 4 * nb
+        for i in range(kk, kk + nb) if run_c is None else ():
             v, vold = Vb[i % 2], Vb[(i + 1) % 2]
             p, pold = Pb[i % 2], Pb[(i + 1) % 2]
             ops.gate(stop_at, i)

@@ -838,3 +838,28 @@ def test_persistent_cg_is_selected_and_repeatable():
     np.testing.assert_array_equal(np.asarray(i1.resnorms), np.asarray(i2.resnorms))
     np.testing.assert_array_equal(x1, x2)
     np.testing.assert_array_equal(np.asarray(i1.resnorms)[1:65].ravel(), h1.ravel())
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_c_side_loops_equal_per_launch_loops(k):
+    """kb_minres_run / kb_gmres_cycle enqueue the same kernels with the same arguments as the
+    per-launch Python loops: histories and solutions are bit-identical."""
+    import krylov_b200.gmres as gm
+    import krylov_b200.minres as mr
+
+    A = st.shifted_laplace3d(14)
+    B = st.convection_diffusion3d(13)
+    bA = A @ rng.standard_normal((A.shape[0], k) if k > 1 else A.shape[0])
+    bB = B @ rng.standard_normal((B.shape[0], k) if k > 1 else B.shape[0])
+    res = {}
+    for flag in (True, False):
+        mr.USE_C_LOOP = gm.USE_C_LOOP = flag
+        try:
+            res[flag] = (kb.minres(A, bA, tol=1e-9), kb.gmres(B, bB, tol=1e-9, maxiter=90),
+                         kb.gmres(B, bB, tol=1e-9, maxiter=90, ortho="mgs2"))
+        finally:
+            mr.USE_C_LOOP = gm.USE_C_LOOP = True
+    for (xc, ic), (xp, ip) in zip(res[True], res[False]):
+        assert ic.numsteps == ip.numsteps and ic.success == ip.success
+        np.testing.assert_array_equal(np.asarray(ic.resnorms), np.asarray(ip.resnorms))
+        np.testing.assert_array_equal(ic.xk, ip.xk)

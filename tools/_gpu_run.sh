@@ -1,3 +1,5 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "persistent or fused_marching" 2>&1 | tail -2
-python tools/small_cg_bench.py 256 128 512 2>&1 | grep -v Warn | tee gpurun_out/r2m_small_cg.txt
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | grep -v Warning | tail -4 > gpurun_out/r2o_pytest_gpu.log
+tail -4 gpurun_out/r2o_pytest_gpu.log
+timeout 300 python tools/bench_configs.py 2>&1 | grep "C1\|C2\|C3" | tee gpurun_out/r2o_configs.txt
