@@ -142,7 +142,9 @@ def make(name):
     raise KeyError(name)
 
 
-if "--one" in sys.argv:
+if "--import" in sys.argv:  # bench.py uses the generators
+    pass
+elif "--one" in sys.argv:
     i = sys.argv.index("--one")
     name, sched, cfg, reps = sys.argv[i + 1], sys.argv[i + 2], int(sys.argv[i + 3]), int(sys.argv[i + 4])
     A, _ = make(name)
@@ -161,7 +163,7 @@ if "--one" in sys.argv:
 names = ["random_100", "banded_100", "powerlaw", "fem27_var"]
 if "--only" in sys.argv:
     names = [sys.argv[sys.argv.index("--only") + 1]]
-for nm in names:
+for nm in ([] if "--import" in sys.argv else names):
     A, extra = make(nm)
     bench(nm, A, extra)
     del A
