@@ -47,7 +47,7 @@ static int g_spmm_lines = 1;    // kb_tune key 16: line-marching SpMM (k > 1, co
                                 // 0 off, 1 where a line fills >= half of its chunks, 2 wherever valid
 static int g_lines_ch = 0;      // kb_tune key 17: lines per work item of it (0 = 32)
 static int g_lines_order = 1;   // kb_tune key 19: work-item order, 0 natural, 1 planes fastest
-static int g_lines_cfg = 0;     // kb_tune key 18: 0 = 1024-entry chunks, 2 CTAs/SM; 1 = 512, 4 CTAs/SM
+static int g_lines_cfg = 0;      // kb_tune key 18: 0 auto (1024-entry chunks, 2 CTAs/SM; 512 where the values are streamed and k <= 16), 1 = 512, 4 CTAs/SM, 2 = 1024
 static int g_stencil_ctas = 0;  // kb_tune key 11: CTAs/SM cap of it (0 = occupancy limit)
 static int g_cgs_jc = 8;  // kb_tune key 9: basis vectors per multi-dot launch (8 or 16)
 static int g_rowwise_contig = -1;  // kb_tune key 5: -1 auto, 0 strided, 1 contiguous rows per block
@@ -415,20 +415,36 @@ int kb_csr_create(kb_csr_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz,
   h->forced = 0;
   h->max_row_len = 0;
   if (n_rows > 0) {
+    // one pass over the row pointers (longest row + structure) and one over the column indices:
+    // a malformed matrix is refused here instead of being read out of bounds by the kernels
     int* d_max = nullptr;
-    cudaError_t e = cudaMalloc(&d_max, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_max, 0, sizeof(int), S(stream));
+    int host[2] = {0, 0};
+    cudaError_t e = cudaMalloc(&d_max, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_max, 0, 2 * sizeof(int), S(stream));
     if (e == cudaSuccess) {
       int grid = (int)((n_rows + 255) / 256);
       if (grid > 1184) grid = 1184;
-      kb_max_row_len_kernel<<<grid, 256, 0, S(stream)>>>(n_rows, rowptr, d_max);
-      e = cudaMemcpyAsync(&h->max_row_len, d_max, sizeof(int), cudaMemcpyDeviceToHost, S(stream));
+      kb_max_row_len_kernel<<<grid, 256, 0, S(stream)>>>(n_rows, nnz, rowptr, d_max);
+      if (nnz > 0) {
+        int g2 = (int)((nnz + 255) / 256 > 2368 ? 2368 : (nnz + 255) / 256);
+        kb_colidx_check_kernel<<<g2, 256, 0, S(stream)>>>(nnz, n_cols, colidx, d_max);
+      }
+      e = cudaMemcpyAsync(host, d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, S(stream));
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(S(stream));  // creation is not on the hot path
     if (d_max) cudaFree(d_max);
     if (e != cudaSuccess) {
       delete h;
       return kb_fail(KB_ECUDA, "kb_csr_create: %s", cudaGetErrorString(e));
+    }
+    h->max_row_len = host[0];
+    if (host[1] != 0) {
+      delete h;
+      return kb_fail(KB_EINVAL, "kb_csr_create: malformed CSR arrays (%s%s%s%s)",
+                     (host[1] & 1) ? "rowptr[0] != 0; " : "",
+                     (host[1] & 2) ? "row pointers decrease; " : "",
+                     (host[1] & 4) ? "rowptr[n_rows] != nnz; " : "",
+                     (host[1] & 8) ? "column index outside [0, n_cols)" : "");
     }
   }
   h->masks = nullptr;
@@ -958,10 +974,18 @@ static int kb_launch_stencil(kb_csr_s* A, kb_ws_s* ws, const double* x, double* 
 // Geometry of kb_spmm_lines_kernel; false if the matrix / block width / operand do not qualify:
 // constant diagonals {-P, -n, -i, 0, +i, +n, +P}, k a power of two in [2, 32] (a thread keeps one
 // column; 288 % k == 0 for the block reduction), x 16-byte aligned (TMA).
-static bool kb_lines_geom(const kb_csr_s* A, int k, const double* x, KbLines* g) {
-  const int TR = g_lines_cfg == 1 ? 512 : 1024;
+// var: the matrix has the pattern but not constant diagonals -- its values are streamed (k >= 8:
+// below that the value area would dominate the ring slot)
+static bool kb_lines_geom(const kb_csr_s* A, int k, const double* x, KbLines* g, bool* var = nullptr) {
+  if (g_spmm_lines <= 0 || !A->pattern_ok || A->pat.nd != 7 || A->masks == nullptr) return false;
+  const bool v = !A->constv || A->schedule == 3;
+  // chunk size: 1024 entries; with streamed values the value area pushes four 1024-entry slots
+  // past half an SM's shared memory for k <= 16 (one CTA per SM: 2.6 ms at 256^3, k = 16, against
+  // 1.87 ms with 512-entry chunks, profiles/r2_spmm_var.txt)
+  const int TR = (g_lines_cfg == 1 || (g_lines_cfg == 0 && v && k <= 16)) ? 512 : 1024;
   g->TR = TR;
-  if (g_spmm_lines <= 0 || !A->constv || A->pat.nd != 7 || A->masks == nullptr) return false;
+  if (v && (var == nullptr || k < 8 || !A->padded)) return false;
+  if (var) *var = v;
   if (k < 2 || k > 32 || (k & (k - 1)) != 0) return false;
   if (((uintptr_t)x & 15u) != 0) return false;
   const int* off = A->pat.off;
@@ -984,7 +1008,10 @@ static bool kb_lines_geom(const kb_csr_s* A, int k, const double* x, KbLines* g)
   g->nlines = (g->N + g->L - 1) / g->L;
   g->ncol = (int)((g->L + TR - 1) / TR);
   if (g_spmm_lines == 1 && 2 * g->L < (long long)g->ncol * TR) return false;  // chunks mostly empty
-  g->slotlen = 3 * TR + 2 * g->H;
+  g->voff = 3 * TR + 2 * g->H;
+  g->vcap = v ? (TR / k) * 7 + 2 : 0;
+  g->n_rows = A->n_rows;
+  g->slotlen = g->voff + g->vcap;
   long long ch = g_lines_ch > 0 ? g_lines_ch : 32;
   if (ch > g->nlines) ch = g->nlines;
   if (ch < 1) ch = 1;
@@ -1003,13 +1030,13 @@ static bool kb_lines_geom(const kb_csr_s* A, int k, const double* x, KbLines* g)
   return true;
 }
 
-template <int RPT, int MINB, int DOT, bool WX>
+template <int RPT, int MINB, int DOT, bool WX, bool VAR = false>
 static int kb_launch_lines_t(kb_csr_s* A, kb_ws_s* ws, const KbLines& g, const double* x, double* y,
                              int mode, const double* z, const double* coef, const double* w,
                              double* out, cudaStream_t st) {
   static int max_smem[64] = {0};
   constexpr int NS = 4;
-  auto kern = kb_spmm_lines_kernel<RPT, NS, MINB, DOT, WX>;
+  auto kern = kb_spmm_lines_kernel<RPT, NS, MINB, DOT, WX, VAR>;
   int dev = 0;
   KB_CUDA(cudaGetDevice(&dev));
   const size_t smem = (size_t)NS * g.slotlen * 8 + 2 * NS * 8;
@@ -1026,15 +1053,21 @@ static int kb_launch_lines_t(kb_csr_s* A, kb_ws_s* ws, const KbLines& g, const d
   long long grid = (long long)ws->num_sms * ctas;
   if (grid > g.nitems) grid = g.nitems;
   if (grid > KB_MAX_BLOCKS) grid = KB_MAX_BLOCKS;
-  kern<<<(int)grid, 288, smem, st>>>(g, A->masks, A->cv, x, y, mode, z, coef, w, out, kb_red(ws));
+  kern<<<(int)grid, 288, smem, st>>>(g, A->masks, A->cv, A->rowptr, A->vals, x, y, mode, z, coef,
+                                     w, out, kb_red(ws));
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
 
 template <int DOT>
-static int kb_launch_lines(kb_csr_s* A, kb_ws_s* ws, const KbLines& g, const double* x, double* y,
-                           int mode, const double* z, const double* coef, const double* w,
-                           double* out, cudaStream_t st) {
+static int kb_launch_lines(kb_csr_s* A, kb_ws_s* ws, const KbLines& g, bool var, const double* x,
+                           double* y, int mode, const double* z, const double* coef,
+                           const double* w, double* out, cudaStream_t st) {
+  if (var) {  // variable coefficients: values streamed through the ring
+    if (g.TR == 512)
+      return kb_launch_lines_t<2, 4, DOT, false, true>(A, ws, g, x, y, mode, z, coef, w, out, st);
+    return kb_launch_lines_t<4, 2, DOT, false, true>(A, ws, g, x, y, mode, z, coef, w, out, st);
+  }
   const bool wx = DOT == 1 && w == x;  // <x, A x>: the operand is the middle diagonal's entry, on chip
   if (g.TR == 512) {
     if (wx) return kb_launch_lines_t<2, 4, DOT, (DOT == 1)>(A, ws, g, x, y, mode, z, coef, w, out, st);
@@ -1139,13 +1172,14 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
     return kb_launch_stream<2>(A, ws, x, y, mode, z, coef, w, out, st);
   }
   // blocked right-hand sides on a constant-coefficient 3-D stencil: line-marching SpMM
-  if (k > 1 && A->schedule == 4 && A->forced != 1) {
+  if (k > 1 && (A->schedule == 4 || A->schedule == 3) && A->forced != 1) {
     KbLines g;
-    if (kb_lines_geom(A, k, x, &g)) {
+    bool var = false;
+    if (kb_lines_geom(A, k, x, &g, &var)) {
       int rc;
-      if (dot == 0) rc = kb_launch_lines<0>(A, ws, g, x, y, mode, z, coef, w, out, st);
-      else if (dot == 1) rc = kb_launch_lines<1>(A, ws, g, x, y, mode, z, coef, w, out, st);
-      else rc = kb_launch_lines<2>(A, ws, g, x, y, mode, z, coef, w, out, st);
+      if (dot == 0) rc = kb_launch_lines<0>(A, ws, g, var, x, y, mode, z, coef, w, out, st);
+      else if (dot == 1) rc = kb_launch_lines<1>(A, ws, g, var, x, y, mode, z, coef, w, out, st);
+      else rc = kb_launch_lines<2>(A, ws, g, var, x, y, mode, z, coef, w, out, st);
       if (rc != KB_EUNSUPPORTED) return rc;
     }
   }
@@ -1183,7 +1217,11 @@ int kb_spmv(kb_csr_t A, kb_ws_t ws, int k, const double* x, double* y, int mode,
 int kb_spmm_is_lines(kb_csr_t A, int k, const double* x, int* yes) {
   KB_REQUIRE(A != nullptr && yes != nullptr, "null argument");
   KbLines g;
-  *yes = (k > 1 && A->schedule == 4 && A->forced != 1 && kb_lines_geom(A, k, x, &g)) ? 1 : 0;
+  bool var = false;
+  *yes = (k > 1 && (A->schedule == 4 || A->schedule == 3) && A->forced != 1 &&
+          kb_lines_geom(A, k, x, &g, &var))
+             ? 1
+             : 0;
   return KB_OK;
 }
 

@@ -17,7 +17,11 @@
 // L2 -> SM boundary instead of 7, DRAM sees X once (the +-Pz chunks were brought in by the CTAs
 // one plane away and are L2 hits: 126 MB of L2 against 8 MB planes).
 // Products, their order and rounding are those of every other schedule (kb_march_rows): results
-// are bit-identical to the row-wise kernel.  Rows next to a boundary skip absent diagonals through
+// are bit-identical to the row-wise kernel.
+// VAR = true: the same ring for matrices with this offset pattern and VARIABLE coefficients (schedule
+// "pattern"): the stored values of a chunk's rows (one contiguous range of the CSR value array)
+// ride in the slot of their line as a fourth TMA piece, the consumers read them from shared memory
+// (k lanes share a row: broadcast).  Streams 8 nnz more bytes per product, same x / y traffic.  Rows next to a boundary skip absent diagonals through
 // the per-row masks, so any matrix with this offset pattern and constant diagonals qualifies
 // (Dirichlet gaps, truncated last plane, row slabs of a partitioned matrix).
 #pragma once
@@ -43,6 +47,10 @@ struct KbLines {
   long long lpp;     // lines per plane (Pz / L), 0 = natural order
   long long nplanes; // ceil(nlines / lpp)
   int tail;          // entries of the last line (N - (nlines - 1) L)
+  // variable coefficients (VAR): the values of a chunk's rows travel in the same ring slot
+  int voff;          // offset of the value area in a slot (doubles) = 3 TR + 2 H
+  int vcap;          // its capacity (doubles, even): (TR / k) rows x 7 + 2
+  long long n_rows;
 };
 
 // lines [r0, r1) and chunk c of a work item; false for an empty item (plane-fastest order only)
@@ -66,9 +74,81 @@ __device__ __forceinline__ bool kb_lines_item(const KbLines& g, long long item, 
   return r1 > r0;
 }
 
-template <int RPT, int NS, int MINB, int DOT, bool WX>
+// Row sums of two entries with the coefficients read from shared memory (VAR): va[q] is the shared
+// address of the first stored value of entry q's row; the values follow in stored (ascending
+// column) order, so a full row uses va + 8 d and a boundary row the rank of d among its diagonals.
+template <int Q0>
+__device__ __forceinline__ void kb_lines_rows_var(const uint32_t (&a)[7], const unsigned* m,
+                                                  const uint32_t* va, double* sum, double* ctr) {
+  const bool allfull = m[Q0] == 127u && m[Q0 + 1] == 127u;
+  if (__all_sync(0xffffffffu, allfull)) {
+    double xa[7], xb[7], ca[7], cb[7];
+#pragma unroll
+    for (int d = 0; d < 7; ++d) {
+      xa[d] = kb_lds_f64<Q0 * 256 * 8>(a[d]);
+      xb[d] = kb_lds_f64<(Q0 + 1) * 256 * 8>(a[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < 7; ++d) {
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ca[d]) : "r"(va[Q0] + 8u * d));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cb[d]) : "r"(va[Q0 + 1] + 8u * d));
+    }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int d = 0; d < 7; ++d) {
+      s0 = __dadd_rn(s0, __dmul_rn(ca[d], xa[d]));
+      s1 = __dadd_rn(s1, __dmul_rn(cb[d], xb[d]));
+    }
+    sum[Q0] = s0;
+    sum[Q0 + 1] = s1;
+    ctr[Q0] = xa[3];
+    ctr[Q0 + 1] = xb[3];
+  } else {
+    double s0 = 0.0, s1 = 0.0;
+    ctr[Q0] = kb_lds_f64<Q0 * 256 * 8>(a[3]);
+    ctr[Q0 + 1] = kb_lds_f64<(Q0 + 1) * 256 * 8>(a[3]);
+    uint32_t v0 = va[Q0], v1 = va[Q0 + 1];
+#pragma unroll
+    for (int d = 0; d < 7; ++d) {
+      if ((m[Q0] >> d) & 1u) {
+        double c;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(c) : "r"(v0));
+        v0 += 8u;
+        s0 = __dadd_rn(s0, __dmul_rn(c, kb_lds_f64<Q0 * 256 * 8>(a[d])));
+      }
+      if ((m[Q0 + 1] >> d) & 1u) {
+        double c;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(c) : "r"(v1));
+        v1 += 8u;
+        s1 = __dadd_rn(s1, __dmul_rn(c, kb_lds_f64<(Q0 + 1) * 256 * 8>(a[d])));
+      }
+    }
+    sum[Q0] = s0;
+    sum[Q0 + 1] = s1;
+  }
+}
+
+// first / one-past-last stored value of the rows of chunk c of line `line` (VAR); b <= a: none
+__device__ __forceinline__ void kb_lines_vrange(const KbLines& g, const int32_t* __restrict__ rowptr,
+                                                long long line, int c, int TR, int& a, int& b) {
+  a = b = 0;
+  if (line < 0 || line >= g.nlines) return;
+  const long long lim = line == g.nlines - 1 ? g.tail : g.L;
+  const long long p0 = (long long)c * TR;
+  if (p0 >= lim) return;
+  const long long p1 = p0 + TR < lim ? p0 + TR : lim;
+  const long long ra = (line * g.L + p0) >> g.kshift;
+  long long rb = (line * g.L + p1) >> g.kshift;
+  if (rb > g.n_rows) rb = g.n_rows;
+  if (ra >= rb) return;
+  a = rowptr[ra];
+  b = rowptr[rb];
+}
+
+template <int RPT, int NS, int MINB, int DOT, bool WX, bool VAR = false>
 __global__ void __launch_bounds__(256 + 32, MINB)
 kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals cv,
+                     const int32_t* __restrict__ rowptr, const double* __restrict__ vals,
                      const double* __restrict__ x, double* __restrict__ y, int mode,
                      const double* __restrict__ z, const double* __restrict__ coef,
                      const double* __restrict__ w, double* __restrict__ out, KbRed rd) {
@@ -96,15 +176,33 @@ kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals 
   double acc = 0.0;
   if (warp == 8) {
     // ---------------------------------------------- producer: one slot per line ---
-    if ((tid & 31) == 0) {
+    // Lane 0 issues the copies.  VAR: all 32 lanes fetch the value ranges of the item's next 32
+    // lines at once (one round of global latency per 32 slots instead of one per slot).
+    {
+      const int lane = tid & 31;
       const uint64_t pol = kb_policy_evict_last();
+      const uint64_t polv = kb_policy_evict_first();
       unsigned cnt = 0;
       for (long long item = blockIdx.x; item < g.nitems; item += gridDim.x) {
         int c;
         long long r0, r1;
-        if (!kb_lines_item(g, item, c, r0, r1)) continue;
+        if (!kb_lines_item(g, item, c, r0, r1)) continue;  // warp-uniform
         const int nload = (int)(r1 - r0) + 2;
+        int my_a = 0, my_b = 0;
         for (int l = 0; l < nload; ++l, ++cnt) {
+          int va = 0, vb = 0;
+          if (VAR) {
+            const bool inside_l = l >= 1 && l <= nload - 2;
+            if (inside_l && ((l - 1) & 31) == 0) {  // lines r0 + (l-1) ... + 31 of this item
+              my_a = my_b = 0;
+              if (l - 1 + lane < nload - 2)
+                kb_lines_vrange(g, rowptr, r0 + (l - 1) + lane, c, TR, my_a, my_b);
+            }
+            va = __shfl_sync(0xffffffffu, my_a, (l - 1) & 31);
+            vb = __shfl_sync(0xffffffffu, my_b, (l - 1) & 31);
+            if (!inside_l) va = vb = 0;
+          }
+          if (lane != 0) continue;
           const int slot = (int)(cnt % NS);
           const unsigned use = cnt / NS;
           if (use > 0) kb_mbar_wait(&s_empty[slot], (use - 1u) & 1u);
@@ -125,8 +223,14 @@ kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals 
             dst[p] = base[p] + (lo[p] - s0[p]);
             if (hi[p] > lo[p]) total += (uint32_t)(hi[p] - lo[p]) * 8u;
           }
+          // VAR: the stored values of this line's rows, from an even index (16-byte source)
+          const int va0 = va & ~1;
+          const uint32_t vbytes = vb > va ? (uint32_t)(((vb - va0) + 1) & ~1) * 8u : 0u;
+          total += vbytes;
           if (total > 0) {
             kb_mbar_expect_tx(&s_full[slot], total);
+            if (vbytes > 0)
+              kb_bulk_g2s_hint(sl + g.voff, vals + va0, vbytes, &s_full[slot], polv);
 #pragma unroll
             for (int p = 0; p < 3; ++p)
               if (hi[p] > lo[p])
@@ -162,10 +266,12 @@ kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals 
       long long e = (r0 - 2) * g.L + pos0;
       unsigned mn[RPT];
       double zn[RPT], wn[RPT];
+      int rpn[RPT], a0n = 0;  // VAR: first stored value of the entry's row / of the chunk's rows
 #pragma unroll
       for (int q = 0; q < RPT; ++q) {
         mn[q] = 0u;
         zn[q] = wn[q] = 0.0;
+        rpn[q] = 0;
       }
       for (int l = 0; l < nload; ++l, ++cnt, e += g.L) {
         const int slot = (int)(cnt % NS);
@@ -176,8 +282,14 @@ kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals 
         unsigned m[RPT];
         double zv[RPT], wv[RPT];
         bool okq[RPT];
+        int rp[RPT];
+        const int a0 = a0n;
         const long long en = e + g.L;
         const uint16_t* const mp = masks + (en >> g.kshift);
+        if (VAR) {
+          a0n = 0;
+          if (limn > c * TR) a0n = rowptr[(en - tid) >> g.kshift] & ~1;  // row of the chunk's entry 0
+        }
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
           const int pos = pos0 + q * 256;
@@ -185,10 +297,12 @@ kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals 
           m[q] = mn[q];
           zv[q] = zn[q];
           wv[q] = wn[q];
+          if (VAR) rp[q] = rpn[q];
           // operands of the next pass (line rc + 1) are requested one pass ahead
           const bool nok = pos < limn;
           mn[q] = nok ? (unsigned)mp[q * mq] : 0u;
           zn[q] = wn[q] = 0.0;
+          if (VAR) rpn[q] = nok ? rowptr[(en >> g.kshift) + q * mq] : 0;
           if (nok) {
             if (mode != 0) zn[q] = z[en + q * 256];
             if (DOT == 1 && !WX) wn[q] = w[en + q * 256];
@@ -208,8 +322,17 @@ kb_spmm_lines_kernel(KbLines g, const uint16_t* __restrict__ masks, KbConstVals 
           a[5] = wnext + own;
           a[6] = wcur + ohi;
           double sum[RPT], ctr[RPT];
-          kb_march_rows<7, 0, 2>(a, m, cv, sum, ctr);
-          if constexpr (RPT == 4) kb_march_rows<7, 2, 2>(a, m, cv, sum, ctr);
+          if constexpr (VAR) {
+            uint32_t va[RPT];
+#pragma unroll
+            for (int q = 0; q < RPT; ++q)
+              va[q] = wcur + (uint32_t)(g.voff + (okq[q] ? rp[q] - a0 : 0)) * 8u;
+            kb_lines_rows_var<0>(a, m, va, sum, ctr);
+            if constexpr (RPT == 4) kb_lines_rows_var<2>(a, m, va, sum, ctr);
+          } else {
+            kb_march_rows<7, 0, 2>(a, m, cv, sum, ctr);
+            if constexpr (RPT == 4) kb_march_rows<7, 2, 2>(a, m, cv, sum, ctr);
+          }
 #pragma unroll
           for (int q = 0; q < RPT; ++q) {
             if (okq[q]) {

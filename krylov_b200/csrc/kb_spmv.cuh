@@ -1293,14 +1293,40 @@ kb_spmv_halo_add_kernel(int64_t n_brows, int k, double sign, const int32_t* __re
 }
 
 // ----------------------------------------------------------- row statistics --
-__global__ void kb_max_row_len_kernel(int64_t n_rows, const int32_t* __restrict__ rowptr,
-                                      int* out) {
-  int m = 0;
+// out[0] = longest row; out[1] |= 1: rowptr[0] != 0, 2: a row pointer decreases, 4: rowptr[n] != nnz
+// (structure check of kb_csr_create: a malformed matrix is refused instead of read out of bounds)
+__global__ void kb_max_row_len_kernel(int64_t n_rows, int64_t nnz,
+                                      const int32_t* __restrict__ rowptr, int* out) {
+  int m = 0, bad = 0;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
-       r += (int64_t)gridDim.x * blockDim.x)
-    m = max(m, rowptr[r + 1] - rowptr[r]);
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const int len = rowptr[r + 1] - rowptr[r];
+    if (len < 0) bad |= 2;
+    m = max(m, len);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (rowptr[0] != 0) bad |= 1;
+    if ((int64_t)rowptr[n_rows] != nnz) bad |= 4;
+  }
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, m);
+    if (bad) atomicOr(out + 1, bad);
+  }
+}
+
+// out[1] |= 8 if a column index lies outside [0, n_cols)
+__global__ void __launch_bounds__(256)
+kb_colidx_check_kernel(int64_t nnz, int64_t n_cols, const int32_t* __restrict__ colidx, int* out) {
+  int bad = 0;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz;
+       j += (int64_t)gridDim.x * blockDim.x) {
+    const int c = colidx[j];
+    if (c < 0 || (int64_t)c >= n_cols) bad = 8;
+  }
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicOr(out + 1, bad);
 }
 
 // ------------------------------------------------------- 7-point generator --

@@ -863,3 +863,67 @@ def test_c_side_loops_equal_per_launch_loops(k):
         assert ic.numsteps == ip.numsteps and ic.success == ip.success
         np.testing.assert_array_equal(np.asarray(ic.resnorms), np.asarray(ip.resnorms))
         np.testing.assert_array_equal(ic.xk, ip.xk)
+
+
+@pytest.mark.parametrize("chunk,order", [(0, 1), (1, 0)])
+@pytest.mark.parametrize("k", [8, 16, 32])
+def test_line_marching_spmm_variable_coefficients_bit_exact(k, chunk, order):
+    """kb_spmm_lines_kernel<VAR>: the 7-point pattern with VARIABLE coefficients (schedule
+    "pattern"), values streamed through the ring slots: bit-identical to SciPy's csr_matvecs and
+    to the row-wise kernel in every mode; lines shorter / longer than a chunk, truncated last
+    plane, missing entries (rows with fewer than 7 diagonals inside the grid)."""
+    import ctypes
+
+    from krylov_b200._lib import check, lib
+
+    def is_lines(Ad, x):
+        yes = ctypes.c_int(0)
+        check(lib.kb_spmm_is_lines(Ad.handle, k, x.data_ptr(), ctypes.byref(yes)))
+        return bool(yes.value)
+
+    lib.kb_tune(16, 2)
+    lib.kb_tune(18, chunk)
+    lib.kb_tune(19, order)
+    try:
+        for (nx, ny, nz), ch in (((70, 5, 4), 0), ((33, 4, 5), 3), ((130, 3, 3), 1), ((16, 16, 16), 0)):
+            lib.kb_tune(17, ch)
+            A = st.to_scipy(st.stencil7_csr(nx, ny, nz))
+            A.data = rng.standard_normal(A.nnz)  # same pattern, every value different
+            if (nx, ny, nz) == (33, 4, 5):
+                A = A[:-7, :-7].tocsr()
+            if (nx, ny, nz) == (16, 16, 16):  # knock out some interior entries: masks with holes
+                A = A.tolil()
+                for r_ in (100, 101, 777, 2000):
+                    A[r_, r_ + 1] = 0.0
+                    A[r_, r_ - 16] = 0.0
+                A = A.tocsr()
+                A.eliminate_zeros()
+            n = A.shape[0]
+            Ad = kb.CsrMatrix.from_scipy(A)
+            assert Ad.info()["schedule"] == "pattern"
+            Ar = kb.CsrMatrix.from_scipy(A).set_schedule("rowwise")
+            X, Z, W = (rng.standard_normal((n, k)) for _ in range(3))
+            coef = rng.standard_normal(k)
+            x, z, w = (torch.from_numpy(a).cuda() for a in (X, Z, W))
+            cf = torch.from_numpy(coef).cuda()
+            assert is_lines(Ad, x) and not is_lines(Ar, x)
+            ops = Ops(n, k)
+            y, yr = torch.empty_like(x), torch.empty_like(x)
+            out, outr = ops.slots(1)[0], ops.slots(1)[0]
+            t = A @ X
+            for mode, ref in ((0, t), (1, t - coef * Z), (2, Z - t)):
+                for dot, ww in ((0, w), (1, w), (1, x), (2, w)):
+                    y.fill_(float("nan"))
+                    ops.spmv(Ad, x, y, mode=mode, z=z, coef=cf, dot=dot, w=ww, out=out)
+                    ops.spmv(Ar, x, yr, mode=mode, z=z, coef=cf, dot=dot, w=ww, out=outr)
+                    np.testing.assert_array_equal(y.cpu().numpy(), ref)
+                    assert torch.equal(y, yr)
+                    if dot:
+                        Wn = X if ww is x else W
+                        dref = np.einsum("ij,ij->j", Wn if dot == 1 else ref, ref)
+                        np.testing.assert_allclose(out.cpu().numpy(), dref, rtol=1e-12, atol=1e-10)
+    finally:
+        lib.kb_tune(16, 1)
+        lib.kb_tune(17, 0)
+        lib.kb_tune(18, 0)
+        lib.kb_tune(19, 1)

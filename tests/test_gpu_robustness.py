@@ -194,3 +194,21 @@ def test_preconditioned_gmres_sparse_vs_oracle(k):
         live = ro / ro[0] >= 1e-5
         assert np.all(np.abs(rg - ro)[live] <= 1e-7 * ro[live]), kw
         assert np.linalg.norm(sol - so) <= 1e-7 * np.linalg.norm(so), kw
+
+
+def test_malformed_csr_is_refused():
+    """kb_csr_create checks the structure once (rowptr[0], monotone row pointers, rowptr[n] ==
+    nnz, column range): a malformed matrix raises instead of being read out of bounds."""
+    import krylov_b200 as kb
+
+    rp = np.array([0, 2, 3], dtype=np.int32)
+    ci = np.array([0, 1, 1], dtype=np.int32)
+    va = np.ones(3)
+    kb.CsrMatrix(rp, ci, va, (2, 2))  # well-formed
+    for bad_rp, bad_ci in ((np.array([1, 2, 3], dtype=np.int32), ci),
+                           (np.array([0, 3, 2], dtype=np.int32), ci),
+                           (np.array([0, 2, 2], dtype=np.int32), ci),
+                           (rp, np.array([0, 2, 1], dtype=np.int32)),
+                           (rp, np.array([0, -1, 1], dtype=np.int32))):
+        with pytest.raises(kb.KrylovB200Error, match="malformed CSR"):
+            kb.CsrMatrix(bad_rp, bad_ci, va, (2, 2))

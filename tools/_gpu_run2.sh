@@ -1,2 +1,3 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "merge_schedule_vs_scipy and powerlaw" 2>&1 | grep -v Warning | tail -40
+python bench.py --steps 20 --warmup 3 --no-cpu --no-configs --no-general --no-parity --e2e-trace > gpurun_out/r2q_e2e.json 2> gpurun_out/r2q_e2e_trace.txt
+grep e2e-trace gpurun_out/r2q_e2e_trace.txt
