@@ -256,6 +256,15 @@ int kb_cg_is_persistent(kb_ws_t ws, const kb_cg_state* s, int* yes);
 int kb_cg_run_timed(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x_pending,
                     void* stream, float* ms, float* total_ms);
 
+/* --- per-column scalar arithmetic on device slots ---------------------- */
+/* out[c] = A op B with A = a ? a[c] : sa, B = b ? b[c] : sb, c < k.  op: 0 A+B, 1 A-B, 2 A*B,
+ * 3 A/B, 4 sqrt(A), 5 |A|, 6 -A, 7 (A != 0 ? A : B), 8 A.  One IEEE operation per launch: the
+ * scalar recurrences of the short-recurrence solvers (bicgstab.py:100-133, qmr.py:101-146,
+ * symmlq.py:108-150 ...) stay on the device with the host's bits and without a read-back per
+ * inner product. */
+int kb_scalar_op(kb_ws_t ws, int k, int op, const double* a, const double* b, double sa, double sb,
+                 double* out, void* stream);
+
 /* --- generic vector kernels (fallback path for M/Ml/Mr/custom inner) ---- */
 /* y += sign * coef[c] * x   (product rounded, then sum: NumPy temporaries) */
 int kb_axpy(kb_ws_t ws, int64_t n, int k, double sign, const double* coef, const double* x,

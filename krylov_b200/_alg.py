@@ -15,18 +15,102 @@ import torch
 from .device import Ops
 
 
+_ADD, _SUB, _MUL, _DIV, _SQRT, _ABS, _NEG, _NZ, _COPY = range(9)
+
+
+class DevScalar:
+    """Per-column scalars (k,) that stay on the device.  Arithmetic (+ - * /, negation, abs, sqrt,
+    ** 2, with other DevScalars, Python numbers and NumPy (k,) arrays) is evaluated at once by
+    ``kb_scalar_op`` -- one IEEE operation per launch, the host's bits -- and never synchronises;
+    ``host()`` is the one read-back.  The short-recurrence solvers keep their NumPy-style scalar
+    statements and lose the device->host round trip per inner product."""
+
+    __slots__ = ("t", "alg")
+    __array_priority__ = 1000.0
+
+    def __init__(self, alg, t):
+        self.alg, self.t = alg, t
+
+    def host(self):
+        return self.t.cpu().numpy().copy()
+
+    # ---- evaluation
+    def _operand(self, v):
+        """-> (device tensor or None, immediate)"""
+        if isinstance(v, DevScalar):
+            return v.t, 0.0
+        if isinstance(v, (int, float, np.floating, np.integer)):
+            return None, float(v)
+        a = np.asarray(v, dtype=np.float64)
+        if a.size == 1:
+            return None, float(a.reshape(-1)[0])
+        return self.alg.coef(a), 0.0
+
+    def _op(self, code, a, b=0.0):
+        ta, sa = self._operand(a)
+        tb, sb = self._operand(b)
+        out = torch.empty(self.alg.prob.k, dtype=torch.float64, device=self.alg.prob.device)
+        self.alg.ops.scalar_op(code, ta, tb, sa, sb, out)
+        return DevScalar(self.alg, out)
+
+    def __add__(self, o): return self._op(_ADD, self, o)
+    def __radd__(self, o): return self._op(_ADD, o, self)
+    def __sub__(self, o): return self._op(_SUB, self, o)
+    def __rsub__(self, o): return self._op(_SUB, o, self)
+    def __mul__(self, o): return self._op(_MUL, self, o)
+    def __rmul__(self, o): return self._op(_MUL, o, self)
+    def __truediv__(self, o): return self._op(_DIV, self, o)
+    def __rtruediv__(self, o): return self._op(_DIV, o, self)
+    def __neg__(self): return self._op(_NEG, self)
+    def __abs__(self): return self._op(_ABS, self)
+
+    def __pow__(self, e):
+        if e == 2:
+            return self._op(_MUL, self, self)
+        raise TypeError("DevScalar supports ** 2 only")
+
+    def sqrt(self): return self._op(_SQRT, self)
+    def nz(self, fill=1.0): return self._op(_NZ, self, fill)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != "__call__" or kwargs:
+            return NotImplemented
+        binary = {np.add: _ADD, np.subtract: _SUB, np.multiply: _MUL, np.true_divide: _DIV}
+        unary = {np.sqrt: _SQRT, np.absolute: _ABS, np.negative: _NEG}
+        if ufunc in binary and len(inputs) == 2:
+            return self._op(binary[ufunc], inputs[0], inputs[1])
+        if ufunc in unary and len(inputs) == 1:
+            return self._op(unary[ufunc], inputs[0])
+        if ufunc is np.square:
+            return self._op(_MUL, inputs[0], inputs[0])
+        raise TypeError(f"DevScalar does not implement {ufunc.__name__}")
+
+    def __array__(self, *a, **kw):
+        raise TypeError("DevScalar stays on the device: call to_host() where the host needs it")
+
+
+def to_host(v):
+    """(k,) float64 host array of a scalar statement's value (DevScalar: the one read-back)."""
+    return v.host() if isinstance(v, DevScalar) else v
+
+
 class Alg:
-    def __init__(self, prob, inner=None):
+    def __init__(self, prob, inner=None, lazy=False):
         self.prob = prob
         self.ops = Ops(prob.n, prob.k, prob.device, comm=prob.comm)
         self._user_inner = None if inner is None else prob.inner(inner)
         self._slot = self.ops.slots(1)[0]
         self._cbuf = self.ops.slots(1)[0]
+        # lazy: inner products are returned as DevScalar (no read-back); only with the default
+        # inner product, and only for callers written for it (the short-recurrence solvers)
+        self.lazy = bool(lazy) and self._user_inner is None
 
     # ---- scalars
     def coef(self, a):
         """host (k,) -> device (k,) coefficient tensor (a fresh one per call:
         launches are asynchronous and must not see a later overwrite)."""
+        if isinstance(a, DevScalar):
+            return a.t  # immutable: every operation wrote a tensor of its own
         a = np.array(np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(-1),
                                      (self.prob.k,)))  # writable copy
         return torch.from_numpy(a).to(self.prob.device)
@@ -36,6 +120,10 @@ class Alg:
         device reduction (_helpers.py:101-110); else the user's callable."""
         if self._user_inner is not None:
             return self._user_inner(x, y)
+        if self.lazy:
+            out = torch.empty(self.prob.k, dtype=torch.float64, device=self.prob.device)
+            self.ops.dot(x, y, out)
+            return DevScalar(self, out)
         self.ops.dot(x, y, self._slot)
         return self._slot.cpu().numpy().copy()
 
@@ -89,8 +177,10 @@ class Alg:
         return r
 
 
-def nz(d):
-    return np.where(d != 0, d, 1.0)
+def nz(d, fill=1.0):
+    if isinstance(d, DevScalar):
+        return d.nz(fill)
+    return np.where(d != 0, d, fill)
 
 
 def as_resnorm(prob, v):

@@ -5,7 +5,45 @@
 // same arguments as the per-launch path of krylov_b200/minres.py and gmres.py.
 #include "kb_handles.cuh"
 
+// Per-column scalar arithmetic on device slots: what the reference does with NumPy (k,) arrays
+// between two vector statements of the short-recurrence solvers (bicgstab.py:100-133,
+// qmr.py:101-146, symmlq.py:108-150, ...).  One IEEE operation per launch, so the values equal
+// the host's bit for bit; keeping them on the device removes the read-back per inner product.
+__global__ void kb_scalar_op_kernel(int k, int op, const double* __restrict__ a,
+                                    const double* __restrict__ b, double sa, double sb,
+                                    double* __restrict__ out, KbRed rd) {
+  if (kb_gated(rd)) return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  const double A = a != nullptr ? a[c] : sa;
+  const double B = b != nullptr ? b[c] : sb;
+  double r;
+  switch (op) {
+    case 0: r = __dadd_rn(A, B); break;
+    case 1: r = __dsub_rn(A, B); break;
+    case 2: r = __dmul_rn(A, B); break;
+    case 3: r = __ddiv_rn(A, B); break;
+    case 4: r = __dsqrt_rn(A); break;
+    case 5: r = fabs(A); break;
+    case 6: r = -A; break;
+    case 7: r = A != 0.0 ? A : B; break;  // nz(A) with B as the replacement
+    default: r = A; break;
+  }
+  out[c] = r;
+}
+
 extern "C" {
+
+int kb_scalar_op(kb_ws_t ws, int k, int op, const double* a, const double* b, double sa, double sb,
+                 double* out, void* stream) {
+  KB_REQUIRE(ws != nullptr && out != nullptr, "null argument");
+  KB_REQUIRE(k >= 1 && k <= KB_MAX_K, "k out of range");
+  KB_REQUIRE(op >= 0 && op <= 8, "unknown operation");
+  kb_scalar_op_kernel<<<(k + 127) / 128, 128, 0, (cudaStream_t)stream>>>(k, op, a, b, sa, sb, out,
+                                                                         kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
 
 int kb_minres_run(kb_ws_t ws, const kb_minres_run_state* s, int i0, int n_iters, void* stream) {
   KB_REQUIRE(ws != nullptr && s != nullptr, "null argument");

@@ -222,6 +222,12 @@ class Ops:
         check(lib.kb_lincomb(self.ws.handle, self.n, self.k, ptr(ca), ptr(x), ptr(cb), ptr(y),
                              ptr(out), cur_stream()))
 
+    def scalar_op(self, op, a, b, sa, sb, out):
+        """out = A op B on (k,) device slots (kb_scalar_op); a / b None: the immediates sa / sb."""
+        self.launches += 1
+        check(lib.kb_scalar_op(self.ws.handle, self.k, int(op), ptr(a), ptr(b), float(sa), float(sb),
+                               ptr(out), cur_stream()))
+
     def xpby(self, y, x, coef):
         self.launches += 1
         check(lib.kb_xpby(self.ws.handle, self.n, self.k, ptr(x), ptr(coef), ptr(y), cur_stream()))

@@ -5,8 +5,11 @@ bicg.py, qmr.py, cgne.py, cgnr.py, cgr.py, gcr.py, chebyshev.py, symmlq.py).
 
 They run on the *general* device path: every vector statement of the reference loop is one kernel
 launch through the C ABI (kb_spmv incl. the transposed matrix for ``rmatvec``, kb_dot, kb_axpy,
-kb_xpby, kb_lincomb, kb_div_scale) on (n, k) CUDA tensors, the per-column scalars live on the host
-as in the reference.  No statement is evaluated on the CPU and there is no CPU fallback.
+kb_xpby, kb_lincomb, kb_div_scale) on (n, k) CUDA tensors.  With the default inner product the
+per-column scalars stay on the device too (``_alg.DevScalar``: every scalar statement of the
+reference is one ``kb_scalar_op`` launch with the host's IEEE result); the only read-back per
+iteration is the residual norm for the stopping test.  A user ``inner`` keeps host scalars as in
+the reference.  No statement is evaluated on the CPU and there is no CPU fallback.
 
 The driver all of them share in the reference (initial residual, ``max(tol * r0, atol)``,
 explicit-residual confirmation, ``maxiter``, callback, Info) is written once here (``_Drive``).
@@ -16,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ._alg import Alg, nz
+from ._alg import Alg, nz, to_host
 from .operators import Info, Problem
 
 __all__ = ["bicgstab", "cgs", "bicg", "qmr", "cgne", "cgnr", "cgr", "gcr", "chebyshev", "symmlq"]
@@ -25,7 +28,7 @@ __all__ = ["bicgstab", "cgs", "bicg", "qmr", "cgne", "cgnr", "cgr", "gcr", "cheb
 class _Drive:
     def __init__(self, A, b, x0, inner, tol, atol, maxiter, callback):
         self.prob = prob = Problem(A, b, x0)
-        self.alg = alg = Alg(prob, inner)
+        self.alg = alg = Alg(prob, inner, lazy=True)
         self.A, self.b = prob.A, prob.b
         self.tol, self.atol, self.maxiter, self.callback = tol, atol, maxiter, callback
         self.x = prob.x0  # Problem clones a user x0; zeros otherwise
@@ -59,20 +62,20 @@ class _Drive:
             with prob.on_device():
                 if self.callback is not None:
                     self.callback(*cb_vecs())
-                res = [first]
+                res = [to_host(first)]
                 crit = np.maximum(self.tol * res[0], self.atol)
                 k, ok, xo = 0, False, None
                 while True:
                     if np.all(res[-1] <= crit):
                         xo = xout()
-                        res[-1] = norm(alg.residual(self.A, self.b, xo))
+                        res[-1] = to_host(norm(alg.residual(self.A, self.b, xo)))
                         if np.all(res[-1] <= crit):
                             ok = True
                             break
                     if k == self.maxiter:
                         xo = xout()
                         break
-                    res.append(step(k, crit))
+                    res.append(to_host(step(k, crit)))
                     k += 1
             prob.launches = alg.ops.launches
             xk = prob.to_user(xo) if xo is not None else None
@@ -80,12 +83,12 @@ class _Drive:
         with prob.on_device():
             if self.callback is not None:
                 self.callback(*cb_vecs())
-            res = [first]
+            res = [to_host(first)]
             crit = np.maximum(self.tol * res[0], self.atol)
             k, ok = 0, False
             while True:
                 if np.all(res[-1] <= crit):
-                    res[-1] = norm(alg.residual(self.A, self.b, self.x))
+                    res[-1] = to_host(norm(alg.residual(self.A, self.b, self.x)))
                     if np.all(res[-1] <= crit):
                         ok = True
                         break
@@ -93,12 +96,12 @@ class _Drive:
                     break
                 out = step(k, crit)
                 if isinstance(out, tuple):
-                    res[-1] = out[1]
+                    res[-1] = to_host(out[1])
                     ok = True
                     break
                 if self.callback is not None:
                     self.callback(*cb_vecs())
-                res.append(out)
+                res.append(to_host(out))
                 k += 1
         prob.launches = alg.ops.launches
         xk = prob.to_user(self.x)
@@ -119,14 +122,14 @@ def bicgstab(A, b, Ml=None, Mr=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15
     def step(k, crit):
         rho_old, s["rho"] = s["rho"], alg.inner(shadow, s["r"])
         beta = s["rho"] * s["alpha"] / nz(rho_old * s["omega"])
-        t = alg.lincomb(s["p"], None, s["v"], -np.asarray(s["omega"]), out=s["p"])  # p - omega v
+        t = alg.lincomb(s["p"], None, s["v"], -s["omega"], out=s["p"])  # p - omega v
         s["p"] = alg.lincomb(s["r"], None, t, beta, out=t)                          # r + beta (.)
         y = alg.apply(Mr, alg.apply(Ml, s["p"]))
         s["v"] = Aop(y)
         s["alpha"] = s["rho"] / nz(alg.inner(shadow, s["v"]))
         half_r = alg.lincomb(s["r"], None, s["v"], -s["alpha"])
         half_x = alg.lincomb(d.x, None, y, s["alpha"])
-        rn = norm(alg.apply(Ml, alg.residual(Aop, d.b, d.x)))  # :117-122, the OLD x
+        rn = to_host(norm(alg.apply(Ml, alg.residual(Aop, d.b, d.x))))  # :117-122, the OLD x
         if np.all(rn <= crit):
             return ("leave", rn)
         Ml_s = alg.apply(Ml, half_r)
@@ -440,7 +443,7 @@ def symmlq(A, b, M=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15, maxiter=No
 
     def cg_point():
         c0 = s["c"][0]
-        zc = s["zeta"][0] / np.where(c0 != 0.0, c0, 1.0e-15)
+        zc = s["zeta"][0] / nz(c0, 1.0e-15)
         return alg.lincomb(d.x, None, s["w_bar"], zc)
 
     def step(k, crit):
@@ -451,7 +454,7 @@ def symmlq(A, b, M=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15, maxiter=No
             s["u"] = alg.lincomb(s["z"], rb)
             c0, s0 = s["c"][0], s["s"][0]
             w = alg.lincomb(s["w_bar"], c0, s["u"], s0)
-            alg.lincomb(s["w_bar"], -np.asarray(s0), s["u"], c0, out=s["w_bar"])
+            alg.lincomb(s["w_bar"], -s0, s["u"], c0, out=s["w_bar"])
             alg.axpy(d.x, s["zeta"][0], w)
             s["zeta"][2], s["zeta"][1] = s["zeta"][1], s["zeta"][0]
         r = Aop(s["u"])  # Lanczos

@@ -70,7 +70,7 @@ class _Ops:
 
 
 class FakeAlg:
-    def __init__(self, prob, inner=None):
+    def __init__(self, prob, inner=None, lazy=False):  # lazy: device-resident scalars (GPU only)
         self.prob, self.ops = prob, _Ops()
         self._user_inner = None if inner is None else prob.inner(inner)
 
