@@ -264,6 +264,12 @@ int kb_cg_run_timed(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x
  * inner product. */
 int kb_scalar_op(kb_ws_t ws, int k, int op, const double* a, const double* b, double sa, double sb,
                  double* out, void* stream);
+/* hist[step*k + c] = val[c]; if val[c] <= crit[c] for every column: *stop_at = step.  The loop
+ * condition of the short-recurrence drivers (`resnorms[-1] > criterion`) on the device: with the
+ * workspace gate, iterations can be enqueued ahead of the host's read-back and become no-ops once
+ * an earlier step met the criterion. */
+int kb_record(kb_ws_t ws, int k, int step, const double* val, const double* crit, double* hist,
+              int* stop_at, void* stream);
 
 /* --- generic vector kernels (fallback path for M/Ml/Mr/custom inner) ---- */
 /* y += sign * coef[c] * x   (product rounded, then sum: NumPy temporaries) */

@@ -104,6 +104,7 @@ class Alg:
         # lazy: inner products are returned as DevScalar (no read-back); only with the default
         # inner product, and only for callers written for it (the short-recurrence solvers)
         self.lazy = bool(lazy) and self._user_inner is None
+        self._const = {}
 
     # ---- scalars
     def coef(self, a):
@@ -111,6 +112,14 @@ class Alg:
         launches are asynchronous and must not see a later overwrite)."""
         if isinstance(a, DevScalar):
             return a.t  # immutable: every operation wrote a tensor of its own
+        if isinstance(a, (int, float)):  # constants (1.0, -1.0, fixed step sizes): upload once
+            t = self._const.get(float(a))
+            if t is None:
+                if len(self._const) > 64:
+                    self._const.clear()
+                t = self._const[float(a)] = torch.full((self.prob.k,), float(a), dtype=torch.float64,
+                                                       device=self.prob.device)
+            return t
         a = np.array(np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(-1),
                                      (self.prob.k,)))  # writable copy
         return torch.from_numpy(a).to(self.prob.device)

@@ -32,7 +32,34 @@ __global__ void kb_scalar_op_kernel(int k, int op, const double* __restrict__ a,
   out[c] = r;
 }
 
+// hist[step * k + c] = val[c]; all columns val <= crit -> *stop_at = step.  The stopping test of
+// the short-recurrence drivers on the device (bicgstab.py:96-99, cgs.py:88-91, ...: the loop
+// condition `resnorms[-1] > criterion`), so that iterations can be enqueued ahead of the read-back.
+__global__ void __launch_bounds__(KB_MAX_K)
+kb_record_kernel(int k, int step, const double* __restrict__ val, const double* __restrict__ crit,
+                 double* __restrict__ hist, int* __restrict__ stop_at, KbRed rd) {
+  if (kb_gated(rd)) return;
+  int ok = 1;
+  if (threadIdx.x < k) {
+    const double v = val[threadIdx.x];
+    hist[(size_t)step * k + threadIdx.x] = v;
+    ok = (v <= crit[threadIdx.x]) ? 1 : 0;
+  }
+  const int all_ok = __syncthreads_and(ok);
+  if (all_ok && threadIdx.x == 0) *stop_at = step;
+}
+
 extern "C" {
+
+int kb_record(kb_ws_t ws, int k, int step, const double* val, const double* crit, double* hist,
+              int* stop_at, void* stream) {
+  KB_REQUIRE(ws != nullptr && val && crit && hist && stop_at, "null argument");
+  KB_REQUIRE(k >= 1 && k <= KB_MAX_K, "k out of range");
+  kb_record_kernel<<<1, KB_MAX_K, 0, (cudaStream_t)stream>>>(k, step, val, crit, hist, stop_at,
+                                                             kb_red(ws));
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
 
 int kb_scalar_op(kb_ws_t ws, int k, int op, const double* a, const double* b, double sa, double sb,
                  double* out, void* stream) {

@@ -228,6 +228,13 @@ class Ops:
         check(lib.kb_scalar_op(self.ws.handle, self.k, int(op), ptr(a), ptr(b), float(sa), float(sb),
                                ptr(out), cur_stream()))
 
+    def record(self, step, val, crit, hist_ptr, stop_at):
+        """hist[step] = val; every column <= crit -> stop_at = step (kb_record); hist_ptr: raw
+        device address of history row 0."""
+        self.launches += 1
+        check(lib.kb_record(self.ws.handle, self.k, int(step), ptr(val), ptr(crit), hist_ptr,
+                            ptr(stop_at), cur_stream()))
+
     def xpby(self, y, x, coef):
         self.launches += 1
         check(lib.kb_xpby(self.ws.handle, self.n, self.k, ptr(x), ptr(coef), ptr(y), cur_stream()))

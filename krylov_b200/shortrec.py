@@ -24,6 +24,9 @@ from .operators import Info, Problem
 
 __all__ = ["bicgstab", "cgs", "bicg", "qmr", "cgne", "cgnr", "cgr", "gcr", "chebyshev", "symmlq"]
 
+_AHEAD = 4  # iterations enqueued ahead of the host's read-back (gated on the device)
+_INT_MAX = 2**31 - 1
+
 
 class _Drive:
     def __init__(self, A, b, x0, inner, tol, atol, maxiter, callback):
@@ -51,60 +54,101 @@ class _Drive:
     def user(self, *vecs):
         return tuple(self.prob.to_user(v) for v in vecs)
 
-    def run(self, norm, step, first, cb_vecs, xout=None):
-        """step(k, crit) advances self.x and returns the new residual norm (host (k,) array), or
-        ("leave", resnorm) to finish successfully at once (bicgstab.py:119-122).  cb_vecs() gives
-        the callback's arguments in the caller's array kind.  xout(): the point that is checked
-        and returned when it is not self.x itself (symmlq's CG point; the step then calls the
-        callback on its own)."""
+    # ---- state the look-ahead has to be able to roll back (see run)
+    def track(self, *containers):
+        """The dicts / lists in which a solver keeps what changes from step to step (buffer
+        references, DevScalars, per-step lists).  Tensors are only ever modified by gated kernels,
+        so restoring the references restores the state."""
+        self._tracked = containers
+
+    def _snapshot(self):
+        snap = [self.x]
+        for c in self._tracked:
+            if isinstance(c, dict):
+                snap.append({k: (list(v) if isinstance(v, list) else v) for k, v in c.items()})
+            else:
+                snap.append(list(c))
+        return snap
+
+    def _restore(self, snap):
+        self.x = snap[0]
+        for c, saved in zip(self._tracked, snap[1:]):
+            if isinstance(c, dict):
+                c.clear()
+                c.update({k: (list(v) if isinstance(v, list) else v) for k, v in saved.items()})
+            else:
+                c[:] = saved
+
+    def run(self, norm, step, first, cb_vecs, xout=None, ahead=True):
+        """step(k, crit) advances self.x and returns the new residual norm, or ("leave", resnorm)
+        to finish successfully at once (bicgstab.py:119-122).  cb_vecs() gives the callback's
+        arguments in the caller's array kind.  xout(): the point that is checked and returned when
+        it is not self.x itself (symmlq's CG point; the step then calls the callback on its own).
+
+        With device-resident scalars (default inner product, no callback, ``ahead``) up to
+        ``_AHEAD`` iterations are enqueued before the host reads anything back: ``kb_record``
+        applies the loop condition on the device and the workspace gate turns every launch behind
+        the step that met the criterion into a no-op; the host then rolls its own references back
+        to that step (``track``) and applies the reference's explicit-residual confirmation."""
         prob, alg = self.prob, self.alg
-        if xout is not None:
-            with prob.on_device():
-                if self.callback is not None:
-                    self.callback(*cb_vecs())
-                res = [to_host(first)]
-                crit = np.maximum(self.tol * res[0], self.atol)
-                k, ok, xo = 0, False, None
-                while True:
-                    if np.all(res[-1] <= crit):
-                        xo = xout()
-                        res[-1] = to_host(norm(alg.residual(self.A, self.b, xo)))
-                        if np.all(res[-1] <= crit):
-                            ok = True
-                            break
-                    if k == self.maxiter:
-                        xo = xout()
-                        break
-                    res.append(to_host(step(k, crit)))
-                    k += 1
-            prob.launches = alg.ops.launches
-            xk = prob.to_user(xo) if xo is not None else None
-            return (xk if ok else None), Info(ok, xk, k, [prob.scalars_to_user(r) for r in res])
+        point = xout if xout is not None else (lambda: self.x)
+        lookahead = (alg.lazy and ahead and self.callback is None and getattr(self, "_tracked", None)
+                     is not None)
         with prob.on_device():
             if self.callback is not None:
                 self.callback(*cb_vecs())
             res = [to_host(first)]
             crit = np.maximum(self.tol * res[0], self.atol)
-            k, ok = 0, False
+            k, ok, xo = 0, False, None
+            if lookahead:
+                dev, kk = prob.device, prob.k
+                crit_d = torch.from_numpy(np.array(
+                    np.broadcast_to(np.asarray(crit, dtype=np.float64).reshape(-1), (kk,)))).to(dev)
+                hist = torch.zeros((_AHEAD, kk), dtype=torch.float64, device=dev)
+                stop_at = torch.full((1,), _INT_MAX, dtype=torch.int32, device=dev)
             while True:
                 if np.all(res[-1] <= crit):
-                    res[-1] = to_host(norm(alg.residual(self.A, self.b, self.x)))
+                    xo = point()
+                    res[-1] = to_host(norm(alg.residual(self.A, self.b, xo)))
                     if np.all(res[-1] <= crit):
                         ok = True
                         break
                 if k == self.maxiter:
+                    xo = point() if xout is not None else xo
                     break
-                out = step(k, crit)
-                if isinstance(out, tuple):
-                    res[-1] = to_host(out[1])
-                    ok = True
-                    break
-                if self.callback is not None:
-                    self.callback(*cb_vecs())
-                res.append(to_host(out))
-                k += 1
+                if not lookahead:
+                    out = step(k, crit)
+                    if isinstance(out, tuple):
+                        res[-1] = to_host(out[1])
+                        ok = True
+                        break
+                    if self.callback is not None and xout is None:
+                        self.callback(*cb_vecs())
+                    res.append(to_host(out))
+                    k += 1
+                    continue
+                nb = min(_AHEAD, self.maxiter - k)
+                stop_at.fill_(_INT_MAX)
+                hist_ptr = hist.data_ptr() - (k + 1) * kk * 8  # history row k + 1 == hist[0]
+                snaps = []
+                for j in range(nb):
+                    snaps.append(self._snapshot())
+                    alg.ops.gate(stop_at, k + j)
+                    out = step(k + j, crit)
+                    alg.ops.record(k + j + 1, alg.coef(out), crit_d, hist_ptr, stop_at)
+                alg.ops.gate(None, 0)
+                stop = int(stop_at.item())  # one read-back per batch
+                done = min(stop, k + nb) - k
+                rows = hist[:done].cpu().numpy()
+                res.extend(rows[j].copy() for j in range(done))
+                if done < nb:  # the launches behind step k + done were no-ops: undo the host side
+                    self._restore(snaps[done])
+                k += done
         prob.launches = alg.ops.launches
-        xk = prob.to_user(self.x)
+        if xout is not None:
+            xk = prob.to_user(xo) if xo is not None else None
+        else:
+            xk = prob.to_user(self.x)
         return (xk if ok else None), Info(ok, xk, k, [prob.scalars_to_user(r) for r in res])
 
 
@@ -141,7 +185,8 @@ def bicgstab(A, b, Ml=None, Mr=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15
         s["r"] = alg.lincomb(half_r, None, tt, -s["omega"], out=half_r)
         return norm(s["r"])
 
-    return d.run(norm, step, norm(d.r0), lambda: d.user(d.x, s["r"]))
+    # the mid-step test on the old x (bicgstab.py:117-122) needs the host inside every step
+    return d.run(norm, step, norm(d.r0), lambda: d.user(d.x, s["r"]), ahead=False)
 
 
 def cgs(A, b, M=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15, maxiter=None, callback=None):
@@ -167,6 +212,7 @@ def cgs(A, b, M=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15, maxiter=None,
         alg.axpy(s["r"], alpha, Aop(uq), sign=-1.0)
         return norm(s["r"])
 
+    d.track(s)
     return d.run(norm, step, norm(s["r"]), lambda: d.user(d.x, s["r"]))
 
 
@@ -204,6 +250,7 @@ def bicg(A, b, M=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15, maxiter=None
         pair = torch.stack([r0_u, r1_u]) if prob.is_torch else np.array([r0_u, r1_u])
         return x_u, pair
 
+    d.track(s, r, p)
     return d.run(norm, step, norm(r[0]), cb)
 
 
@@ -272,6 +319,7 @@ def qmr(A, b, Ml=None, Mr=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15, max
         alg.axpy(s["r"], 1.0, s["s"], sign=-1.0)
         return norm(s["r"])
 
+    d.track(s)
     return d.run(norm, step, first, lambda: d.user(d.x, s["r"]))
 
 
@@ -363,6 +411,7 @@ def cgr(A, b, M=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15, maxiter=None,
         alg.xpby(s["Ap"], s["Ar"], beta)
         return norm(s["r"])
 
+    d.track(s)
     return d.run(norm, step, norm(s["r"]), lambda: d.user(d.x, s["r"]))
 
 
@@ -389,6 +438,7 @@ def gcr(A, b, x0=None, inner=None, tol=1e-5, atol=1.0e-15, maxiter=None, callbac
         alg.axpy(s["r"], g, V[-1], sign=-1.0)
         return norm(s["r"])
 
+    d.track(s, S, V)
     return d.run(norm, step, norm(s["r"]), lambda: d.user(d.x, s["r"]))
 
 
@@ -421,6 +471,7 @@ def chebyshev(A, b, eigenvalue_estimates, M=None, x0=None, inner=None, tol=1e-5,
         alg.axpy(s["r"], s["alpha"], Aop(s["p"]), sign=-1.0)
         return norm(s["r"])
 
+    d.track(s)
     return d.run(norm, step, norm(s["r"]), lambda: d.user(d.x, s["r"]))
 
 
@@ -483,4 +534,5 @@ def symmlq(A, b, M=None, x0=None, inner=None, tol=1e-5, atol=1.0e-15, maxiter=No
             callback(*d.user(cg_point(), r))
         return norm(r)
 
+    d.track(s)
     return d.run(norm, step, first, lambda: d.user(d.x, s["r"]), xout=cg_point)

@@ -72,6 +72,7 @@ class _Ops:
 class FakeAlg:
     def __init__(self, prob, inner=None, lazy=False):  # lazy: device-resident scalars (GPU only)
         self.prob, self.ops = prob, _Ops()
+        self.lazy = False  # host scalars: the per-iteration loop of _Drive.run
         self._user_inner = None if inner is None else prob.inner(inner)
 
     def _c(self, a):
