@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 import scipy.sparse
+import scipy.sparse.linalg
 import torch
 
 import cases_extra
@@ -140,3 +141,61 @@ def test_workspace_pool_survives_cyclic_garbage():
         out = ops.slots(1)
         ops.dot(x, x, out[0])
         assert float(out[0, 0]) == 100.0
+
+
+@pytest.mark.parametrize("solver", ["cgs", "bicg", "qmr", "cgr", "gcr", "chebyshev"])
+def test_lookahead_rollback_equals_step_by_step(solver, monkeypatch):
+    """The drivers enqueue 4 gated iterations ahead of the host's read-back and roll their own
+    references back to the step that met the criterion.  Force the rare path as well -- the
+    explicit-residual confirmation FAILS once, so the solver resumes from the rolled-back state
+    -- and compare with look-ahead 1 (no ghost iterations): identical bits."""
+    import krylov_b200.shortrec as sr
+    from krylov_b200._alg import Alg
+
+    A = (st.convection_diffusion3d(9) if solver in ("cgs", "bicg", "qmr", "gcr")
+         else st.poisson3d(9))
+    b = A @ np.random.default_rng(3).standard_normal(A.shape[0])
+    kw = {"tol": 1e-7, "maxiter": 300}
+    if solver == "chebyshev":
+        lam = np.linalg.eigvalsh(A.toarray())
+        kw["eigenvalue_estimates"] = (lam[0], lam[-1])
+    out = {}
+    for ahead in (4, 1):
+        calls = {"n": 0}
+        orig = Alg.residual
+
+        def residual(self, Aop, bb, z):
+            r = orig(self, Aop, bb, z)
+            calls["n"] += 1
+            if calls["n"] == 1:  # the first confirmation sees a residual 1000 x too large
+                r = r * 1000.0
+            return r
+
+        monkeypatch.setattr(Alg, "residual", residual)
+        monkeypatch.setattr(sr, "_AHEAD", ahead)
+        out[ahead] = getattr(kb, solver)(A, b, **kw)
+        monkeypatch.setattr(Alg, "residual", orig)
+        assert calls["n"] >= 2  # failed once, confirmed later
+    (x4, i4), (x1, i1) = out[4], out[1]
+    assert i4.success and i1.success and i4.numsteps == i1.numsteps
+    np.testing.assert_array_equal(np.asarray(i4.resnorms), np.asarray(i1.resnorms))
+    np.testing.assert_array_equal(x4, x1)
+    x_ref = scipy.sparse.linalg.spsolve(A.tocsc(), b)
+    assert np.linalg.norm(x4 - x_ref) <= 1e-5 * np.linalg.norm(x_ref)
+
+
+def test_lookahead_symmlq_equals_step_by_step(monkeypatch):
+    """symmlq records the norm of the unnormalised Lanczos vector and checks the CG point (xout):
+    look-ahead 4 and 1 give the same bits, converged or not."""
+    import krylov_b200.shortrec as sr
+
+    A = st.poisson3d(9)
+    b = A @ np.random.default_rng(3).standard_normal(A.shape[0])
+    out = {}
+    for ahead in (4, 1):
+        monkeypatch.setattr(sr, "_AHEAD", ahead)
+        out[ahead] = kb.symmlq(A, b, tol=1e-6, maxiter=120)
+    (x4, i4), (x1, i1) = out[4], out[1]
+    assert i4.numsteps == i1.numsteps and i4.success == i1.success
+    np.testing.assert_array_equal(np.asarray(i4.resnorms), np.asarray(i1.resnorms))
+    np.testing.assert_array_equal(np.asarray(i4.xk), np.asarray(i1.xk))
