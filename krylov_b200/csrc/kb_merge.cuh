@@ -45,14 +45,24 @@ struct KbMergeSmem {
   uint64_t empty[NG][STAGES];
 };
 
-// lanes per row of a tile (log2): enough to keep the 256 threads of a group busy in one pass
-// when the tile has few rows, and at least (longest row piece) / 8 so that one long row among
-// many short ones does not serialise the tile.  0 (one lane per row) sums left to right.
+// lanes per row of a tile (log2), from a cost model of phase 2: a pass over 256 / G rows costs
+// about 125 cycles of bookkeeping, a lane's serial add about 30, a butterfly step about 20 --
+//   cost(G) = ceil(nr / (256 / G)) * 125 + ceil(maxlen / G) * 30 + log2(G) * 20.
+// Few long rows get many lanes, many short rows one lane each (G = 1 sums left to right: SciPy's
+// order), and a tile that mixes one long row with many short ones lands in between instead of
+// serialising either way.
 __device__ __forceinline__ int kb_merge_lg(int nr, int maxlen) {
-  int lg = 0;
-  while (lg < 5 && nr * (2 << lg) <= 256) ++lg;
-  while (lg < 5 && (8 << lg) < maxlen) ++lg;
-  return lg;
+  int best = 0;
+  long long bestc = -1;
+  for (int lg = 0; lg <= 5; ++lg) {
+    const long long passes = (nr + (256 >> lg) - 1) / (256 >> lg);
+    const long long c = passes * 125 + (long long)((maxlen + (1 << lg) - 1) >> lg) * 30 + lg * 20;
+    if (bestc < 0 || c < bestc) {
+      bestc = c;
+      best = lg;
+    }
+  }
+  return best;
 }
 
 // meta[t] = {first row this tile sums, last row, tail entries past the tile it finishes,

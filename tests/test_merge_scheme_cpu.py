@@ -37,11 +37,8 @@ def tile_meta(rowptr, nnz, n_rows, T, TAIL):
         for r in range(r_first, r_last + 1):
             maxlen = max(maxlen, min(rowptr[r + 1], b + tail) - max(rowptr[r], a))
         nr = r_last - r_first + 1
-        lg = 0  # kb_merge_lg
-        while lg < 5 and nr * (2 << lg) <= 256:
-            lg += 1
-        while lg < 5 and (8 << lg) < maxlen:
-            lg += 1
+        lg = min(range(6), key=lambda g: (-(-nr // (256 >> g)) * 125 + -(-int(maxlen) // (1 << g)) * 30
+                                           + g * 20, g))  # kb_merge_lg's cost model
         meta.append((r_first, r_last, int(tail), lg))
     return meta
 
