@@ -15,8 +15,6 @@
 // two inner products differs (fixed: block partials in block order), so runs are repeatable.
 // The matrix arrays are read through the non-coherent path (L1 hits from the second iteration
 // on), r and p -- written by other CTAs -- through L2 (ld.global.cg).
-#include <new>
-
 #include "kb_handles.cuh"
 
 int g_small_n = 262144;  // kb_tune key 28: largest n for the persistent CG kernel (0: off)
@@ -40,17 +38,11 @@ struct KbSmallCg {
                      // before the launch (entries on one line made every poll queue at one L2 slice)
 };
 
-// gpu-scope variants of kb_ll_store / kb_ll_load (kb_common.cuh uses system scope: peers)
-__device__ __forceinline__ void kb_ll_store_gpu(double* dst16, double v, unsigned flag) {
-  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
-  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst16), "r"(lo),
-               "r"(flag), "r"(hi), "r"(flag)
-               : "memory");
-}
-// the same entry as two 8-byte halves, the first a RELEASE store: everything this CTA wrote
-// (ordered before by the block barrier) is visible at gpu scope before the flag -- a release,
-// unlike fence.acq_rel / __threadfence(), does not invalidate the SM's L1 (the matrix stays
-// cached across iterations)
+// gpu-scope variants of kb_ll_store / kb_ll_load (kb_common.cuh uses system scope: peers).
+// The entry {lo word, flag, hi word, flag} is written as two 8-byte halves, the first a RELEASE
+// store: everything this CTA wrote (ordered before by the block barrier) is visible at gpu scope
+// before the flag -- a release, unlike fence.acq_rel / __threadfence(), does not invalidate the
+// SM's L1 (the matrix stays cached across iterations)
 __device__ __forceinline__ void kb_ll_store_release(double* dst16, double v, unsigned flag) {
   const unsigned long long lo = (unsigned long long)(unsigned)__double2loint(v) |
                                 ((unsigned long long)flag << 32);
