@@ -38,7 +38,7 @@ struct KbSmallCg {
                      // before the launch (entries on one line made every poll queue at one L2 slice)
 };
 
-// gpu-scope variants of kb_ll_store / kb_ll_load (kb_common.cuh uses system scope: peers).
+// gpu-scope variant of kb_ll_store (kb_common.cuh uses system scope: peers).
 // The entry {lo word, flag, hi word, flag} is written as two 8-byte halves, the first a RELEASE
 // store: everything this CTA wrote (ordered before by the block barrier) is visible at gpu scope
 // before the flag -- a release, unlike fence.acq_rel / __threadfence(), does not invalidate the
@@ -51,17 +51,6 @@ __device__ __forceinline__ void kb_ll_store_release(double* dst16, double v, uns
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(dst16), "l"(lo) : "memory");
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst16 + 1), "l"(hi) : "memory");
 }
-__device__ __forceinline__ bool kb_ll_load_gpu(const double* src16, unsigned flag, double* v) {
-  unsigned a, b, c, d;
-  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
-               : "l"(src16)
-               : "memory");
-  if (b != flag || d != flag) return false;
-  *v = __hiloint2double((int)c, (int)a);
-  return true;
-}
-
 // Sum over the grid + barrier in one round trip: every CTA stores its block partial as ONE
 // self-validating 16-byte entry {value, sequence flag} (kb_ll_store) and a warp polls all the
 // entries -- arrival and data travel together, no counter, no second read.  Every CTA adds the
@@ -85,13 +74,34 @@ __device__ __forceinline__ double kb_small_allsum(double v, const KbSmallCg& q, 
       kb_ll_store_release(slot + 16 * blockIdx.x, tot, flag);
     }
     __syncwarp();
-    double a = 0.0;
-    for (int b = t; b < (int)gridDim.x; b += 32) {
-      double x = 0.0;
-      while (!kb_ll_load_gpu(slot + 16 * (size_t)b, flag, &x)) {
-      }
-      a += x;
+    // lane t polls entries t, t + 32, ...: all its loads are issued before the first flag is
+    // tested (one L2 round trip per polling round, however many CTAs there are)
+    double xs[KB_BAR_CTAS / 32];
+    unsigned need = 0;
+#pragma unroll
+    for (int i = 0; i < KB_BAR_CTAS / 32; ++i) {
+      xs[i] = 0.0;
+      if (t + 32 * i < (int)gridDim.x) need |= 1u << i;
     }
+    while (need != 0u) {
+      unsigned w0[KB_BAR_CTAS / 32], w1[KB_BAR_CTAS / 32], w2[KB_BAR_CTAS / 32], w3[KB_BAR_CTAS / 32];
+#pragma unroll
+      for (int i = 0; i < KB_BAR_CTAS / 32; ++i)
+        if ((need >> i) & 1u)
+          asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w0[i]), "=r"(w1[i]), "=r"(w2[i]), "=r"(w3[i])
+                       : "l"(slot + 16 * (size_t)(t + 32 * i))
+                       : "memory");
+#pragma unroll
+      for (int i = 0; i < KB_BAR_CTAS / 32; ++i)
+        if (((need >> i) & 1u) && w1[i] == flag && w3[i] == flag) {
+          xs[i] = __hiloint2double((int)w2[i], (int)w0[i]);
+          need &= ~(1u << i);
+        }
+    }
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < KB_BAR_CTAS / 32; ++i) a += xs[i];  // block order within the lane
     a = kb_warp_sum(a);
     if (t == 0) sm[32] = a;
   }
@@ -102,8 +112,11 @@ __device__ __forceinline__ double kb_small_allsum(double v, const KbSmallCg& q, 
 
 // ONE: every thread owns at most one row for the whole launch -- x, r, p and A p of that row
 // stay in registers; only p' and r go to memory (the neighbouring rows read them).
+#define KB_SMALL_BLOCK 512  // 128 registers per thread: the row's entries + its gathers in flight
+#define KB_SMALL_ROW 8      // entries of a row kept in registers (longer rows: loop over memory)
+
 template <bool ONE>
-__global__ void __launch_bounds__(1024, 1) kb_cg_small_kernel(KbSmallCg q) {
+__global__ void __launch_bounds__(KB_SMALL_BLOCK, 1) kb_cg_small_kernel(KbSmallCg q) {
   __shared__ double sm[40];
   const int nthreads = gridDim.x * blockDim.x;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -115,13 +128,26 @@ __global__ void __launch_bounds__(1024, 1) kb_cg_small_kernel(KbSmallCg q) {
   const bool mine = gtid < q.n;
   double x_own = 0.0, r_own = 0.0, p_own = 0.0, ap_own = 0.0;
   int lo1 = 0, hi1 = 0;
+  // ONE: a row of at most KB_SMALL_ROW entries lives in registers for the whole launch, so that a
+  // step's gathers of r and p are issued together (one L2 round trip instead of one per entry)
+  int cidx[KB_SMALL_ROW];
+  double cval[KB_SMALL_ROW];
+  bool inreg = false;
   if (ONE && mine) {
     x_own = q.x[gtid];
     r_own = q.r[gtid];
     p_own = (pc ? q.pb1 : q.pb0)[gtid];
     lo1 = q.rowptr[gtid];
     hi1 = q.rowptr[gtid + 1];
+    inreg = hi1 - lo1 <= KB_SMALL_ROW;
+#pragma unroll
+    for (int j = 0; j < KB_SMALL_ROW; ++j) {
+      const bool in = inreg && lo1 + j < hi1;
+      cidx[j] = in ? q.colidx[lo1 + j] : 0;
+      cval[j] = in ? q.vals[lo1 + j] : 0.0;
+    }
   }
+  const int len1 = hi1 - lo1;
   for (int i = q.i0; i < q.i0 + q.n_iters; ++i) {
     const double* p_old = pc ? q.pb1 : q.pb0;
     double* p_new = (i > 0) == (pc != 0) ? q.pb0 : q.pb1;
@@ -135,6 +161,25 @@ __global__ void __launch_bounds__(1024, 1) kb_cg_small_kernel(KbSmallCg q) {
           if (x_pending) x_own = kb_mul_add(alpha_prev, p_own, x_own);
           p_own = kb_mul_add(omega, p_own, r_own);
           p_new[gtid] = p_own;
+        }
+        if (inreg) {
+          double pg[KB_SMALL_ROW], rg[KB_SMALL_ROW];
+#pragma unroll
+          for (int j = 0; j < KB_SMALL_ROW; ++j) {
+            pg[j] = rg[j] = 0.0;
+            if (j < len1) {
+              pg[j] = __ldcg(p_old + cidx[j]);
+              if (i > 0) rg[j] = __ldcg(q.r + cidx[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < KB_SMALL_ROW; ++j) {
+            if (j < len1) {  // same products, same order as the loop below
+              const double pcn = i > 0 ? kb_mul_add(omega, pg[j], rg[j]) : pg[j];
+              sum = __dadd_rn(sum, __dmul_rn(cval[j], pcn));
+            }
+          }
+        } else if (i > 0) {
           for (int j = lo1; j < hi1; ++j) {
             const int c = __ldg(q.colidx + j);
             const double pcn = kb_mul_add(omega, __ldcg(p_old + c), __ldcg(q.r + c));
@@ -226,8 +271,8 @@ int kb_cg_small_run(kb_ws_s* ws, const kb_cg_state* s, int i0, int n_iters, int 
   KB_CUDA(cudaGetDevice(&dev));
   KB_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
   if (resident[dev] == 0) {
-    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident[dev],
-                                                          kb_cg_small_kernel<false>, 1024, 0));
+    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident[dev], kb_cg_small_kernel<false>,
+                                                          KB_SMALL_BLOCK, 0));
     KB_REQUIRE(resident[dev] >= 1, "persistent CG kernel does not fit an SM");
   }
   KbSmallCg q;
@@ -249,17 +294,17 @@ int kb_cg_small_run(kb_ws_s* ws, const kb_cg_state* s, int i0, int n_iters, int 
   q.hist = s->hist;
   q.stop_at = s->stop_at;
   q.partials = ws->barbuf;
-  // one row per thread while the rows fit co-resident CTAs of 1024 threads; all CTAs must be
-  // resident (they meet at grid-wide barriers): cooperative launch
-  int grid = (int)((s->n + 1023) / 1024);
+  // one row per thread while the rows fit co-resident CTAs; all CTAs must be resident (they meet
+  // at grid-wide barriers): cooperative launch
+  int grid = (int)((s->n + KB_SMALL_BLOCK - 1) / KB_SMALL_BLOCK);
   const int cap = ws->num_sms * resident[dev];
   if (grid > cap) grid = cap;
   if (grid > KB_BAR_CTAS) grid = KB_BAR_CTAS;
   KB_CUDA(cudaMemsetAsync(q.partials, 0, 2 * 128 * (size_t)grid, st));
   void* args[] = {&q};
-  const bool one = (int64_t)grid * 1024 >= s->n;
+  const bool one = (int64_t)grid * KB_SMALL_BLOCK >= s->n;
   KB_CUDA(cudaLaunchCooperativeKernel(
       one ? (const void*)kb_cg_small_kernel<true> : (const void*)kb_cg_small_kernel<false>,
-      dim3(grid), dim3(1024), args, 0, st));
+      dim3(grid), dim3(KB_SMALL_BLOCK), args, 0, st));
   return KB_OK;
 }
