@@ -22,7 +22,7 @@ import torch
 
 import ctypes as C
 
-from . import _trace
+from . import _complex, _trace
 from ._alg import Alg, nz
 from ._lib import CgState, check, lib
 from .device import Ops, cur_stream, ptr
@@ -37,6 +37,10 @@ def cg(A, b, M=None, Ml=None, inner=None, x0=None, tol=1e-5, atol=1.0e-15, maxit
        return_arnoldi=False, callback=None, inner_product=None):
     if inner is None and inner_product is not None:  # alias used by BASELINE.json's wording
         inner = inner_product
+    if _complex.any_complex(A, b, x0, M, Ml):  # Hermitian systems: real-equivalent embedding
+        return _complex.solve_hermitian(cg, A, b, x0, {"M": M, "Ml": Ml}, inner, callback,
+                                        dict(tol=tol, atol=atol, maxiter=maxiter,
+                                             return_arnoldi=return_arnoldi))
     _trace.mark("cg: enter")
     prob = Problem(A, b, x0)
     _trace.mark("cg: Problem (b, x0, A on the device)")

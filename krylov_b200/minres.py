@@ -18,6 +18,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from . import _complex
 from ._alg import Alg, nz
 import ctypes as C
 
@@ -38,6 +39,9 @@ def minres(A, b, M=None, Ml=None, Mr=None, inner=None, x0=None, tol=1e-5, atol=1
            maxiter=None, callback=None, inner_product=None):
     if inner is None and inner_product is not None:
         inner = inner_product
+    if _complex.any_complex(A, b, x0, M, Ml, Mr):  # Hermitian systems: real-equivalent embedding
+        return _complex.solve_hermitian(minres, A, b, x0, {"M": M, "Ml": Ml, "Mr": Mr}, inner,
+                                        callback, dict(tol=tol, atol=atol, maxiter=maxiter))
     prob = Problem(A, b, x0)
     maxiter = prob.n if maxiter is None else int(maxiter)
     with torch.cuda.device(prob.device):

@@ -156,7 +156,10 @@ class Problem:
         assert A.shape[0] == A.shape[1]
         assert A.shape[1] == b.shape[0]
         if _dtype_is_complex(b) or _dtype_is_complex(A):
-            raise NotImplementedError("complex dtypes are out of scope (north_star: fp64)")
+            raise NotImplementedError(
+                "complex128: cg and minres accept HERMITIAN matrices (real-equivalent embedding, "
+                "krylov_b200/_complex.py); gmres, the Arnoldi builders and the other solvers are "
+                "fp64 only (north_star)")
         self.user_shape = tuple(b.shape)
         self.n = int(b.shape[0])
         self.k = int(np.prod(self.user_shape[1:])) if len(self.user_shape) > 1 else 1
