@@ -1,3 +1,5 @@
+# Row-partitioned runs on one 8-GPU box: 8-rank parity check (tools/dist_check.py), then bench.py at N = 8, 4, 2
+# (what profiles/r2_bench_n{2,4,8}_b.json and r2_dist8_parity_b.json come from).  usage: gpurun --gpus 8 -- bash tools/scale_n842.sh
 cd /root/repo
 mkdir -p gpurun_out
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 tools/dist_check.py gpurun_out/r2b_dist8.json 48 > gpurun_out/r2b_dist8.log 2>&1
