@@ -236,18 +236,23 @@ class DistCsrMatrix:
         with *global* column indices."""
         from .csr import CsrMatrix
 
+        from . import _trace
+
         self.comm = comm if comm is not None else Comm()
+        _trace.mark("dist: communicator (peer-memory mailbox, IPC handles)")
         self.device = local_csr.device
         self.global_shape = (int(offsets[-1]), int(offsets[-1]))
         plan = HaloPlan(local_csr.rowptr, local_csr.colidx, local_csr.vals[: local_csr.nnz],
                         offsets, self.comm)
         self.plan = plan
+        _trace.mark("dist: halo plan (split into local / halo parts, send lists)")
         n_loc = plan.row_end - plan.row_start
         self.shape = (n_loc, n_loc)
         self.nnz = local_csr.nnz
         self.A_loc = CsrMatrix(plan.loc_rowptr, plan.loc_colidx, plan.loc_vals, (n_loc, n_loc),
                                self.device)
         plan.loc_rowptr = plan.loc_colidx = plan.loc_vals = None
+        _trace.mark("dist: local matrix (kb_csr_create)")
         self._bufs = {}
         self._ops = {}
         self._halos = {}
