@@ -313,6 +313,11 @@ typedef struct {
   int* flags;          /* bit0: invariant subspace */
 } kb_minres_state;
 int kb_minres_scalar(kb_ws_t ws, int k, int iter, const kb_minres_state* st, void* stream);
+/* kb_axpy_dot (dot 2: w -= coef u, st->ww = <w, w>) and kb_minres_scalar(iter) in ONE launch: the
+ * scalar recurrences run in the finishing block of the reduction (arnoldi.py:264-267 +
+ * minres.py:190-228).  Same arithmetic, one launch less per MINRES step (what kb_minres_run uses). */
+int kb_axpy_dot_minres(kb_ws_t ws, int64_t n, int k, const double* coef, const double* u, double* w,
+                       int iter, const kb_minres_state* st, void* stream);
 /* z = (v - R0 W0 - R1 W1)/nz(R2); W0 <- z (becomes W1 by buffer rotation);
  * yk += y0 z; vnext = Av / nz(h2)   (minres.py:219-221, arnoldi.py:274-277).
  * With a preconditioner M pass MAv = M Av and pnext: vnext = MAv / nz(h2),
@@ -323,7 +328,8 @@ int kb_minres_update(kb_ws_t ws, int64_t n, int k, const double* coefs, const do
 
 /* Whole-loop entry point (SURVEY.md 8b "kb_minres_solve"): enqueues MINRES iterations
  * i0 .. i0+n_iters-1 of the unpreconditioned fused path on one GPU -- per iteration kb_spmv
- * (Lanczos product fused with alpha), kb_axpy_dot (beta^2), kb_minres_scalar, kb_minres_update --
+ * (Lanczos product fused with alpha), kb_axpy_dot_minres (beta^2 + the scalar recurrences in the
+ * reduction's finishing block), kb_minres_update: three launches --
  * each gated on *st.stop_at <= i.  V[i % 2] holds v_i (V[(i+1) % 2] = v_{i-1}, overwritten with
  * v_{i+1}), W[i % 2] / W[(i+1) % 2] the two W vectors; st.hist row 0 receives step i0+1 when the
  * caller offsets the pointer as for kb_minres_scalar.  Replaces the loop minres.py:168-236. */

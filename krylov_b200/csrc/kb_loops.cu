@@ -92,11 +92,9 @@ int kb_minres_run(kb_ws_t ws, const kb_minres_run_state* s, int i0, int n_iters,
       rc = kb_spmv(s->A, ws, k, v, s->Av, 0, nullptr, nullptr, 1, v, (double*)st->alpha, stream);
     else
       rc = kb_spmv(s->A, ws, k, v, s->Av, 1, vold, st->h2prev, 1, v, (double*)st->alpha, stream);
-    // Av -= alpha v, beta_i^2 = <Av, Av>             (arnoldi.py:264-267)
-    if (rc == KB_OK)
-      rc = kb_axpy_dot(ws, s->n, k, st->alpha, nullptr, v, s->Av, 2, nullptr, (double*)st->ww,
-                       stream);
-    if (rc == KB_OK) rc = kb_minres_scalar(ws, k, i, st, stream);  // minres.py:190-228
+    // Av -= alpha v, beta_i^2 = <Av, Av> (arnoldi.py:264-267); the scalar recurrences of
+    // minres.py:190-228 in the finishing block of the same launch
+    if (rc == KB_OK) rc = kb_axpy_dot_minres(ws, s->n, k, st->alpha, v, s->Av, i, st, stream);
     if (rc == KB_OK)  // minres.py:219-221, arnoldi.py:274-277
       rc = kb_minres_update(ws, s->n, k, st->coefs, v, s->W[i % 2], s->W[(i + 1) % 2], s->Av, s->yk,
                             vold, nullptr, nullptr, stream);

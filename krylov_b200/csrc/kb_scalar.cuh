@@ -61,9 +61,10 @@ __global__ void kb_lartg_kernel(int n, const double* f, const double* g, double*
 }
 
 // ---------------------------------------------------------------- MINRES --
-// minres.py:190-228 for Lanczos step `iter` (0-based); thread c = column.
-__global__ void kb_minres_scalar_kernel(int k, int iter, kb_minres_state st, KbRed rd) {
-  if (kb_gated(rd)) return;
+// minres.py:190-228 for Lanczos step `iter` (0-based); thread c = column.  Block-wide: every
+// thread of ONE block (>= k threads) calls it -- the scalar kernel below, or the finishing block
+// of the reduction that produced st.ww (kb_axpy_dot_minres_kernel: one launch less per step).
+__device__ __forceinline__ void kb_minres_scalar_body(int k, int iter, const kb_minres_state& st) {
   const int c = threadIdx.x;
   int conv = 1, inv = 1;
   if (c < k) {
@@ -106,6 +107,11 @@ __global__ void kb_minres_scalar_kernel(int k, int iter, kb_minres_state st, KbR
     if (all_inv) atomicOr(st.flags, 1);
     if (all_conv || all_inv) *st.stop_at = iter + 1;
   }
+}
+
+__global__ void kb_minres_scalar_kernel(int k, int iter, kb_minres_state st, KbRed rd) {
+  if (kb_gated(rd)) return;
+  kb_minres_scalar_body(k, iter, st);
 }
 
 // ----------------------------------------------------------------- GMRES --

@@ -164,7 +164,7 @@ def _minres_fused(prob, tol, atol, maxiter, callback, M=None, Ml=None, Mr=None):
         if run_c is not None:
             run_c.st = st
             check(lib.kb_minres_run(ops.ws.handle, C.byref(run_c), kk, nb, cur_stream()))
-            ops.launches += 4 * nb
+            ops.launches += 3 * nb
         for i in range(kk, kk + nb) if run_c is None else ():
             v, vold = Vb[i % 2], Vb[(i + 1) % 2]
             p, pold = Pb[i % 2], Pb[(i + 1) % 2]
