@@ -363,11 +363,16 @@ typedef struct {
   int have_h;          /* 1: Householder path -- `dots` already holds h[0..j+1] */
 } kb_gmres_state;
 int kb_gmres_scalar(kb_ws_t ws, int k, int iter, const kb_gmres_state* st, void* stream);
+/* kb_axpy_dot (dot 2: w -= coef u, st->ww = <w, w>) and kb_gmres_scalar(iter) in ONE launch (the
+ * last projection of an Arnoldi-MGS step, arnoldi.py:157-162,184-185 + gmres.py:199-221); what
+ * kb_gmres_cycle uses. */
+int kb_axpy_dot_gmres(kb_ws_t ws, int64_t n, int k, const double* coef, const double* u, double* w,
+                      int iter, const kb_gmres_state* st, void* stream);
 /* Whole-loop entry point (SURVEY.md 8b "kb_gmres_cycle"): enqueues Arnoldi steps i0 ..
  * i0+n_iters-1 of unpreconditioned GMRES with modified Gram-Schmidt (st.num_reorthos sweeps) on
- * one GPU -- per step kb_spmv (w = A V[i] fused with <V[0], w>), (i+1) x sweeps kb_axpy_dot,
- * kb_gmres_scalar (Givens update of the Hessenberg column, residual norm, stop flag),
- * kb_div_scale (V[i+1] = w / h[i+1]) -- each gated on *st.stop_at <= i.  V[j] = Vbuf + j*vstride
+ * one GPU -- per step kb_spmv (w = A V[i] fused with <V[0], w>), (i+1) x sweeps kb_axpy_dot, the
+ * last of them kb_axpy_dot_gmres (Givens update of the Hessenberg column, residual norm and stop
+ * flag in its finishing block), kb_div_scale (V[i+1] = w / h[i+1]) -- each gated on *st.stop_at <= i.  V[j] = Vbuf + j*vstride
  * must hold i0+n_iters+1 vectors; dots has num_reorthos*(st.maxiter+1)+2 rows of k doubles and
  * must equal st.dots.  Replaces the loop gmres.py:179-234 with arnoldi.py:153-200. */
 typedef struct {

@@ -113,6 +113,7 @@ SIGNATURES = {
     "kb_scalar_op": [vp, i32, i32, vp, vp, C.c_double, C.c_double, vp, vp],
     "kb_record": [vp, i32, i32, vp, vp, vp, vp, vp],
     "kb_axpy_dot_minres": [vp, i64, i32, vp, vp, vp, i32, C.POINTER(MinresState), vp],
+    "kb_axpy_dot_gmres": [vp, i64, i32, vp, vp, vp, i32, C.POINTER(GmresState), vp],
     "kb_minres_run": [vp, C.POINTER(MinresRunState), i32, i32, vp],
     "kb_gmres_cycle": [vp, C.POINTER(GmresCycleState), i32, i32, vp],
     "kb_cg_run_timed": [vp, C.POINTER(CgState), i32, i32, i32, vp, C.POINTER(C.c_float),

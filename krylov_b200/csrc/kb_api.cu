@@ -1724,6 +1724,20 @@ int kb_axpy_dot_minres(kb_ws_t ws, int64_t n, int k, const double* coef, const d
   return KB_OK;
 }
 
+int kb_axpy_dot_gmres(kb_ws_t ws, int64_t n, int k, const double* coef, const double* u, double* w,
+                      int iter, const kb_gmres_state* stt, void* stream) {
+  KB_VEC_PROLOGUE();
+  KB_REQUIRE(coef && u && w && stt, "null argument");
+  KB_REQUIRE(stt->ww != nullptr && stt->have_h == 0, "needs the Gram-Schmidt state (ww, have_h == 0)");
+  KB_REQUIRE(total > 0, "empty vectors");
+  KB_REQUIRE(iter >= 0 && iter < stt->maxiter, "iter exceeds the Hessenberg storage");
+  const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
+  kb_axpy_dot_gmres_kernel<<<grid, block, 0, st>>>(total, k, coef, u, w, (double*)stt->ww, iter,
+                                                   *stt, rd);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
 int kb_minres_scalar(kb_ws_t ws, int k, int iter, const kb_minres_state* stt, void* stream) {
   KB_REQUIRE(ws != nullptr && stt != nullptr, "null argument");
   KB_REQUIRE(k >= 1 && k <= ws->max_k, "k exceeds workspace max_k");

@@ -108,6 +108,7 @@ int kb_gmres_cycle(kb_ws_t ws, const kb_gmres_cycle_state* s, int i0, int n_iter
   KB_REQUIRE(ws != nullptr && s != nullptr, "null argument");
   KB_REQUIRE(s->A && s->Vbuf && s->w && s->dots && s->ww && s->hlast,
              "null field in kb_gmres_cycle_state");
+  KB_REQUIRE(s->st.ww == s->ww && s->st.have_h == 0, "st.ww must be the ww slot (MGS path)");
   KB_REQUIRE(i0 >= 0 && n_iters >= 0, "negative iteration range");
   KB_REQUIRE(i0 + n_iters <= s->st.maxiter, "basis storage too small for this range");
   const int k = s->k;
@@ -127,14 +128,15 @@ int kb_gmres_cycle(kb_ws_t ws, const kb_gmres_cycle_state* s, int i0, int n_iter
       for (int j = 0; j <= i && rc == KB_OK; ++j, ++idx) {  // arnoldi.py:157-162
         double* Vj = s->Vbuf + (size_t)j * s->vstride;
         double* coef = s->dots + (size_t)idx * k;
-        if (sweep == nre - 1 && j == i) {  // last projection + <w, w>   (arnoldi.py:184-185)
-          rc = kb_axpy_dot(ws, s->n, k, coef, nullptr, Vj, s->w, 2, nullptr, s->ww, stream);
+        if (sweep == nre - 1 && j == i) {
+          // last projection + <w, w> (arnoldi.py:184-185); the Hessenberg / Givens update of
+          // gmres.py:206-221 in the finishing block of the same launch
+          rc = kb_axpy_dot_gmres(ws, s->n, k, coef, Vj, s->w, i, &s->st, stream);
         } else {
           const double* nxt = j < i ? Vj + s->vstride : V0;
           rc = kb_axpy_dot(ws, s->n, k, coef, nullptr, Vj, s->w, 1, nxt, coef + k, stream);
         }
       }
-    if (rc == KB_OK) rc = kb_gmres_scalar(ws, k, i, &s->st, stream);  // gmres.py:206-221
     if (rc == KB_OK)  // V[i+1] = w / h[i+1]   (arnoldi.py:191-193)
       rc = kb_div_scale(ws, s->n, k, s->w, s->hlast, Vi + s->vstride, stream);
   }

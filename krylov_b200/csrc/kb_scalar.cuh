@@ -117,8 +117,9 @@ __global__ void kb_minres_scalar_kernel(int k, int iter, kb_minres_state st, KbR
 // ----------------------------------------------------------------- GMRES --
 // gmres.py:199-221 for Arnoldi step `iter`; R is (maxiter+1, maxiter, k)
 // row-major like the reference's array, Gc/Gs the rotation list, y the rhs.
-__global__ void kb_gmres_scalar_kernel(int k, int iter, kb_gmres_state st, KbRed rd) {
-  if (kb_gated(rd)) return;
+// Block-wide like kb_minres_scalar_body: the scalar kernel below, or the finishing block of the
+// reduction that produced st.ww (kb_axpy_dot_gmres_kernel).
+__device__ __forceinline__ void kb_gmres_scalar_body(int k, int iter, const kb_gmres_state& st) {
   const int c = threadIdx.x;
   const int mi = st.maxiter;
   int conv = 1, inv = 1;
@@ -173,6 +174,11 @@ __global__ void kb_gmres_scalar_kernel(int k, int iter, kb_gmres_state st, KbRed
     if (all_inv) atomicOr(st.flags, 1);
     if (all_conv || all_inv) *st.stop_at = iter + 1;
   }
+}
+
+__global__ void kb_gmres_scalar_kernel(int k, int iter, kb_gmres_state st, KbRed rd) {
+  if (kb_gated(rd)) return;
+  kb_gmres_scalar_body(k, iter, st);
 }
 
 // yy = R[:m,:m]^{-1} y[:m] per column; all-zero rhs column -> zeros

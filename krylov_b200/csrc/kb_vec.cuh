@@ -411,6 +411,49 @@ kb_axpy_dot_minres_kernel(int64_t total, int k, const double* __restrict__ coef,
   }
 }
 
+// Last projection of an Arnoldi-MGS step with the Hessenberg update in the reduction's finishing
+// block: w -= h V[j], <w, w> (arnoldi.py:157-162, 184-185), then gmres.py:199-221
+// (kb_gmres_scalar_body).  Same arithmetic as kb_axpy_dot (dot 2) + kb_gmres_scalar, one launch.
+__global__ void __launch_bounds__(KB_BLOCK)
+kb_axpy_dot_gmres_kernel(int64_t total, int k, const double* __restrict__ coef,
+                          const double* __restrict__ u, double* __restrict__ w,
+                          double* __restrict__ out, int iter, kb_gmres_state st, KbRed rd) {
+  if (kb_gated(rd)) return;
+  __shared__ double sm[KB_BLOCK];
+  const double a = coef[threadIdx.x % k];
+  double acc = 0.0;
+  KB_TILE_LOOP_BEGIN(total)
+  if (kb_full) {
+    double uv[KB_UNROLL], wv[KB_UNROLL];
+#pragma unroll
+    for (int q = 0; q < KB_UNROLL; ++q) {
+      uv[q] = u[KB_IDX(q)];
+      wv[q] = w[KB_IDX(q)];
+    }
+#pragma unroll
+    for (int q = 0; q < KB_UNROLL; ++q) {
+      const double wn = kb_mul_sub(a, uv[q], wv[q]);
+      w[KB_IDX(q)] = wn;
+      acc = fma(wn, wn, acc);
+    }
+  } else {
+    for (int q = 0; q < KB_UNROLL; ++q) {
+      const int64_t i = KB_IDX(q);
+      if (i < total) {
+        const double wn = kb_mul_sub(a, u[i], w[i]);
+        w[i] = wn;
+        acc = fma(wn, wn, acc);
+      }
+    }
+  }
+  KB_TILE_LOOP_END
+  const bool last = kb_grid_colsum(acc, k, rd, out, sm);
+  if (last) {  // block-uniform
+    __syncthreads();  // out[] (== st.ww) written by threads t < k of this block
+    kb_gmres_scalar_body(k, iter, st);
+  }
+}
+
 // --------------------------------------------------------- MINRES update -
 // coefs = [R0 | R1 | R2 | y0 | h2] (k each)
 // z = (v - R0 W0 - R1 W1) / nz(R2);  W0 <- z;  yk += y0 z;  vnext = Av / nz(h2)

@@ -293,7 +293,7 @@ def _gmres(prob, M, Ml, Mr, inner, ortho, tol, atol, maxiter, callback):
             cyc = GmresCycleState(A=csr_chain[0].handle, n=n, k=k, Vbuf=ptr(Vbuf), vstride=n * k,
                                   w=ptr(Wbuf), dots=ptr(dots), ww=ptr(ww), hlast=ptr(hlast), st=st)
             check(lib.kb_gmres_cycle(ops.ws.handle, C.byref(cyc), kk, nb, cur_stream()))
-            ops.launches += sum(3 + nre * (i + 1) for i in range(kk, kk + nb))
+            ops.launches += sum(2 + nre * (i + 1) for i in range(kk, kk + nb))
         else:
             for i in range(kk, kk + nb):
                 ops.gate(stop_at, i)
