@@ -27,6 +27,25 @@ int kb_fail(int code, const char* fmt, ...) {
 
 static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
 
+// Launch with the programmatic-stream-serialization attribute (see kb_pdl_prologue): only for
+// kernels that start with kb_pdl_prologue().
+template <typename... KArgs, typename... Args>
+static inline void kb_launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // runtime tunables (kb_tune): stream-kernel configuration and grid sizing
 static int g_stream_cfg = 0;
 static int g_stream_ctas = 0;  // 0 = configuration default
@@ -40,6 +59,8 @@ static int g_cg_fuse = 1;      // kb_tune key 15: fused marching CG kernels in k
 static int g_part_dbg = 0;     // kb_tune key 21 (measurement only, results become wrong): bit 0 no
                                // peer pushes of r, bit 1 no all-reduce in the partitioned CG kernels
 static int g_cg_cfg[2] = {-1, -1};  // kb_tune keys 22 / 23: shape of the fused CG kernels KIND 1 / 2 (-1 auto)
+static int g_pdl = 1;           // kb_tune key 29: programmatic dependent launch of the short kernels
+                                // of a MINRES step and of the marching kernels (0 off)
 static int g_march_depth = 96;  // kb_tune key 24: deepest grid marched top to bottom by one CTA per column
 static int g_march_even = 0;   // kb_tune key 20: marching grids sized for equal items per CTA (measured
                                // no gain at 512^3 on one GPU: profiles/r2_march_even.txt)
@@ -212,6 +233,7 @@ int kb_tune(int key, int value) {
     case 26: g_merge_ctas = value; return KB_OK; // its CTAs per SM (0 = all that fit)
     case 27: g_merge_order = value; return KB_OK; // tile -> CTA order (kb_merge.cuh)
     case 28: g_small_n = value; return KB_OK;     // largest n of the persistent CG kernel (0 off)
+    case 29: g_pdl = value; return KB_OK;
     default: return kb_fail(KB_EINVAL, "kb_tune: unknown key %d", key);
   }
 }
@@ -844,8 +866,9 @@ static int kb_launch_march_t(kb_csr_s* A, kb_ws_s* ws, const KbMarch& g, const d
     const int rounds = (g.nitems + grid - 1) / grid;
     grid = (g.nitems + rounds - 1) / rounds;
   }
-  kern<<<grid, CT + 32, smem, st>>>((int)A->n_rows, (int)A->n_cols, g, A->masks, A->pat, A->cv, x, y,
-                                mode, z, coef, w, cg, g_stencil_l2pol, out, kb_red(ws));
+  kb_launch_pdl(g_pdl != 0, kern, dim3(grid), dim3(CT + 32), smem, st, (int)A->n_rows,
+                (int)A->n_cols, g, (const uint16_t*)A->masks, A->pat, A->cv, x, y, mode, z, coef, w, cg,
+                g_stencil_l2pol, out, kb_red(ws));
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -1718,8 +1741,8 @@ int kb_axpy_dot_minres(kb_ws_t ws, int64_t n, int k, const double* coef, const d
   KB_REQUIRE(stt->ww != nullptr && stt->alpha != nullptr, "null field in kb_minres_state");
   KB_REQUIRE(total > 0, "empty vectors");
   const int grid = kb_grid_for(ws, total, block, KB_UNROLL);
-  kb_axpy_dot_minres_kernel<<<grid, block, 0, st>>>(total, k, coef, u, w, (double*)stt->ww, iter,
-                                                    *stt, rd);
+  kb_launch_pdl(g_pdl != 0, kb_axpy_dot_minres_kernel, dim3(grid), dim3(block), 0, st, total, k,
+                coef, u, w, (double*)stt->ww, iter, *stt, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -1759,8 +1782,8 @@ int kb_minres_update(kb_ws_t ws, int64_t n, int k, const double* coefs, const do
     kb_minres_update_kernel<true><<<grid, block, 0, st>>>(total, k, coefs, v, W0, W1, Av, yk, vnext,
                                                           MAv, pnext, rd);
   else
-    kb_minres_update_kernel<false><<<grid, block, 0, st>>>(total, k, coefs, v, W0, W1, Av, yk,
-                                                           vnext, nullptr, nullptr, rd);
+    kb_launch_pdl(g_pdl != 0, kb_minres_update_kernel<false>, dim3(grid), dim3(block), 0, st, total,
+                  k, coefs, v, W0, W1, Av, yk, vnext, (const double*)nullptr, (double*)nullptr, rd);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

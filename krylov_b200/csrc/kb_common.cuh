@@ -180,6 +180,17 @@ static inline int kb_grid_for(const kb_ws_s* ws, int64_t total, int block, int p
 }
 
 // ----------------------------------------------------------- device side --
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-
+// serialization attribute may be scheduled while its predecessor in the stream drains;
+// griddepcontrol.wait blocks until that predecessor has completed and its memory is visible (a
+// no-op for a normal launch), launch_dependents lets the successor's CTAs take SM slots as soon as
+// every CTA of this grid has started.  Used at the very top of the short kernels of a solver step,
+// so that launch latency overlaps the predecessor's tail instead of following it.
+__device__ __forceinline__ void kb_pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ bool kb_gated(const KbRed& rd) {
   // uniform across the grid: only single-block scalar kernels of *earlier*
   // launches ever write the gate word

@@ -154,6 +154,7 @@ kb_stencil_march_kernel(int n_rows, int n_cols, KbMarch g, const uint16_t* __res
   static_assert(RPT >= 2 && RPT <= 4, "rows per thread");
   static_assert(CT % 32 == 0 && CT >= 128 && CT <= 256, "consumer threads");
   static_assert(NS >= 4, "ring: previous, current, next plane + one in flight");
+  kb_pdl_prologue();
   if (kb_gated(rd)) return;
   constexpr int TR = CT * RPT;
   constexpr int NR = KIND == 1 ? 2 : 0;  // staging windows of r (KIND 1)

@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(KB_BLOCK)
 kb_axpy_dot_minres_kernel(int64_t total, int k, const double* __restrict__ coef,
                           const double* __restrict__ u, double* __restrict__ w,
                           double* __restrict__ out, int iter, kb_minres_state st, KbRed rd) {
+  kb_pdl_prologue();
   if (kb_gated(rd)) return;
   __shared__ double sm[KB_BLOCK];
   const double a = coef[threadIdx.x % k];
@@ -469,6 +470,7 @@ kb_minres_update_kernel(int64_t total, int k, const double* __restrict__ coefs,
                         const double* __restrict__ W1, const double* __restrict__ Av,
                         double* __restrict__ yk, double* __restrict__ vnext,
                         const double* __restrict__ MAv, double* __restrict__ pnext, KbRed rd) {
+  kb_pdl_prologue();
   if (kb_gated(rd)) return;
   const int c = threadIdx.x % k;
   const double R0 = coefs[c];
