@@ -828,10 +828,23 @@ static bool kb_march_geom(const kb_csr_s* A, int RPT, KbMarch* g, int CT = 256, 
       (slots > 0 ? (g->ncol <= slots && g->ncol * 100 >= slots * 85) : g->ncol >= 148))
     ch = g->nplanes;
   if (ch > g->nplanes) ch = g->nplanes;
-  // small planes (128^3: 16 column tiles): fewer work items than CTA slots would leave SMs idle --
-  // shorter marches instead (C2 MINRES 128^3: 66 -> 63 us per step with 4 planes per item)
-  if (g_march_ch == 0 && ch < g->nplanes)
-    while (ch > 2 && (long long)g->ncol * ((g->nplanes + ch - 1) / ch) < 296) ch /= 2;
+  // Grids below 512 planes: the work items (ncol x ceil(nplanes / ch)) are dealt to `slots` CTAs in
+  // rounds, and a last round that fills a fraction of the machine costs a whole march -- pick the
+  // ch that minimises rounds x (ch + 2 planes per march).  256^3: 32 planes per item = 512 items =
+  // 2 rounds on 444 slots, 83.9 us; 8 planes = 2048 items = 5 rounds, 67.2 us; 128^3: 4 planes,
+  // 14.0 instead of 24.9 us (profiles/r2_march_ch.txt).  512^3 keeps 32 (tuned in round 1).
+  if (g_march_ch == 0 && ch < g->nplanes && g->nplanes < 512) {
+    const long long sl = slots > 0 ? slots : 444;
+    long long best = -1;
+    for (int c = 2; c <= 64 && c <= g->nplanes; c *= 2) {
+      const long long items = (long long)g->ncol * ((g->nplanes + c - 1) / c);
+      const long long cost = ((items + sl - 1) / sl) * (c + 2);
+      if (best < 0 || cost <= best) {  // ties: the longer march (fewer redundant planes)
+        best = cost;
+        ch = c;
+      }
+    }
+  }
   g->ch = ch;
   g->nitems = g->ncol * ((g->nplanes + ch - 1) / ch);
   return true;
