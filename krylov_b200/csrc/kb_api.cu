@@ -832,9 +832,12 @@ static bool kb_march_geom(const kb_csr_s* A, int RPT, KbMarch* g, int CT = 256, 
   // rounds, and a last round that fills a fraction of the machine costs a whole march -- pick the
   // ch that minimises rounds x (ch + 2 planes per march).  256^3: 32 planes per item = 512 items =
   // 2 rounds on 444 slots, 83.9 us; 8 planes = 2048 items = 5 rounds, 67.2 us; 128^3: 4 planes,
-  // 14.0 instead of 24.9 us (profiles/r2_march_ch.txt).  512^3 keeps 32 (tuned in round 1).
-  if (g_march_ch == 0 && ch < g->nplanes && g->nplanes < 512) {
-    const long long sl = slots > 0 ? slots : 444;
+  // 14.0 instead of 24.9 us (profiles/r2_march_ch.txt).  Only where the default gives fewer than four
+  // rounds: with many rounds the quantisation is small and the tuned 32 / 16 stay (2-GPU slabs of
+  // 512^3: 1263 it/s with 32 planes per item, 1237 with the model's 64).
+  const long long sl = slots > 0 ? slots : 444;
+  if (g_march_ch == 0 && ch < g->nplanes && g->nplanes < 512 &&
+      (long long)g->ncol * ((g->nplanes + ch - 1) / ch) < 4 * sl) {  // fewer than 4 rounds
     long long best = -1;
     for (int c = 2; c <= 64 && c <= g->nplanes; c *= 2) {
       const long long items = (long long)g->ncol * ((g->nplanes + c - 1) / c);
