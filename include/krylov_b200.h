@@ -258,7 +258,8 @@ int kb_cg_run_timed(kb_ws_t ws, const kb_cg_state* s, int i0, int n_iters, int x
 
 /* --- per-column scalar arithmetic on device slots ---------------------- */
 /* out[c] = A op B with A = a ? a[c] : sa, B = b ? b[c] : sb, c < k.  op: 0 A+B, 1 A-B, 2 A*B,
- * 3 A/B, 4 sqrt(A), 5 |A|, 6 -A, 7 (A != 0 ? A : B), 8 A.  One IEEE operation per launch: the
+ * 3 A/B, 4 sqrt(A), 5 |A|, 6 -A, 7 (A != 0 ? A : B), 8 A, 9 A / (B != 0 ? B : sb) (the reference's
+ * `x / np.where(y != 0, y, 1)` in one launch; B a device array).  One IEEE operation per launch: the
  * scalar recurrences of the short-recurrence solvers (bicgstab.py:100-133, qmr.py:101-146,
  * symmlq.py:108-150 ...) stay on the device with the host's bits and without a read-back per
  * inner product. */

@@ -15,7 +15,7 @@ import torch
 from .device import Ops
 
 
-_ADD, _SUB, _MUL, _DIV, _SQRT, _ABS, _NEG, _NZ, _COPY = range(9)
+_ADD, _SUB, _MUL, _DIV, _SQRT, _ABS, _NEG, _NZ, _COPY, _DIV_NZ = range(10)
 
 
 class DevScalar:
@@ -47,6 +47,12 @@ class DevScalar:
         return self.alg.coef(a), 0.0
 
     def _op(self, code, a, b=0.0):
+        if code == _DIV and isinstance(b, _LazyNz) and b._t is None:
+            # x / nz(y): one launch (the where() never materialises)
+            ta, sa = self._operand(a)
+            out = torch.empty(self.alg.prob.k, dtype=torch.float64, device=self.alg.prob.device)
+            self.alg.ops.scalar_op(_DIV_NZ, ta, b.src.t, sa, b.fill, out)
+            return DevScalar(self.alg, out)
         ta, sa = self._operand(a)
         tb, sb = self._operand(b)
         out = torch.empty(self.alg.prob.k, dtype=torch.float64, device=self.alg.prob.device)
@@ -70,7 +76,7 @@ class DevScalar:
         raise TypeError("DevScalar supports ** 2 only")
 
     def sqrt(self): return self._op(_SQRT, self)
-    def nz(self, fill=1.0): return self._op(_NZ, self, fill)
+    def nz(self, fill=1.0): return _LazyNz(self, float(fill))
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         if method != "__call__" or kwargs:
@@ -87,6 +93,28 @@ class DevScalar:
 
     def __array__(self, *a, **kw):
         raise TypeError("DevScalar stays on the device: call to_host() where the host needs it")
+
+
+class _LazyNz(DevScalar):
+    """``nz(d)`` = ``where(d != 0, d, fill)``: almost always the denominator of the next
+    statement, so it is evaluated only if something other than a division asks for its value."""
+
+    __slots__ = ("src", "fill", "_t")
+
+    def __init__(self, src, fill):
+        self.alg, self.src, self.fill, self._t = src.alg, src, fill, None
+
+    @property
+    def t(self):
+        if self._t is None:
+            out = torch.empty(self.alg.prob.k, dtype=torch.float64, device=self.alg.prob.device)
+            self.alg.ops.scalar_op(_NZ, self.src.t, None, 0.0, self.fill, out)
+            self._t = out
+        return self._t
+
+    @t.setter
+    def t(self, v):
+        self._t = v
 
 
 def to_host(v):

@@ -27,6 +27,8 @@ __global__ void kb_scalar_op_kernel(int k, int op, const double* __restrict__ a,
     case 5: r = fabs(A); break;
     case 6: r = -A; break;
     case 7: r = A != 0.0 ? A : B; break;  // nz(A) with B as the replacement
+    case 9: r = __ddiv_rn(A, B != 0.0 ? B : (b != nullptr ? sb : 1.0)); break;  // A / nz(B): the
+                                                                           // fill travels in sb
     default: r = A; break;
   }
   out[c] = r;
@@ -65,7 +67,8 @@ int kb_scalar_op(kb_ws_t ws, int k, int op, const double* a, const double* b, do
                  double* out, void* stream) {
   KB_REQUIRE(ws != nullptr && out != nullptr, "null argument");
   KB_REQUIRE(k >= 1 && k <= KB_MAX_K, "k out of range");
-  KB_REQUIRE(op >= 0 && op <= 8, "unknown operation");
+  KB_REQUIRE(op >= 0 && op <= 9, "unknown operation");
+  KB_REQUIRE(op != 9 || b != nullptr, "op 9 (A / nz(B)) needs B as a device array");
   kb_scalar_op_kernel<<<(k + 127) / 128, 128, 0, (cudaStream_t)stream>>>(k, op, a, b, sa, sb, out,
                                                                          kb_red(ws));
   KB_LAUNCH_CHECK();
