@@ -128,9 +128,57 @@ class Comm:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def allgather_object(self, obj):
+        """Every rank's object.  ``bytes`` of at most 256 bytes (IPC handles) on an NCCL group
+        travel as ONE fixed-size device all-gather instead of torch's pickled object collective
+        (two collectives + host staging: milliseconds each at 8 ranks, and a row-partitioned
+        solve set-up makes several)."""
+        if (isinstance(obj, bytes) and len(obj) <= 256 and torch.cuda.is_available()
+                and dist.get_backend(self.group) == "nccl"):
+            buf = torch.zeros(260, dtype=torch.uint8)
+            buf[0] = len(obj) & 0xFF
+            buf[1] = len(obj) >> 8
+            if obj:
+                buf[4:4 + len(obj)] = torch.frombuffer(bytearray(obj), dtype=torch.uint8)
+            mine = buf.cuda()
+            allb = torch.empty(260 * self.size, dtype=torch.uint8, device=mine.device)
+            dist.all_gather_into_tensor(allb, mine, group=self.group)
+            allb = allb.cpu().reshape(self.size, 260)
+            return [bytes(allb[p, 4:4 + int(allb[p, 0]) + 256 * int(allb[p, 1])].tolist())
+                    for p in range(self.size)]
         out = [None] * self.size
         dist.all_gather_object(out, obj, group=self.group)
         return out
+
+    def exchange_halo_ids(self, halo_globals, recv_counts):
+        """halo_globals: the global column ids this rank needs, sorted (so grouped by owner);
+        recv_counts[p]: how many of them rank p owns.  Returns (ids the other ranks need from this
+        rank, concatenated by requesting rank; their counts; the full count matrix
+        all_recv[p][q] = what p gets from q).  NCCL: one all-gather of the counts and one
+        all-to-all of exactly the ids each owner has to see; otherwise object collectives."""
+        size, rank = self.size, self.rank
+        if (torch.cuda.is_available() and halo_globals.is_cuda
+                and dist.get_backend(self.group) == "nccl"):
+            dev = halo_globals.device
+            mine = torch.as_tensor(np.asarray(recv_counts, dtype=np.int64)).to(dev)
+            allc = torch.empty(size * size, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allc, mine, group=self.group)
+            all_recv = allc.cpu().numpy().reshape(size, size)
+            send_counts = all_recv[:, rank].copy()
+            out = torch.empty(int(send_counts.sum()), dtype=torch.int64, device=dev)
+            dist.all_to_all_single(out, halo_globals.to(torch.int64).contiguous(),
+                                   output_split_sizes=[int(c) for c in send_counts],
+                                   input_split_sizes=[int(c) for c in recv_counts],
+                                   group=self.group)
+            return out, send_counts, all_recv
+        hg = halo_globals.cpu().numpy()
+        bounds = np.concatenate([[0], np.cumsum(recv_counts)])
+        wanted = [hg[bounds[p]:bounds[p + 1]] for p in range(size)]  # global ids I need from p
+        everyone = self.allgather_object(wanted)                     # everyone[q][p]: q needs from p
+        lists = [np.asarray(everyone[q][rank], dtype=np.int64) for q in range(size)]
+        send_counts = np.array([len(x) for x in lists], dtype=np.int64)
+        cat = np.concatenate(lists) if send_counts.sum() else np.zeros(0, np.int64)
+        all_recv = np.asarray(self.allgather_object([int(c) for c in recv_counts]), dtype=np.int64)
+        return torch.from_numpy(cat).to(halo_globals.device), send_counts, all_recv
 
 
 class HaloPlan:
@@ -180,18 +228,18 @@ class HaloPlan:
         owner = np.searchsorted(self.offsets, hg, side="right") - 1
         self.recv_counts = np.bincount(owner, minlength=comm.size).astype(np.int64)
         assert self.recv_counts[rank] == 0
-        wanted = [hg[owner == p] for p in range(comm.size)]  # global ids I need from p
-        everyone = comm.allgather_object(wanted)              # everyone[q][p]: q needs from p
-        send_lists = [np.asarray(everyone[q][rank], dtype=np.int64) - r0 for q in range(comm.size)]
-        self.send_counts = np.array([len(s) for s in send_lists], dtype=np.int64)
-        cat = np.concatenate(send_lists) if sum(self.send_counts) else np.zeros(0, np.int64)
-        assert cat.size == 0 or (cat.min() >= 0 and cat.max() < n_loc)
-        self.send_idx = torch.from_numpy(cat.astype(np.int32)).to(dev)
-        self.n_send = int(cat.size)
+        # the ids every other rank needs from me (grouped by requesting rank), and the count
+        # matrix all_recv[p][q] = what p gets from q
+        ids, self.send_counts, all_recv = comm.exchange_halo_ids(self.halo_globals,
+                                                                 self.recv_counts)
+        self.n_send = int(ids.numel())
+        self.send_idx = (ids - r0).to(torch.int32).to(dev)
+        if self.n_send:
+            lo, hi = int(self.send_idx.min()), int(self.send_idx.max())
+            assert lo >= 0 and hi < n_loc
         self.peers = [p for p in range(comm.size)
                       if p != rank and (self.send_counts[p] or self.recv_counts[p])]
         # ---- peer-memory push tables: where my rows land in each destination's data area
-        all_recv = comm.allgather_object(self.recv_counts.tolist())  # all_recv[p][q]: p gets from q
         segs = []
         so = np.concatenate([[0], np.cumsum(self.send_counts)])
         for p in range(comm.size):
