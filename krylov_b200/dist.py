@@ -426,8 +426,13 @@ class DistCsrMatrix:
                 and bool(torch.all(rows[hi] >= n - P)) \
                 and bool(torch.all(plan.h_val[lo] == c_lo)) and bool(torch.all(plan.h_val[hi] == c_hi))
             rows_lo, rows_hi = rows[lo], rows[hi]
-        votes = comm.allgather_object((bool(ok), P, coeffs))
-        if not all(v[0] and v[1] == votes[0][1] and v[2] == votes[0][2] for v in votes):
+        # every rank must qualify with the same plane stride and coefficients (fixed-size payload:
+        # the fast path of allgather_object)
+        import struct
+
+        mine = struct.pack("<?q7d", bool(ok), int(P), *(list(coeffs) + [0.0] * (7 - len(coeffs))))
+        votes = [struct.unpack("<?q7d", v) for v in comm.allgather_object(mine)]
+        if not all(v[0] and v[1:] == votes[0][1:] for v in votes):
             return None
         n_ext = n + 2 * P
         with torch.cuda.device(dev):
